@@ -1,0 +1,1020 @@
+// engine.cpp -- the extern "C" layer of include/gaselect_b200.h: host-side state, the one-off
+// device setup (K0) and the per-generation launch sequence (K1 -> K2, or K3 for the LM evaluator).
+//
+// What the reference does per chromosome inside Evaluator::evaluate (src/PLSEvaluator.cpp:71-91,
+// src/BICEvaluator.cpp:54-91, src/LMEvaluator.cpp:27-67) is done here for a whole population per
+// call.  There is no CPU fallback: without a CUDA device every evaluate call fails (GSB_ERR_CUDA).
+#include "../../include/gaselect_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "host_rng.hpp"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+namespace {
+
+std::string g_createError;
+
+int roundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+struct CudaFailure {
+	cudaError_t code;
+	const char* what;
+	const char* file;
+	int line;
+};
+
+#define GSB_CUDA(expr)                                                     \
+	do {                                                                   \
+		cudaError_t err__ = (expr);                                        \
+		if (err__ != cudaSuccess) throw CudaFailure{err__, #expr, __FILE__, __LINE__}; \
+	} while (0)
+
+template <class T>
+struct DeviceArray {
+	T* ptr = nullptr;
+	size_t capacity = 0; // elements
+	void reserve(size_t count) {
+		if (count <= capacity) return;
+		release();
+		const size_t want = std::max<size_t>(count, 16);
+		GSB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T)));
+		capacity = want;
+	}
+	void release() {
+		if (ptr) cudaFree(ptr);
+		ptr = nullptr;
+		capacity = 0;
+	}
+	DeviceArray() {}
+	~DeviceArray() { release(); }
+	DeviceArray(const DeviceArray&) = delete;
+	DeviceArray& operator=(const DeviceArray&) = delete;
+	void upload(const T* host, size_t count, cudaStream_t s) {
+		reserve(count);
+		if (count) GSB_CUDA(cudaMemcpyAsync(ptr, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+	}
+	void upload(const std::vector<T>& host, cudaStream_t s) { upload(host.data(), host.size(), s); }
+};
+
+template <class T>
+struct PinnedArray {
+	T* ptr = nullptr;
+	size_t capacity = 0;
+	void reserve(size_t count) {
+		if (count <= capacity) return;
+		release();
+		const size_t want = std::max<size_t>(count + count / 2, 64);
+		GSB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ptr), want * sizeof(T), cudaHostAllocDefault));
+		capacity = want;
+	}
+	void release() {
+		if (ptr) cudaFreeHost(ptr);
+		ptr = nullptr;
+		capacity = 0;
+	}
+	PinnedArray() {}
+	~PinnedArray() { release(); }
+	PinnedArray(const PinnedArray&) = delete;
+	PinnedArray& operator=(const PinnedArray&) = delete;
+};
+
+struct Bucket {
+	int begin;
+	int count;
+	int kMax;
+};
+
+// subset-size classes: one K1 launch per class, shared memory sized for the class maximum
+int bucketCeil(int k) {
+	if (k <= 64) return roundUp(k, 8);
+	if (k <= 128) return roundUp(k, 16);
+	return roundUp(k, 32);
+}
+
+} // namespace
+
+struct gsb_engine {
+	gsb_config cfg;
+	std::string error;
+
+	// host copies (PLS::PLS copies X and Y, src/PLS.h:25,95-96)
+	int n = 0, p = 0;
+	std::vector<double> X, y;
+	std::vector<double> xMean; // global column means (the device works on globally centred data)
+	double yMean = 0.0;
+	double r2denom = 0.0;
+	bool haveData = false, haveSegmentation = false, prepared = false, deviceReady = false, zReady = false;
+
+	std::vector<gsb::RowSet> segmentation;
+	gsb::CvShape shape;
+	gsb::FitPlan plan;
+
+	// device
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	int smCount = 0, smemLimit = 0;
+	int ldz = 0;
+	DeviceArray<double> zpool, gram, s0, xm;
+	DeviceArray<gsb::FitDesc> fits;
+	DeviceArray<gsb::TaskDesc> tasks;
+	DeviceArray<gsb::BlockDesc> blocks;
+	DeviceArray<int> outerRows;
+	double ymAllRows = 0.0;
+
+	// resident population
+	int npop = 0, kMaxPop = 0, tableA = 1;
+	bool populationReady = false, resultsReady = false;
+	std::vector<Bucket> buckets;
+	DeviceArray<uint32_t> dIdx, dOffsets;
+	DeviceArray<int> dBucket, dStatus;
+	DeviceArray<double> dMse, dOstat, dFitness;
+	PinnedArray<uint32_t> hIdx, hOffsets;
+	PinnedArray<int> hBucket, hStatus;
+	PinnedArray<double> hFitness;
+	double lastH2dMs = 0.0;
+
+	gsb_info info;
+	gsb_timing timing;
+
+	gsb_engine() {
+		std::memset(&cfg, 0, sizeof(cfg));
+		std::memset(&info, 0, sizeof(info));
+		std::memset(&timing, 0, sizeof(timing));
+	}
+};
+
+namespace {
+
+int fail(gsb_engine* e, int code, const std::string& msg) {
+	if (e) e->error = msg; else g_createError = msg;
+	return code;
+}
+
+int failCuda(gsb_engine* e, const CudaFailure& f) {
+	char buf[512];
+	std::snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", static_cast<int>(f.code),
+	              cudaGetErrorString(f.code), f.what, f.file, f.line);
+	cudaGetLastError(); // clear the sticky-less error state
+	return fail(e, GSB_ERR_CUDA, buf);
+}
+
+void releaseDevice(gsb_engine* e) {
+	e->zpool.release(); e->gram.release(); e->s0.release(); e->xm.release();
+	e->fits.release(); e->tasks.release(); e->blocks.release(); e->outerRows.release();
+	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
+	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
+	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
+	for (int i = 0; i < 6; ++i) { if (e->ev[i]) cudaEventDestroy(e->ev[i]); e->ev[i] = nullptr; }
+	if (e->stream) cudaStreamDestroy(e->stream);
+	e->stream = nullptr;
+	e->deviceReady = e->zReady = e->prepared = e->populationReady = e->resultsReady = false;
+}
+
+// Selects the device and creates the stream; fails loudly when there is no usable GPU.
+void ensureDevice(gsb_engine* e) {
+	if (e->deviceReady) {
+		GSB_CUDA(cudaSetDevice(e->cfg.device));
+		return;
+	}
+	int count = 0;
+	GSB_CUDA(cudaGetDeviceCount(&count));
+	if (count <= 0 || e->cfg.device >= count) throw CudaFailure{cudaErrorNoDevice, "device ordinal not present", __FILE__, __LINE__};
+	GSB_CUDA(cudaSetDevice(e->cfg.device));
+	cudaDeviceProp prop;
+	GSB_CUDA(cudaGetDeviceProperties(&prop, e->cfg.device));
+	e->smCount = prop.multiProcessorCount;
+	e->smemLimit = static_cast<int>(prop.sharedMemPerBlockOptin);
+	GSB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 6; ++i) GSB_CUDA(cudaEventCreate(&e->ev[i]));
+	e->deviceReady = true;
+}
+
+// Z = [X - colmeans | y - mean | 1], rows padded with zeros to a multiple of 4, column-major.
+void uploadZ(gsb_engine* e, size_t poolDoubles) {
+	const int n = e->n, p = e->p, P2 = p + 2;
+	e->ldz = roundUp(n, 4);
+	const size_t zDoubles = static_cast<size_t>(e->ldz) * P2;
+	std::vector<double> Z(zDoubles, 0.0);
+	e->xMean.assign(static_cast<size_t>(p), 0.0);
+	for (int c = 0; c < p; ++c) {
+		const double* col = e->X.data() + static_cast<size_t>(c) * n;
+		long double s = 0.0L;
+		for (int r = 0; r < n; ++r) s += col[r];
+		const double m = static_cast<double>(s / n);
+		e->xMean[static_cast<size_t>(c)] = m;
+		double* dst = Z.data() + static_cast<size_t>(c) * e->ldz;
+		for (int r = 0; r < n; ++r) dst[r] = col[r] - m;
+	}
+	long double sy = 0.0L;
+	for (int r = 0; r < n; ++r) sy += e->y[static_cast<size_t>(r)];
+	e->yMean = static_cast<double>(sy / n);
+	double* yc = Z.data() + static_cast<size_t>(p) * e->ldz;
+	double* one = Z.data() + static_cast<size_t>(p + 1) * e->ldz;
+	double ss = 0.0;
+	for (int r = 0; r < n; ++r) {
+		yc[r] = e->y[static_cast<size_t>(r)] - e->yMean;
+		one[r] = 1.0;
+		ss += yc[r] * yc[r];
+	}
+	e->r2denom = ss; // n * var_pop(y) (src/BICEvaluator.cpp:37) == sum (y - mean)^2 (src/LMEvaluator.cpp:24)
+	e->zpool.reserve(std::max(poolDoubles, zDoubles));
+	GSB_CUDA(cudaMemcpyAsync(e->zpool.ptr, Z.data(), zDoubles * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+	GSB_CUDA(cudaStreamSynchronize(e->stream));
+	e->zReady = true;
+}
+
+// K0: block copies, DMMA SYRK of the full data and of every excluded block, per-fit combination.
+void prepareDevice(gsb_engine* e) {
+	ensureDevice(e);
+	const int n = e->n, p = e->p, P2 = p + 2;
+	const gsb::FitPlan& plan = e->plan;
+	const int nfits = static_cast<int>(plan.fits.size());
+	const int nblocks = static_cast<int>(plan.blocks.size());
+	const int ldz = roundUp(n, 4);
+
+	// ---- held-out row blocks, each a contiguous column-major copy (coalesced prediction reads)
+	std::vector<gsb::BlockDesc> bdesc(static_cast<size_t>(nblocks));
+	std::vector<uint32_t> blockRows;
+	std::vector<size_t> blockRowOff(static_cast<size_t>(nblocks), 0);
+	size_t pool = static_cast<size_t>(ldz) * P2;
+	for (int b = 0; b < nblocks; ++b) {
+		const gsb::PlanBlock& pb = plan.blocks[static_cast<size_t>(b)];
+		gsb::BlockDesc& d = bdesc[static_cast<size_t>(b)];
+		d.nrows = static_cast<int>(pb.rows.size());
+		if (pb.allRows) {
+			d.zOff = 0;
+			d.ld = ldz;
+		} else {
+			d.ld = roundUp(d.nrows, 4);
+			d.zOff = pool;
+			pool += static_cast<size_t>(d.ld) * P2;
+			blockRowOff[static_cast<size_t>(b)] = blockRows.size();
+			blockRows.insert(blockRows.end(), pb.rows.begin(), pb.rows.end());
+		}
+	}
+	e->zReady = false;
+	uploadZ(e, pool);
+	DeviceArray<uint32_t> dRows;
+	dRows.upload(blockRows, e->stream);
+	for (int b = 0; b < nblocks; ++b) {
+		if (plan.blocks[static_cast<size_t>(b)].allRows) continue;
+		const gsb::BlockDesc& d = bdesc[static_cast<size_t>(b)];
+		gsb::launchBlockGather(e->zpool.ptr, ldz, P2, nullptr, dRows.ptr + blockRowOff[static_cast<size_t>(b)], d.nrows,
+		                       e->zpool.ptr + d.zOff, d.ld, e->stream);
+	}
+	GSB_CUDA(cudaGetLastError());
+
+	// ---- SYRK units: the full data, then every block some fit excludes
+	std::vector<int> unitOfBlock(static_cast<size_t>(nblocks), -1);
+	std::vector<int> unitBlocks; // block id per unit >= 1
+	for (int f = 0; f < nfits; ++f) {
+		for (size_t x = 0; x < plan.fits[static_cast<size_t>(f)].exclBlocks.size(); ++x) {
+			const int b = plan.fits[static_cast<size_t>(f)].exclBlocks[x];
+			if (unitOfBlock[static_cast<size_t>(b)] < 0) {
+				unitBlocks.push_back(b);
+				unitOfBlock[static_cast<size_t>(b)] = static_cast<int>(unitBlocks.size());
+			}
+		}
+	}
+	const int units = 1 + static_cast<int>(unitBlocks.size());
+	const int ldm = roundUp(P2, 4);
+	const size_t mDoubles = static_cast<size_t>(P2) * ldm;
+	const size_t triP = static_cast<size_t>(gsb::tri(static_cast<unsigned long long>(p)));
+	const size_t gramDoubles = triP * static_cast<size_t>(nfits);
+
+	size_t freeB = 0, totalB = 0;
+	GSB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+	const double need = 8.0 * (static_cast<double>(mDoubles) * units + static_cast<double>(gramDoubles) +
+	                           2.0 * static_cast<double>(nfits) * p);
+	if (need > 0.92 * static_cast<double>(freeB)) {
+		char buf[256];
+		std::snprintf(buf, sizeof(buf), "Gram tables need %.1f GB of device memory, %.1f GB are free", need / 1e9,
+		              static_cast<double>(freeB) / 1e9);
+		throw std::string(buf);
+	}
+
+	DeviceArray<double> mPool;
+	mPool.reserve(mDoubles * static_cast<size_t>(units));
+	GSB_CUDA(cudaMemsetAsync(mPool.ptr, 0, mDoubles * static_cast<size_t>(units) * sizeof(double), e->stream));
+	std::vector<const double*> unitPtrs(static_cast<size_t>(units));
+	std::vector<double*> outPtrs(static_cast<size_t>(units));
+	std::vector<int> unitLd(static_cast<size_t>(units)), unitRows(static_cast<size_t>(units));
+	std::vector<const double*> mOfBlock(static_cast<size_t>(std::max(nblocks, 1)), nullptr);
+	double flops = 0.0;
+	for (int u = 0; u < units; ++u) {
+		outPtrs[static_cast<size_t>(u)] = mPool.ptr + mDoubles * static_cast<size_t>(u);
+		if (u == 0) {
+			unitPtrs[0] = e->zpool.ptr;
+			unitLd[0] = ldz;
+			unitRows[0] = ldz;
+			flops += static_cast<double>(n) * P2 * (P2 + 1.0);
+		} else {
+			const int b = unitBlocks[static_cast<size_t>(u - 1)];
+			const gsb::BlockDesc& d = bdesc[static_cast<size_t>(b)];
+			unitPtrs[static_cast<size_t>(u)] = e->zpool.ptr + d.zOff;
+			unitLd[static_cast<size_t>(u)] = d.ld;
+			unitRows[static_cast<size_t>(u)] = d.ld;
+			mOfBlock[static_cast<size_t>(b)] = outPtrs[static_cast<size_t>(u)];
+			flops += static_cast<double>(d.nrows) * P2 * (P2 + 1.0);
+		}
+	}
+	DeviceArray<const double*> dUnitPtrs, dMOfBlock;
+	DeviceArray<double*> dOutPtrs;
+	DeviceArray<int> dUnitLd, dUnitRows, dExclIndex, dExclCount, dFitIds, dFitNtr;
+	DeviceArray<unsigned long long> dGramOffs;
+	DeviceArray<double> dYm;
+	dUnitPtrs.upload(unitPtrs, e->stream);
+	dOutPtrs.upload(outPtrs, e->stream);
+	dUnitLd.upload(unitLd, e->stream);
+	dUnitRows.upload(unitRows, e->stream);
+	dMOfBlock.upload(mOfBlock, e->stream);
+
+	GSB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+	// grid.y is limited to 65535 units per launch
+	for (int u0 = 0; u0 < units; u0 += 32768) {
+		const int cnt = std::min(32768, units - u0);
+		gsb::launchGramSyrk(dUnitPtrs.ptr + u0, dUnitLd.ptr + u0, dUnitRows.ptr + u0, dOutPtrs.ptr + u0, cnt, P2, ldm, e->stream);
+	}
+	GSB_CUDA(cudaGetLastError());
+	GSB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+
+	// ---- per training set: centred Gram (packed), s0, xm, ym
+	std::vector<int> exclIndex(static_cast<size_t>(nfits) * 2, 0), exclCount(static_cast<size_t>(nfits), 0);
+	std::vector<int> fitIds(static_cast<size_t>(nfits)), fitNtr(static_cast<size_t>(nfits));
+	std::vector<unsigned long long> gramOffs(static_cast<size_t>(nfits));
+	for (int f = 0; f < nfits; ++f) {
+		const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
+		exclCount[static_cast<size_t>(f)] = static_cast<int>(pf.exclBlocks.size());
+		for (size_t x = 0; x < pf.exclBlocks.size(); ++x) exclIndex[static_cast<size_t>(f) * 2 + x] = pf.exclBlocks[x];
+		fitIds[static_cast<size_t>(f)] = f;
+		fitNtr[static_cast<size_t>(f)] = static_cast<int>(pf.rows.size());
+		gramOffs[static_cast<size_t>(f)] = static_cast<unsigned long long>(triP) * static_cast<unsigned long long>(f);
+	}
+	dExclIndex.upload(exclIndex, e->stream);
+	dExclCount.upload(exclCount, e->stream);
+	dFitIds.upload(fitIds, e->stream);
+	dFitNtr.upload(fitNtr, e->stream);
+	dGramOffs.upload(gramOffs, e->stream);
+	dYm.reserve(static_cast<size_t>(nfits));
+	e->gram.reserve(gramDoubles);
+	e->s0.reserve(static_cast<size_t>(nfits) * p);
+	e->xm.reserve(static_cast<size_t>(nfits) * p);
+	for (int f0 = 0; f0 < nfits; f0 += 32768) {
+		const int cnt = std::min(32768, nfits - f0);
+		gsb::launchGramCombine(mPool.ptr, dMOfBlock.ptr, dExclIndex.ptr + static_cast<size_t>(f0) * 2, dExclCount.ptr + f0,
+		                       dFitIds.ptr + f0, dFitNtr.ptr + f0, cnt, p, ldm, e->gram.ptr, dGramOffs.ptr, e->s0.ptr,
+		                       e->xm.ptr, dYm.ptr, e->stream);
+	}
+	GSB_CUDA(cudaGetLastError());
+	GSB_CUDA(cudaEventRecord(e->ev[2], e->stream));
+	std::vector<double> ym(static_cast<size_t>(nfits));
+	GSB_CUDA(cudaMemcpyAsync(ym.data(), dYm.ptr, static_cast<size_t>(nfits) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+	GSB_CUDA(cudaStreamSynchronize(e->stream));
+	float msSyrk = 0.f, msAll = 0.f;
+	GSB_CUDA(cudaEventElapsedTime(&msSyrk, e->ev[0], e->ev[1]));
+	GSB_CUDA(cudaEventElapsedTime(&msAll, e->ev[0], e->ev[2]));
+
+	// ---- descriptors
+	std::vector<gsb::FitDesc> fdesc(static_cast<size_t>(nfits));
+	for (int f = 0; f < nfits; ++f) {
+		const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
+		gsb::FitDesc& d = fdesc[static_cast<size_t>(f)];
+		d.gramOff = gramOffs[static_cast<size_t>(f)];
+		d.ym = ym[static_cast<size_t>(f)];
+		d.ntr = static_cast<int>(pf.rows.size());
+		d.taskBegin = pf.taskBegin;
+		d.taskCount = pf.taskCount;
+		d.pad = 0;
+	}
+	std::vector<gsb::TaskDesc> tdesc(plan.tasks.size());
+	for (size_t t = 0; t < plan.tasks.size(); ++t) {
+		tdesc[t].block = plan.tasks[t].block;
+		tdesc[t].kind = plan.tasks[t].kind;
+		tdesc[t].dest = plan.tasks[t].dest;
+		tdesc[t].pad = 0;
+	}
+	e->fits.upload(fdesc, e->stream);
+	e->tasks.upload(tdesc, e->stream);
+	e->blocks.upload(bdesc, e->stream);
+	e->outerRows.upload(plan.outerRows, e->stream);
+	e->ymAllRows = nfits > 0 ? ym[0] : 0.0;
+	GSB_CUDA(cudaStreamSynchronize(e->stream));
+
+	mPool.release(); // give the SYRK scratch back before the population tables are allocated
+
+	gsb_info& inf = e->info;
+	inf.n = n; inf.p = p;
+	inf.max_ncomp = e->shape.maxNComp;
+	inf.inner_segments = e->shape.inner;
+	inf.outer_segments = e->shape.outer;
+	inf.num_replications = e->shape.replications;
+	inf.segmentation_vectors = static_cast<int32_t>(e->segmentation.size());
+	inf.fits_per_evaluation = plan.fitsPerEvaluation;
+	inf.distinct_fits = nfits;
+	inf.distinct_blocks = nblocks;
+	inf.prediction_tasks = static_cast<int32_t>(plan.tasks.size());
+	inf.sm_count = e->smCount;
+	inf.gram_bytes = static_cast<int64_t>((gramDoubles + 2 * static_cast<size_t>(nfits) * p) * sizeof(double));
+	inf.block_bytes = static_cast<int64_t>((pool - static_cast<size_t>(ldz) * P2) * sizeof(double));
+	inf.sdfact_effective = e->shape.sdfact;
+	inf.setup_ms = msAll;
+	inf.gram_dmma_ms = msSyrk;
+	inf.gram_flops = flops;
+	e->prepared = true;
+	e->populationReady = e->resultsReady = false;
+}
+
+int prepareChecked(gsb_engine* e) {
+	if (!e->haveData) return fail(e, GSB_ERR_STATE, "gsb_set_data has not been called");
+	if (e->cfg.evaluator != GSB_EVAL_LM && !e->haveSegmentation) {
+		return fail(e, GSB_ERR_STATE, "no CV segmentation: call gsb_init_segmentation or gsb_set_segmentation");
+	}
+	try {
+		if (e->cfg.evaluator == GSB_EVAL_LM) {
+			gsb::buildAllRowsPlan(e->n, e->plan);
+			e->shape = gsb::CvShape();
+		} else {
+			const std::string msg = gsb::buildCvPlan(e->n, e->segmentation, e->shape, e->cfg.evaluator == GSB_EVAL_PLS_FIT, e->plan);
+			if (!msg.empty()) return fail(e, GSB_ERR_INVALID_ARGUMENT, msg);
+		}
+		prepareDevice(e);
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	} catch (const std::string& msg) {
+		return fail(e, GSB_ERR_MEMORY, msg);
+	} catch (const std::bad_alloc&) {
+		return fail(e, GSB_ERR_MEMORY, "host allocation failed");
+	}
+	return GSB_OK;
+}
+
+std::string deriveShape(gsb_engine* e, std::vector<gsb::RowSet>& seg, const uint32_t* seed624) {
+	const gsb_config& c = e->cfg;
+	if (c.evaluator == GSB_EVAL_PLS_CV) {
+		return gsb::buildPlsSegmentation(e->n, c.num_replications, c.max_ncomp, c.inner_segments, c.outer_segments,
+		                                 c.test_set_size, c.sdfact, seed624, seg, e->shape);
+	}
+	return gsb::buildFitSegmentation(e->n, c.max_ncomp, c.inner_segments, c.sdfact, seed624, seg, e->shape);
+}
+
+} // namespace
+
+extern "C" {
+
+int gsb_abi_version(void) { return GSB_ABI_VERSION; }
+
+int gsb_create(gsb_engine** out, const gsb_config* cfg) {
+	if (!out || !cfg) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "null argument");
+	*out = nullptr;
+	if (cfg->struct_size != static_cast<int32_t>(sizeof(gsb_config))) {
+		return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "gsb_config.struct_size does not match this library");
+	}
+	if (cfg->device < 0) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "negative device ordinal");
+	switch (cfg->evaluator) {
+	case GSB_EVAL_PLS_CV:
+		if (cfg->num_replications < 1) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "numReplications must be at least 1");
+		// src/PLSEvaluator.cpp:50-52 (rdCV overrides the test set size, :46-48)
+		if (cfg->outer_segments <= 1 && (cfg->test_set_size < 0.0 || cfg->test_set_size >= 1.0)) {
+			return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "The test set size must be within the interval (0, 1)");
+		}
+		if (cfg->inner_segments < 1) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "innerSegments must be positive");
+		if (cfg->max_ncomp < 0) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "maxNComp must not be negative");
+		break;
+	case GSB_EVAL_PLS_FIT:
+		if (cfg->inner_segments < 2) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "For CV at least 2 segments are needed");
+		if (cfg->statistic < GSB_STAT_BIC || cfg->statistic > GSB_STAT_R2) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "unknown statistic");
+		break;
+	case GSB_EVAL_LM:
+		if (cfg->statistic < GSB_STAT_BIC || cfg->statistic > GSB_STAT_R2) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "unknown statistic");
+		break;
+	default:
+		return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "unknown evaluator kind (the user-function evaluator is out of scope)");
+	}
+	gsb_engine* e = new (std::nothrow) gsb_engine();
+	if (!e) return fail(nullptr, GSB_ERR_MEMORY, "host allocation failed");
+	e->cfg = *cfg;
+	*out = e;
+	return GSB_OK;
+}
+
+void gsb_destroy(gsb_engine* e) {
+	if (!e) return;
+	if (e->deviceReady) cudaSetDevice(e->cfg.device);
+	releaseDevice(e);
+	delete e;
+}
+
+int gsb_last_error(const gsb_engine* e, char* buf, size_t buflen) {
+	if (!buf || buflen == 0) return GSB_ERR_INVALID_ARGUMENT;
+	const std::string& msg = e ? e->error : g_createError;
+	std::snprintf(buf, buflen, "%s", msg.c_str());
+	return GSB_OK;
+}
+
+int gsb_set_data(gsb_engine* e, const double* X_colmajor, const double* y, int32_t n, int32_t p) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!X_colmajor || !y || n < 4 || p < 1) return fail(e, GSB_ERR_INVALID_ARGUMENT, "X must be n x p with n >= 4, p >= 1");
+	if (n > 65535 || p > 65535) return fail(e, GSB_ERR_INVALID_ARGUMENT, "n and p are limited to 65535 (src/Control.h:67-68, src/OnlineStddev.h:62)");
+	try {
+		e->X.assign(X_colmajor, X_colmajor + static_cast<size_t>(n) * p);
+		e->y.assign(y, y + n);
+	} catch (const std::bad_alloc&) {
+		return fail(e, GSB_ERR_MEMORY, "host allocation failed");
+	}
+	e->n = n;
+	e->p = p;
+	e->haveData = true;
+	e->haveSegmentation = false;
+	e->prepared = e->zReady = e->populationReady = e->resultsReady = false;
+	return GSB_OK;
+}
+
+int gsb_seed_vector(uint32_t seed, uint32_t* out624) {
+	if (!out624) return GSB_ERR_INVALID_ARGUMENT;
+	gsb::Well19937a rng(seed);
+	for (int i = 0; i < GSB_SEED_WORDS; ++i) out624[i] = rng.next();
+	return GSB_OK;
+}
+
+int gsb_rng_stream(const uint32_t* seed624, int32_t n, uint32_t* out) {
+	if (!seed624 || !out || n < 0) return GSB_ERR_INVALID_ARGUMENT;
+	gsb::Well19937a rng(seed624);
+	for (int i = 0; i < n; ++i) out[i] = rng.next();
+	return GSB_OK;
+}
+
+int gsb_shuffle_all(const uint32_t* seed624, int32_t size, int32_t ncalls, uint32_t* out) {
+	if (!seed624 || !out || size < 1 || ncalls < 0) return GSB_ERR_INVALID_ARGUMENT;
+	gsb::Well19937a rng(seed624);
+	gsb::RowShuffler rows(static_cast<uint32_t>(size));
+	for (int c = 0; c < ncalls; ++c) {
+		const std::vector<uint32_t>& s = rows.shuffleAll(rng);
+		std::copy(s.begin(), s.end(), out + static_cast<size_t>(c) * size);
+	}
+	return GSB_OK;
+}
+
+int gsb_init_segmentation(gsb_engine* e, const uint32_t* seed624) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (e->cfg.evaluator == GSB_EVAL_LM) return GSB_OK;
+	if (!seed624) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null seed");
+	if (!e->haveData) return fail(e, GSB_ERR_STATE, "gsb_set_data has not been called");
+	const std::string msg = deriveShape(e, e->segmentation, seed624);
+	if (!msg.empty()) return fail(e, GSB_ERR_INVALID_ARGUMENT, msg);
+	e->haveSegmentation = true;
+	e->prepared = false;
+	return GSB_OK;
+}
+
+int gsb_set_segmentation(gsb_engine* e, const uint32_t* rows, const uint32_t* offsets, int32_t nvec) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (e->cfg.evaluator == GSB_EVAL_LM) return GSB_OK;
+	if (!rows || !offsets || nvec < 2) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null or empty segmentation");
+	if (!e->haveData) return fail(e, GSB_ERR_STATE, "gsb_set_data has not been called");
+	// segment lengths and the maxNComp clamp depend only on n and the configuration
+	std::vector<uint32_t> zeros(GSB_SEED_WORDS, 0u);
+	zeros[0] = 1u;
+	std::vector<gsb::RowSet> own;
+	const std::string msg = deriveShape(e, own, zeros.data());
+	if (!msg.empty()) return fail(e, GSB_ERR_INVALID_ARGUMENT, msg);
+	if (static_cast<size_t>(nvec) != own.size()) return fail(e, GSB_ERR_INVALID_ARGUMENT, "segmentation has the wrong number of index vectors for this evaluator");
+	std::vector<gsb::RowSet> seg(static_cast<size_t>(nvec));
+	for (int v = 0; v < nvec; ++v) {
+		if (offsets[v + 1] < offsets[v]) return fail(e, GSB_ERR_INVALID_ARGUMENT, "segmentation offsets must be non-decreasing");
+		seg[static_cast<size_t>(v)].assign(rows + offsets[v], rows + offsets[v + 1]);
+	}
+	e->segmentation.swap(seg);
+	e->haveSegmentation = true;
+	e->prepared = false;
+	return GSB_OK;
+}
+
+int gsb_get_segmentation(const gsb_engine* e, uint32_t* rows, uint32_t* offsets, int32_t* nvec, int64_t* total) {
+	if (!e || !nvec || !total) return GSB_ERR_INVALID_ARGUMENT;
+	int64_t tot = 0;
+	for (size_t v = 0; v < e->segmentation.size(); ++v) tot += static_cast<int64_t>(e->segmentation[v].size());
+	*nvec = static_cast<int32_t>(e->segmentation.size());
+	*total = tot;
+	if (!rows || !offsets) return GSB_OK;
+	uint32_t pos = 0;
+	for (size_t v = 0; v < e->segmentation.size(); ++v) {
+		offsets[v] = pos;
+		std::copy(e->segmentation[v].begin(), e->segmentation[v].end(), rows + pos);
+		pos += static_cast<uint32_t>(e->segmentation[v].size());
+	}
+	offsets[e->segmentation.size()] = pos;
+	return GSB_OK;
+}
+
+int gsb_prepare(gsb_engine* e) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (e->prepared) return GSB_OK;
+	return prepareChecked(e);
+}
+
+int gsb_get_info(const gsb_engine* e, gsb_info* info) {
+	if (!e || !info) return GSB_ERR_INVALID_ARGUMENT;
+	*info = e->info;
+	if (!e->prepared) { // host-side facts are available before the device setup
+		info->n = e->n;
+		info->p = e->p;
+		info->max_ncomp = e->shape.maxNComp;
+		info->inner_segments = e->shape.inner;
+		info->outer_segments = e->shape.outer;
+		info->num_replications = e->shape.replications;
+		info->segmentation_vectors = static_cast<int32_t>(e->segmentation.size());
+		info->sdfact_effective = e->shape.sdfact;
+	}
+	return GSB_OK;
+}
+
+int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!offsets || npop < 0 || (!idx && npop > 0 && offsets[npop] > 0)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null population");
+	if (!e->prepared) {
+		const int rc = prepareChecked(e);
+		if (rc != GSB_OK) return rc;
+	}
+	try {
+		ensureDevice(e);
+		const size_t total = npop > 0 ? offsets[npop] : 0;
+		e->hIdx.reserve(total + 1);
+		e->hOffsets.reserve(static_cast<size_t>(npop) + 1);
+		e->hBucket.reserve(static_cast<size_t>(npop) + 1);
+		const int lmMaxK = std::min(gsb::olsKernelMaxK(e->smemLimit), e->n - 2);
+		int kMaxPop = 0;
+		for (int c = 0; c < npop; ++c) {
+			if (offsets[c + 1] < offsets[c]) return fail(e, GSB_ERR_INVALID_ARGUMENT, "population offsets must be non-decreasing");
+			const uint32_t b = offsets[c], en = offsets[c + 1];
+			const int k = static_cast<int>(en - b);
+			bool sorted = true;
+			for (uint32_t i = b; i < en; ++i) {
+				const uint32_t v = idx[i];
+				if (v >= static_cast<uint32_t>(e->p)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "column index out of range");
+				if (i > b && v < idx[i - 1]) sorted = false;
+				e->hIdx.ptr[i] = v;
+			}
+			if (!sorted) std::sort(e->hIdx.ptr + b, e->hIdx.ptr + en); // the fit does not depend on the column order
+			e->hOffsets.ptr[c] = b;
+			kMaxPop = std::max(kMaxPop, k);
+			if (e->cfg.evaluator == GSB_EVAL_LM && k > lmMaxK) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the OLS kernel (k <= min(n - 2, shared-memory limit))");
+			if (e->cfg.evaluator != GSB_EVAL_LM && k > 1024) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the SIMPLS kernel (k <= 1024)");
+		}
+		e->hOffsets.ptr[npop] = static_cast<uint32_t>(total);
+
+		// counting sort of the non-empty chromosomes into subset-size classes
+		std::vector<int> order;
+		order.reserve(static_cast<size_t>(npop));
+		for (int c = 0; c < npop; ++c) if (offsets[c + 1] > offsets[c]) order.push_back(c);
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+			return bucketCeil(static_cast<int>(offsets[a + 1] - offsets[a])) < bucketCeil(static_cast<int>(offsets[b + 1] - offsets[b]));
+		});
+		e->buckets.clear();
+		for (size_t i = 0; i < order.size(); ++i) {
+			const int k = static_cast<int>(offsets[order[i] + 1] - offsets[order[i]]);
+			const int cls = bucketCeil(k);
+			if (e->buckets.empty() || bucketCeil(e->buckets.back().kMax) != cls) {
+				Bucket b = {static_cast<int>(i), 0, 0};
+				e->buckets.push_back(b);
+			}
+			e->buckets.back().count += 1;
+			e->buckets.back().kMax = std::max(e->buckets.back().kMax, k);
+			e->hBucket.ptr[i] = order[i];
+		}
+
+		e->npop = npop;
+		e->kMaxPop = kMaxPop;
+		e->tableA = std::max(1, std::min(e->shape.maxNComp, kMaxPop));
+		GSB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+		e->dIdx.upload(e->hIdx.ptr, total, e->stream);
+		e->dOffsets.upload(e->hOffsets.ptr, static_cast<size_t>(npop) + 1, e->stream);
+		e->dBucket.upload(e->hBucket.ptr, order.size(), e->stream);
+		GSB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+		e->dFitness.reserve(static_cast<size_t>(npop));
+		e->dStatus.reserve(static_cast<size_t>(npop));
+		if (e->cfg.evaluator != GSB_EVAL_LM) {
+			const size_t innerDests = static_cast<size_t>(e->plan.groups) * e->plan.innerPerGroup;
+			e->dMse.reserve(static_cast<size_t>(npop) * innerDests * e->tableA);
+			e->dOstat.reserve(static_cast<size_t>(npop) * e->plan.groups * e->tableA * 2);
+		}
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		float ms = 0.f;
+		GSB_CUDA(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+		e->lastH2dMs = ms;
+		e->populationReady = true;
+		e->resultsReady = false;
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	} catch (const std::bad_alloc&) {
+		return fail(e, GSB_ERR_MEMORY, "host allocation failed");
+	}
+	return GSB_OK;
+}
+
+int gsb_population_evaluate(gsb_engine* e) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->populationReady) return fail(e, GSB_ERR_STATE, "no resident population: call gsb_population_upload first");
+	try {
+		ensureDevice(e);
+		long long ctas = 0;
+		int launches = 0;
+		GSB_CUDA(cudaEventRecord(e->ev[2], e->stream));
+		if (e->cfg.evaluator == GSB_EVAL_LM) {
+			gsb::launchMarkEmpty(e->dOffsets.ptr, e->npop, e->dFitness.ptr, e->dStatus.ptr, e->stream);
+			++launches;
+			for (size_t b = 0; b < e->buckets.size(); ++b) {
+				gsb::OlsParams prm;
+				prm.gram = e->gram.ptr;
+				prm.s0 = e->s0.ptr;
+				prm.xm = e->xm.ptr;
+				prm.ym = e->ymAllRows;
+				prm.z = e->zpool.ptr;
+				prm.ldz = e->ldz;
+				prm.n = e->n;
+				prm.p = e->p;
+				prm.idx = e->dIdx.ptr;
+				prm.offsets = e->dOffsets.ptr;
+				prm.bucket = e->dBucket.ptr + e->buckets[b].begin;
+				prm.bucketCount = e->buckets[b].count;
+				prm.statistic = e->cfg.statistic;
+				prm.r2denom = e->r2denom;
+				prm.fitness = e->dFitness.ptr;
+				prm.status = e->dStatus.ptr;
+				GSB_CUDA(gsb::launchOlsKernel(prm, e->buckets[b].kMax, e->smemLimit, e->stream));
+				ctas += prm.bucketCount;
+				++launches;
+			}
+			GSB_CUDA(cudaEventRecord(e->ev[3], e->stream));
+			GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
+		} else {
+			const int innerDests = e->plan.groups * e->plan.innerPerGroup;
+			for (size_t b = 0; b < e->buckets.size(); ++b) {
+				gsb::FitParams prm;
+				prm.gram = e->gram.ptr;
+				prm.s0 = e->s0.ptr;
+				prm.xm = e->xm.ptr;
+				prm.zpool = e->zpool.ptr;
+				prm.fits = e->fits.ptr;
+				prm.tasks = e->tasks.ptr;
+				prm.blocks = e->blocks.ptr;
+				prm.idx = e->dIdx.ptr;
+				prm.offsets = e->dOffsets.ptr;
+				prm.bucket = e->dBucket.ptr + e->buckets[b].begin;
+				prm.bucketCount = e->buckets[b].count;
+				prm.nfits = static_cast<int>(e->plan.fits.size());
+				prm.p = e->p;
+				prm.maxNComp = e->tableA;
+				prm.innerDests = innerDests;
+				prm.outerDests = e->plan.groups;
+				prm.mse = e->dMse.ptr;
+				prm.ostat = e->dOstat.ptr;
+				prm.coefOut = nullptr;
+				GSB_CUDA(gsb::launchFitKernel(prm, e->buckets[b].kMax, e->tableA, e->smemLimit, e->stream, &ctas));
+				++launches;
+			}
+			GSB_CUDA(cudaEventRecord(e->ev[3], e->stream));
+			gsb::ReduceParams rp;
+			rp.mse = e->dMse.ptr;
+			rp.ostat = e->dOstat.ptr;
+			rp.offsets = e->dOffsets.ptr;
+			rp.outerRows = e->outerRows.ptr;
+			rp.npop = e->npop;
+			rp.groups = e->plan.groups;
+			rp.inner = e->plan.innerPerGroup;
+			rp.outerPerRep = e->plan.groupsPerReplication;
+			rp.replications = e->shape.replications;
+			rp.maxNComp = e->tableA;
+			rp.innerDests = innerDests;
+			rp.outerDests = e->plan.groups;
+			rp.kind = e->cfg.evaluator;
+			rp.statistic = e->cfg.statistic;
+			rp.n = e->n;
+			rp.sdfact = e->shape.sdfact;
+			rp.gamma = e->cfg.evaluator == GSB_EVAL_PLS_CV ? e->cfg.complexity_penalty : 0.0;
+			rp.r2denom = e->r2denom;
+			rp.fitness = e->dFitness.ptr;
+			rp.status = e->dStatus.ptr;
+			gsb::launchReduceKernel(rp, e->stream);
+			GSB_CUDA(cudaGetLastError());
+			++launches;
+			GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
+		}
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		float msFit = 0.f, msRed = 0.f;
+		GSB_CUDA(cudaEventElapsedTime(&msFit, e->ev[2], e->ev[3]));
+		GSB_CUDA(cudaEventElapsedTime(&msRed, e->ev[3], e->ev[4]));
+		e->timing.h2d_ms = e->lastH2dMs;
+		e->timing.fit_kernel_ms = msFit;
+		e->timing.reduce_kernel_ms = msRed;
+		e->timing.d2h_ms = 0.0;
+		e->timing.total_ms = e->lastH2dMs + msFit + msRed;
+		e->timing.fit_ctas = ctas;
+		e->timing.kernel_launches = launches;
+		e->resultsReady = true;
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	}
+	return GSB_OK;
+}
+
+int gsb_population_download(gsb_engine* e, double* fitness, int32_t* status) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!fitness || !status) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null output buffer");
+	if (!e->resultsReady) return fail(e, GSB_ERR_STATE, "no results: call gsb_population_evaluate first");
+	try {
+		ensureDevice(e);
+		const size_t np = static_cast<size_t>(e->npop);
+		e->hFitness.reserve(np + 1);
+		e->hStatus.reserve(np + 1);
+		GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
+		GSB_CUDA(cudaMemcpyAsync(e->hFitness.ptr, e->dFitness.ptr, np * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+		GSB_CUDA(cudaMemcpyAsync(e->hStatus.ptr, e->dStatus.ptr, np * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+		GSB_CUDA(cudaEventRecord(e->ev[5], e->stream));
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		float ms = 0.f;
+		GSB_CUDA(cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]));
+		e->timing.d2h_ms = ms;
+		e->timing.total_ms = e->timing.h2d_ms + e->timing.fit_kernel_ms + e->timing.reduce_kernel_ms + ms;
+		std::memcpy(fitness, e->hFitness.ptr, np * sizeof(double));
+		for (size_t i = 0; i < np; ++i) status[i] = e->hStatus.ptr[i];
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	}
+	return GSB_OK;
+}
+
+int gsb_population_device_results(gsb_engine* e, void** d_fitness, void** d_status, int32_t* npop) {
+	if (!e || !d_fitness || !d_status || !npop) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->populationReady) return fail(e, GSB_ERR_STATE, "no resident population");
+	*d_fitness = e->dFitness.ptr;
+	*d_status = e->dStatus.ptr;
+	*npop = e->npop;
+	return GSB_OK;
+}
+
+int gsb_evaluate_indices(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop, double* fitness,
+                         int32_t* status) {
+	int rc = gsb_population_upload(e, idx, offsets, npop);
+	if (rc != GSB_OK) return rc;
+	if (npop == 0) return GSB_OK;
+	rc = gsb_population_evaluate(e);
+	if (rc != GSB_OK) return rc;
+	return gsb_population_download(e, fitness, status);
+}
+
+int gsb_evaluate_bitsets(gsb_engine* e, const uint64_t* bitsets, int32_t words_per_chrom, int32_t npop, double* fitness,
+                         int32_t* status) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->haveData) return fail(e, GSB_ERR_STATE, "gsb_set_data has not been called");
+	if (!bitsets || npop < 0) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null population");
+	const int words = (e->p + 63) / 64;
+	if (words_per_chrom != words) return fail(e, GSB_ERR_INVALID_ARGUMENT, "words_per_chrom must be ceil(p / 64)");
+	// Chromosome::toColumnSubset (src/Chromosome.cpp:419-438): variable v is bit unusedBits + v
+	const int unused = words * 64 - e->p;
+	std::vector<uint32_t> idx, offsets(static_cast<size_t>(npop) + 1, 0u);
+	try {
+		for (int c = 0; c < npop; ++c) {
+			const uint64_t* w = bitsets + static_cast<size_t>(c) * words;
+			for (int part = 0; part < words; ++part) {
+				uint64_t bits = w[part];
+				if (part == 0 && unused > 0) bits &= ~((uint64_t(1) << unused) - 1);
+				while (bits) {
+					const int bit = __builtin_ctzll(bits);
+					idx.push_back(static_cast<uint32_t>(part * 64 + bit - unused));
+					bits &= bits - 1;
+				}
+			}
+			offsets[static_cast<size_t>(c) + 1] = static_cast<uint32_t>(idx.size());
+		}
+	} catch (const std::bad_alloc&) {
+		return fail(e, GSB_ERR_MEMORY, "host allocation failed");
+	}
+	if (idx.empty()) idx.push_back(0u);
+	return gsb_evaluate_indices(e, idx.data(), offsets.data(), npop, fitness, status);
+}
+
+int gsb_last_timing(const gsb_engine* e, gsb_timing* t) {
+	if (!e || !t) return GSB_ERR_INVALID_ARGUMENT;
+	*t = e->timing;
+	return GSB_OK;
+}
+
+int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* rows, int32_t nrows, int32_t ncomp,
+               double* coef, double* intercepts) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->haveData) return fail(e, GSB_ERR_STATE, "gsb_set_data has not been called");
+	if (!cols || k < 1 || k > 1024 || ncomp < 1 || !coef || !intercepts) return fail(e, GSB_ERR_INVALID_ARGUMENT, "invalid SIMPLS request");
+	const int n = e->n, p = e->p;
+	std::vector<uint32_t> trainRows;
+	if (rows && nrows > 0) trainRows.assign(rows, rows + nrows);
+	else { trainRows.resize(static_cast<size_t>(n)); std::iota(trainRows.begin(), trainRows.end(), 0u); }
+	const int ntr = static_cast<int>(trainRows.size());
+	for (int i = 0; i < ntr; ++i) if (trainRows[static_cast<size_t>(i)] >= static_cast<uint32_t>(n)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "row index out of range");
+	for (int i = 0; i < k; ++i) {
+		if (cols[i] >= static_cast<uint32_t>(p)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "column index out of range");
+		if (i > 0 && cols[i] <= cols[i - 1]) return fail(e, GSB_ERR_INVALID_ARGUMENT, "columns must be strictly ascending");
+	}
+	// PLSSimpls::fit clamps the number of components (src/PLSSimpls.cpp:107-110)
+	const int A = std::min(ncomp, std::min(k, ntr - 1));
+	if (A < 1) return fail(e, GSB_ERR_INVALID_ARGUMENT, "too few training rows");
+	try {
+		ensureDevice(e);
+		if (!e->zReady) uploadZ(e, 0);
+		const int K2 = k + 2, ld = roundUp(ntr, 4), ldm = roundUp(K2, 4);
+		std::vector<uint32_t> colSel(cols, cols + k);
+		colSel.push_back(static_cast<uint32_t>(p));
+		colSel.push_back(static_cast<uint32_t>(p + 1));
+		DeviceArray<uint32_t> dCols, dRows, dIdx, dOff;
+		DeviceArray<double> dSub, dM, dGram, dS0, dXm, dYm, dOut, dDummy;
+		DeviceArray<const double*> dUnit, dMBlocks;
+		DeviceArray<double*> dOutPtr;
+		DeviceArray<int> dLd, dNr, dExclIdx, dExclCnt, dFitId, dFitNtr, dBucket;
+		DeviceArray<unsigned long long> dGOff;
+		DeviceArray<gsb::FitDesc> dFit;
+		dCols.upload(colSel, e->stream);
+		dRows.upload(trainRows, e->stream);
+		dSub.reserve(static_cast<size_t>(ld) * K2);
+		gsb::launchBlockGather(e->zpool.ptr, e->ldz, K2, dCols.ptr, dRows.ptr, ntr, dSub.ptr, ld, e->stream);
+		dM.reserve(static_cast<size_t>(K2) * ldm);
+		GSB_CUDA(cudaMemsetAsync(dM.ptr, 0, static_cast<size_t>(K2) * ldm * sizeof(double), e->stream));
+		const double* unitPtr = dSub.ptr;
+		double* outPtr = dM.ptr;
+		const double* noBlock = nullptr;
+		const int zero = 0, two[2] = {0, 0};
+		const unsigned long long goff = 0;
+		dUnit.upload(&unitPtr, 1, e->stream);
+		dOutPtr.upload(&outPtr, 1, e->stream);
+		dLd.upload(&ld, 1, e->stream);
+		dNr.upload(&ld, 1, e->stream);
+		dMBlocks.upload(&noBlock, 1, e->stream);
+		dExclIdx.upload(two, 2, e->stream);
+		dExclCnt.upload(&zero, 1, e->stream);
+		dFitId.upload(&zero, 1, e->stream);
+		dFitNtr.upload(&ntr, 1, e->stream);
+		dGOff.upload(&goff, 1, e->stream);
+		gsb::launchGramSyrk(dUnit.ptr, dLd.ptr, dNr.ptr, dOutPtr.ptr, 1, K2, ldm, e->stream);
+		dGram.reserve(static_cast<size_t>(gsb::tri(static_cast<unsigned long long>(k))));
+		dS0.reserve(static_cast<size_t>(k));
+		dXm.reserve(static_cast<size_t>(k));
+		dYm.reserve(1);
+		gsb::launchGramCombine(dM.ptr, dMBlocks.ptr, dExclIdx.ptr, dExclCnt.ptr, dFitId.ptr, dFitNtr.ptr, 1, k, ldm, dGram.ptr,
+		                       dGOff.ptr, dS0.ptr, dXm.ptr, dYm.ptr, e->stream);
+		GSB_CUDA(cudaGetLastError());
+		double ymc = 0.0;
+		GSB_CUDA(cudaMemcpyAsync(&ymc, dYm.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		gsb::FitDesc fd;
+		fd.gramOff = 0; fd.ym = ymc; fd.ntr = ntr; fd.taskBegin = 0; fd.taskCount = 0; fd.pad = 0;
+		std::vector<uint32_t> ident(static_cast<size_t>(k));
+		std::iota(ident.begin(), ident.end(), 0u);
+		const uint32_t off[2] = {0u, static_cast<uint32_t>(k)};
+		dFit.upload(&fd, 1, e->stream);
+		dIdx.upload(ident, e->stream);
+		dOff.upload(off, 2, e->stream);
+		dBucket.upload(&zero, 1, e->stream);
+		dOut.reserve(static_cast<size_t>(k) * A + A);
+		dDummy.reserve(16);
+		gsb::FitParams prm;
+		prm.gram = dGram.ptr; prm.s0 = dS0.ptr; prm.xm = dXm.ptr; prm.zpool = dSub.ptr;
+		prm.fits = dFit.ptr; prm.tasks = nullptr; prm.blocks = nullptr;
+		prm.idx = dIdx.ptr; prm.offsets = dOff.ptr; prm.bucket = dBucket.ptr; prm.bucketCount = 1; prm.nfits = 1;
+		prm.p = k; prm.maxNComp = A; prm.innerDests = 0; prm.outerDests = 0;
+		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr;
+		GSB_CUDA(gsb::launchFitKernel(prm, k, A, e->smemLimit, e->stream, nullptr));
+		std::vector<double> out(static_cast<size_t>(k) * A + A);
+		GSB_CUDA(cudaMemcpyAsync(out.data(), dOut.ptr, out.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		// back to the caller's (uncentred) coordinates: slopes are unchanged, b0 = ybar + b0c - xbar'B
+		for (int a = 0; a < A; ++a) {
+			double shift = 0.0;
+			for (int i = 0; i < k; ++i) {
+				const double b = out[static_cast<size_t>(a) * k + i];
+				coef[static_cast<size_t>(a) * k + i] = b;
+				shift += e->xMean[cols[i]] * b;
+			}
+			intercepts[a] = e->yMean + out[static_cast<size_t>(k) * A + a] - shift;
+		}
+		for (int a = A; a < ncomp; ++a) { // components beyond the clamp do not exist in the reference either
+			intercepts[a] = std::nan("");
+			for (int i = 0; i < k; ++i) coef[static_cast<size_t>(a) * k + i] = std::nan("");
+		}
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	} catch (const std::bad_alloc&) {
+		return fail(e, GSB_ERR_MEMORY, "host allocation failed");
+	}
+	return GSB_OK;
+}
+
+} // extern "C"

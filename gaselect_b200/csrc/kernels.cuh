@@ -1,0 +1,127 @@
+// kernels.cuh -- device-side tables shared by the CUDA kernels and the engine.
+//
+// HBM layout (all FP64 unless noted; "P2" = p + 2 augmented columns [Xc | yc | 1]):
+//   Z        ldz x P2   column-major, globally centred X and y, ones column; rows padded to a
+//                       multiple of 4 with zeros (they do not change any Gram)
+//   blocks   per distinct held-out block b: ld_b x P2 column-major copy of Z[rows_b, :] so that a
+//                       selected column of a block is one contiguous, coalesced segment
+//   gram     per distinct training set T: packed lower triangle (row-major, tri(p) doubles) of
+//                       the centred Gram  Xc_T' Xc_T - n_T xm xm'
+//   fitvec   per T: s0 = Xc_T' yc_T (p), xm = column means over T (p)
+#ifndef GASELECT_B200_KERNELS_CUH
+#define GASELECT_B200_KERNELS_CUH
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gsb {
+
+struct FitDesc {
+	unsigned long long gramOff; // offset (doubles) into the gram pool
+	double ym;                  // mean of yc over the training rows
+	int ntr;
+	int taskBegin;
+	int taskCount;
+	int pad;
+};
+
+struct TaskDesc {
+	int block;
+	int kind; // 0 inner (MSEP table), 1 outer (pooled residual statistics)
+	int dest;
+	int pad;
+};
+
+struct BlockDesc {
+	unsigned long long zOff; // offset (doubles) into the block pool (or into Z when allRows)
+	int ld;
+	int nrows;
+};
+
+// everything K1 needs, passed by value
+struct FitParams {
+	const double* gram;
+	const double* s0;   // nfits x p
+	const double* xm;   // nfits x p
+	const double* zpool;
+	const FitDesc* fits;
+	const TaskDesc* tasks;
+	const BlockDesc* blocks;
+	const uint32_t* idx;     // CSR column lists of the population
+	const uint32_t* offsets;
+	const int* bucket;       // chromosome ids handled by this launch
+	int bucketCount;
+	int nfits;
+	int p;
+	int maxNComp;            // table stride (components)
+	int innerDests;          // groups * I
+	int outerDests;          // groups
+	double* mse;             // [chrom][innerDest][maxNComp]
+	double* ostat;           // [chrom][outerDest][maxNComp][2] = (sum e, sum e^2)
+	double* coefOut;         // optional (gsb_simpls): [k x A] + A intercepts for fit 0 / bucket[0]
+};
+
+struct ReduceParams {
+	const double* mse;
+	const double* ostat;
+	const uint32_t* offsets;
+	const int* outerRows; // per group
+	int npop;
+	int groups;
+	int inner;
+	int outerPerRep;
+	int replications;
+	int maxNComp;
+	int innerDests;
+	int outerDests;
+	int kind;      // gsb_evaluator_kind
+	int statistic;
+	int n;
+	double sdfact;
+	double gamma;
+	double r2denom;
+	double* fitness;
+	int* status;
+};
+
+struct OlsParams {
+	const double* gram;   // packed centred Gram of all rows
+	const double* s0;
+	const double* xm;
+	double ym;
+	const double* z;      // Z (ldz x P2)
+	int ldz;
+	int n;
+	int p;
+	const uint32_t* idx;
+	const uint32_t* offsets;
+	const int* bucket;
+	int bucketCount;
+	int statistic;
+	double r2denom;
+	double* fitness;
+	int* status;
+};
+
+__host__ __device__ inline unsigned long long tri(unsigned long long i) { return i * (i + 1ull) / 2ull; }
+
+// launchers (definitions next to the kernels)
+void launchGramSyrk(const double* const* unitPtrs, const int* unitLd, const int* unitRows, double* const* outPtrs,
+                    int units, int P2, int ldm, cudaStream_t stream);
+void launchGramCombine(const double* mFull, const double* const* mBlocks, const int* exclIndex, const int* exclCount,
+                       const int* fitIds, const int* fitNtr, int nfitsChunk, int p, int ldm, double* gramPool,
+                       const unsigned long long* gramOffs, double* s0, double* xm, double* ym, cudaStream_t stream);
+void launchBlockGather(const double* z, int ldz, int ncols, const uint32_t* cols, const uint32_t* rows, int nrows,
+                       double* dst, int ld, cudaStream_t stream);
+int fitKernelSharedBytes(int k, int A);
+int fitKernelMaxK(int A, int smemLimit);
+cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
+void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream);
+cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream);
+int olsKernelMaxK(int smemLimit);
+void launchMarkEmpty(const uint32_t* offsets, int npop, double* fitness, int* status, cudaStream_t stream);
+
+} // namespace gsb
+
+#endif

@@ -36,3 +36,25 @@ def ref_lib():
     if not bindings.have_ref():
         pytest.skip("oracle/_ref/libgaselect_ref.so not available")
     return bindings.RefLib()
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """The product library (gaselect_b200/libgaselect_b200.so), built on demand with nvcc."""
+    import subprocess
+    from gaselect_b200 import _capi
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "gaselect_b200", "csrc")], check=True)
+    return _capi.lib()
+
+
+def cuda_device_count():
+    import ctypes
+    try:
+        rt = ctypes.CDLL("libcuda.so.1")
+    except OSError:
+        return 0
+    if rt.cuInit(0) != 0:
+        return 0
+    n = ctypes.c_int(0)
+    rt.cuDeviceGetCount(ctypes.byref(n))
+    return n.value

@@ -1,0 +1,211 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+  (a) the committed golden vectors produced by the reference's own code,
+  (b) the CPU oracle on fresh seeded inputs, and
+  (c) size-independent properties at BASELINE.json's full sizes.
+Tolerance: BASELINE.json north_star -- fitness within RELATIVE 1e-8 in FP64; statuses,
+segmentations and subsets bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from gaselect_b200 import synth
+from helpers import make_checker_evaluator, make_data, make_subsets, rel_err
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-8  # north_star: "within relative 1e-8 in FP64"
+
+
+def _product_evaluator(spec, X, y, seed):
+    from gaselect_b200 import evaluators as E
+    spec = dict(spec)
+    kind = spec.pop("kind")
+    if kind == "pls":
+        return E.PLSEvaluator(X, y, seed, **spec)
+    if kind == "fit":
+        return E.BICEvaluator(X, y, seed, **spec)
+    return E.LMEvaluator(X, y, **spec)
+
+
+def _case_names():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")) as fh:
+        return [c["name"] for c in json.load(fh)["cases"]]
+
+
+@pytest.mark.parametrize("name", _case_names())
+def test_golden_case(engine, golden, name):
+    case = next(c for c in golden["cases"] if c["name"] == name)
+    X, y = make_data(case["data"])
+    subsets = make_subsets(case["subsets"], X.shape[1])
+    with _product_evaluator(case["evaluator"], X, y, golden["ga_seed"]) as ev:
+        fit, status = ev.evaluate_population(subsets)
+        t = ev.timing()
+    assert status.tolist() == case["status"]
+    ok = np.asarray(case["status"]) == 0
+    err = rel_err(fit[ok], np.asarray(case["fitness"])[ok])
+    assert err.max() <= REL_TOL, (name, float(err.max()))
+    assert t["kernel_launches"] >= 1 and t["fit_ctas"] >= 1  # the CUDA kernels really ran
+
+
+def test_survey_appendix_c_values(engine):
+    from gaselect_b200 import evaluators as E
+    X, y = synth.closed_form()
+    with E.PLSEvaluator(X, y, 123, numReplications=2, maxNComp=5, innerSegments=4, outerSegments=3) as ev:
+        fit, _ = ev.evaluate_population([[2, 5, 11, 29], list(range(12)), [7], [1, 2, 5, 8, 11, 13, 17, 19, 23, 29]])
+        want = [-0.082050888884043549, -0.40119862398530326, -1.6049334059118827, -0.26544539104666021]
+        assert rel_err(fit, want).max() <= REL_TOL
+        assert ev.evaluate([2, 5, 11, 29]) == pytest.approx(want[0], rel=REL_TOL)
+    with E.LMEvaluator(X, y, "BIC") as ev:
+        assert ev.evaluate([1, 2, 5, 8, 11, 13, 17, 19, 23, 29]) == pytest.approx(174.02302223845993, rel=REL_TOL)
+    with E.BICEvaluator(X, y, 123, statistic="BIC") as ev:
+        assert ev.evaluate([2, 5, 11, 29]) == pytest.approx(191.69625628073339, rel=REL_TOL)
+
+
+def test_raw_simpls_coefficients(engine, golden):
+    from gaselect_b200 import evaluators as E
+    g = golden["simpls_closed"]
+    X, y = synth.closed_form()
+    with E.PLSEvaluator(X, y, 123, numReplications=1, innerSegments=3) as ev:
+        B, b0 = ev.simpls(g["cols"], g["ncomp"])
+        assert np.abs(B - np.asarray(g["coef"]).reshape(B.shape)).max() <= 1e-9 * np.abs(B).max()
+        assert b0 == pytest.approx(g["intercepts"], rel=1e-9)
+        # a row subset, against the oracle
+    from oracle import bindings
+    orc = bindings.OracleLib()
+    rows = np.arange(0, 40, 2, dtype=np.uint32)
+    Bo, b0o = orc.simpls_fit(X, y, [1, 4, 9, 16, 25], 4, rows=rows)
+    with E.LMEvaluator(X, y) as ev:
+        B, b0 = ev.simpls([1, 4, 9, 16, 25], 4, rows=rows)
+    assert np.abs(B - Bo).max() <= 1e-9 * np.abs(Bo).max() and b0 == pytest.approx(b0o, rel=1e-9)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n=57, p=80, kw=dict(numReplications=3, maxNComp=5, innerSegments=5, outerSegments=3)),
+    dict(n=64, p=50, kw=dict(numReplications=2, maxNComp=0, innerSegments=4, outerSegments=1)),
+    dict(n=45, p=60, kw=dict(numReplications=2, maxNComp=4, innerSegments=2, outerSegments=2)),
+    dict(n=90, p=300, kw=dict(numReplications=3, maxNComp=8, innerSegments=4, outerSegments=5)),
+    dict(n=31, p=33, kw=dict(numReplications=2, maxNComp=3, innerSegments=3, outerSegments=1, testSetSize=0.3, sdfact=2.0,
+                             complexityPenalty=0.02)),
+])
+def test_pls_against_oracle_on_fresh_inputs(engine, oracle_lib, cfg):
+    from gaselect_b200 import evaluators as E
+    n, p, kw = cfg["n"], cfg["p"], cfg["kw"]
+    X, y = synth.nir_spectra(n, p, seed=300 + n)
+    sv = oracle_lib.make_seedvec(2000 + p)
+    subsets = synth.random_subsets(p, 48, 1, min(p, 70), seed=n) + [np.arange(p, dtype=np.uint32)[: min(p, 150)]]
+    chk = oracle_lib.pls_evaluator(X, y, sv, **kw)
+    fo, so = chk.evaluate(subsets, threads=4)
+    with E.PLSEvaluator(X, y, sv, **kw) as ev:
+        assert all((a == b).all() for a, b in zip(ev.getSegmentation(), chk.segmentation()))
+        fg, sg = ev.evaluate_population(subsets)
+    assert (sg == so).all()
+    assert rel_err(fg[so == 0], fo[so == 0]).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("stat", ["BIC", "AIC", "adjusted.r.squared", "r.squared"])
+def test_fit_and_lm_against_oracle(engine, oracle_lib, stat):
+    from gaselect_b200 import evaluators as E
+    X, y = synth.gaussian(120, 90, seed=5)
+    sv = oracle_lib.make_seedvec(77)
+    subsets = synth.random_subsets(90, 40, 1, 45, seed=3)
+    fo, so = oracle_lib.fit_evaluator(X, y, sv, numSegments=6, statistic=stat, maxNComp=7).evaluate(subsets)
+    with E.BICEvaluator(X, y, sv, numSegments=6, statistic=stat, maxNComp=7) as ev:
+        fg, sg = ev.evaluate_population(subsets)
+    assert (sg == so).all() and rel_err(fg, fo).max() <= REL_TOL
+    fo, so = oracle_lib.lm_evaluator(X, y, stat).evaluate(subsets)
+    with E.LMEvaluator(X, y, stat) as ev:
+        fg, sg = ev.evaluate_population(subsets)
+    assert (sg == so).all() and rel_err(fg, fo).max() <= REL_TOL
+
+
+def test_empty_ragged_and_unsorted_subsets(engine, oracle_lib):
+    from gaselect_b200 import evaluators as E
+    X, y = synth.closed_form()
+    sv = oracle_lib.make_seedvec(5)
+    subsets = [[], [3], [1, 2], [], list(range(30)), [29, 0, 7]]
+    with E.PLSEvaluator(X, y, sv, numReplications=2, innerSegments=3, maxNComp=4) as ev:
+        fit, status = ev.evaluate_population(subsets)
+        assert status.tolist() == [1, 0, 0, 1, 0, 0] and fit[0] == 0.0 and fit[3] == 0.0
+        fo, _ = oracle_lib.pls_evaluator(X, y, sv, numReplications=2, innerSegments=3, maxNComp=4).evaluate(
+            [sorted(s) for s in subsets if len(s)])
+        assert rel_err(fit[status == 0], fo).max() <= REL_TOL
+        with pytest.raises(E.EvaluatorException):
+            ev.evaluate([])
+        with pytest.raises(ValueError):
+            ev.evaluate([30])          # column out of range
+        f0, s0 = ev.evaluate_population([])
+        assert len(f0) == 0
+    with E.LMEvaluator(X, y) as ev:
+        fit, status = ev.evaluate_population(subsets)
+        assert status.tolist() == [1, 0, 0, 1, 0, 0]
+
+
+def test_bitset_entry_matches_index_entry(engine):
+    """gsb_evaluate_bitsets decodes the reference layout (src/Chromosome.cpp:419-438)."""
+    from gaselect_b200 import evaluators as E
+    for p in (30, 64, 100, 200):
+        X, y = synth.gaussian(60, p, seed=p)
+        subsets = synth.random_subsets(p, 20, 1, 25, seed=p)
+        words = (p + 63) // 64
+        unused = words * 64 - p
+        bits = np.zeros((len(subsets), words), dtype=np.uint64)
+        for c, s in enumerate(subsets):
+            for v in s:
+                pos = unused + int(v)
+                bits[c, pos // 64] |= np.uint64(1) << np.uint64(pos % 64)
+        bits[:, 0] |= np.uint64((1 << unused) - 1)  # garbage in the unused low bits must be ignored
+        with E.PLSEvaluator(X, y, 9, numReplications=2, innerSegments=4, maxNComp=6) as ev:
+            fa, sa = ev.evaluate_population(subsets)
+            fb, sb = ev.evaluate_bitsets(bits)
+        assert (sa == sb).all() and (fa == fb).all()  # bit-exact: same kernels, same inputs
+
+
+def test_results_do_not_depend_on_batch_composition(engine):
+    """Each chromosome's fitness is a pure function of its subset: evaluating it alone, in a
+    shuffled batch or next to different neighbours gives bit-identical results."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(150, 1000, seed=777)
+    subsets = synth.sweep_subsets(1000, 64, 40, seed=2)
+    with E.PLSEvaluator(X, y, 123, numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5) as ev:
+        f1, s1 = ev.evaluate_population(subsets)
+        perm = np.argsort(synth.SplitMix64(4).uniform(len(subsets)))
+        f2, s2 = ev.evaluate_population([subsets[i] for i in perm])
+        assert (f1[perm] == f2).all() and (s1[perm] == s2).all()
+        f3, _ = ev.evaluate_population(subsets[:5])
+        assert (f3 == f1[:5]).all()
+        assert ev.evaluate(subsets[7]) == f1[7]
+
+
+def test_cfg3_full_size_population_against_reference_build(engine, ref_lib):
+    """BASELINE config 3 at full size (n=150, p=1000, population 500, rdCV 10 x 5/4, <=10
+    components) against the reference's own code, 8 host threads."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(150, 1000, seed=777, noise=1e-2)
+    sv = ref_lib.make_seedvec(123)
+    subsets = synth.random_subsets(1000, 500, 10, 200, seed=42)
+    kw = dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)
+    with E.PLSEvaluator(X, y, sv, **kw) as ev:
+        fg, sg = ev.evaluate_population(subsets)
+        inf = ev.info()
+    assert (inf["fits_per_evaluation"], inf["distinct_fits"], inf["distinct_blocks"]) == (250, 150, 50)
+    fr, sr = ref_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets[:120], threads=8)
+    assert (sg == 0).all() and (sr == 0).all()
+    assert rel_err(fg[:120], fr).max() <= REL_TOL
+
+
+def test_cfg4_shape_properties(engine, oracle_lib):
+    """BASELINE config 4 shape (n=500, p=5000): a sample against the oracle plus properties."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(500, 5000, seed=778, noise=1e-2)
+    sv = oracle_lib.make_seedvec(123)
+    subsets = synth.random_subsets(5000, 96, 20, 200, seed=43)
+    kw = dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)
+    with E.PLSEvaluator(X, y, sv, **kw) as ev:
+        fg, sg = ev.evaluate_population(subsets)
+        fg2, _ = ev.evaluate_population(subsets[::-1])
+    assert (sg == 0).all() and (fg2[::-1] == fg).all() and (fg < 0).all()
+    fo, so = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets[:12], threads=8)
+    assert rel_err(fg[:12], fo).max() <= REL_TOL
