@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- chromosome fitness evaluations per second (repeated-CV PLS) on B200.
+
+A "step" is ONE generation's fitness pass: every chromosome of the population is scored by
+R*O*(I+1) cross-validated SIMPLS fits (BASELINE.json config "evaluatorPLS repeated double CV
+(10 outer reps, 5/4 segments, <=10 components), n=150 p=1000 NIR-like spectra, population 500").
+At N GPUs every rank scores its own 500-chromosome shard of a 500*N population (weak scaling; the
+units are independent, the only exchange is the all-gather of the fitness vectors over NCCL).
+
+  value     device-resident throughput: population already in HBM, K1+K2 enqueued per step
+  e2e       through the public call (gsb_evaluate_indices) with HOST buffers: per step the CSR
+            lists go host->device and fitness/status come back
+  roofline  K1 (simplsFitKernel) algorithmic bytes / its CUDA-event time
+  cpu_baseline / --impl reference: the reference's own evaluator code (oracle/_ref, built from
+            /root/reference/src) on the box's host cores, on a bounded sample of the same population
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from gaselect_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric (repeated-CV PLS) is quoted on
+    "cfg3": dict(n=150, p=1000, pop=500, kmin=10, kmax=200, data_seed=777,
+                 kw=dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)),
+    # BASELINE.json configs[3] shape, per-GPU shard of the 2000-chromosome population
+    "cfg4": dict(n=500, p=5000, pop=250, kmin=20, kmax=200, data_seed=778,
+                 kw=dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)),
+}
+GA_SEED = 123
+
+
+def bytes_eval(k, seg_lengths):
+    """algorithmic bytes of one evaluation.  seg_lengths: list over (rep, outer)
+    groups of (list of inner test lengths, outer test length)."""
+    def bytes_fit(k, nte):
+        return 8.0 * (k * (k + 1) / 2 + 2 * k + 2) + 8.0 * nte * (k + 1)
+    total = 16.0
+    for inner, outer in seg_lengths:
+        total += sum(bytes_fit(k, t) for t in inner) + bytes_fit(k, outer)
+    return total
+
+
+def group_lengths(seg, inner):
+    per = 2 * (inner + 1)
+    out = []
+    for g in range(len(seg) // per):
+        base = g * per
+        out.append(([len(seg[base + 2 * j + 1]) for j in range(inner)], len(seg[base + 2 * inner + 1])))
+    return out
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML while the timed region runs (the
+    nvidia-smi clocks line of B200_PROFILING.md, without spawning a process next to the GPU work)."""
+
+    def __init__(self, device, period=0.05):
+        self.device, self.period, self.rows, self.thread, self.h = device, period, [], None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # no NVML: report that instead of a number
+            self.err = repr(exc)
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.h is not None:
+            self.rows = []
+            self._stop.clear()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "err", "")]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        masks = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(name for name, m in masks.items() if any(r[1] & m for r in self.rows))
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max([r[2] for r in self.rows], default=None)}
+
+
+def reference_library():
+    from oracle import bindings
+    if os.path.isdir("/root/reference/src"):
+        bindings.build("ref")
+    if bindings.have_ref():
+        return bindings.RefLib(), "reference"
+    bindings.build("port")
+    return bindings.OracleLib(), "port"
+
+
+def cpu_leg(w, X, y, subsets, budget_s):
+    """The reference's own evaluator on the host cores, bounded sample of the population."""
+    lib, kind = reference_library()
+    cores = os.cpu_count() or 1
+    sv = lib.make_seedvec(GA_SEED)
+    ev = lib.pls_evaluator(X, y, sv, **w["kw"])
+    probe = subsets[:cores]
+    _, _, t0 = ev.evaluate(probe, threads=cores, return_time=True)
+    per_round = max(t0, 1e-3)
+    rounds = int(max(1, min(len(subsets) // cores - 1, budget_s / per_round)))
+    sample = subsets[cores:cores + rounds * cores] or probe
+    _, st, t = ev.evaluate(sample, threads=cores, return_time=True)
+    return {"value": len(sample) / t, "unit": "evals/s", "cores": cores, "kind": kind,
+            "sample": "%d of the %d chromosomes of one generation (k %d..%d), %d host threads, %.1f s; linear algebra under the "
+                      "reference code is the repo's stand-in for Armadillo/BLAS (no R in the image)" %
+                      (len(sample), len(subsets), w["kmin"], w["kmax"], cores, t)}, len(sample), t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--pop", type=int, default=0, help="chromosomes per GPU (default: the workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = dict(WORKLOADS[args.workload])
+    if args.pop:
+        w["pop"] = args.pop
+    X, y = synth.nir_spectra(w["n"], w["p"], seed=w["data_seed"], noise=1e-2)
+    config = {"workload": "%s: evaluatorPLS rdCV R=%d outer=%d inner=%d maxNComp=%d, NIR-like n=%d p=%d (noise 1e-2), "
+                          "population %d per GPU, subset sizes U[%d,%d]" %
+                          (args.workload, w["kw"]["numReplications"], w["kw"]["outerSegments"], w["kw"]["innerSegments"],
+                           w["kw"]["maxNComp"], w["n"], w["p"], w["pop"], w["kmin"], w["kmax"]),
+              "population_per_gpu": w["pop"], "global_population": w["pop"] * world, "ga_seed": GA_SEED,
+              "parallelism": "population sharded over %d GPU(s); fitness all-gather over NCCL" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        subsets = synth.random_subsets(w["p"], w["pop"], w["kmin"], w["kmax"], seed=42)
+        lib, kind = reference_library()
+        cores = os.cpu_count() or 1
+        ev = lib.pls_evaluator(X, y, lib.make_seedvec(GA_SEED), **w["kw"])
+        _, _, t_probe = ev.evaluate(subsets[:cores], threads=cores, return_time=True)
+        # bounded sample of the generation per step: the whole generation when the run stays under ~2.5 min
+        afford = int(150.0 / (args.steps + args.warmup) / max(t_probe, 1e-4)) * cores
+        per_step = max(cores, min(len(subsets), afford))
+        for i in range(args.warmup):
+            ev.evaluate(subsets[:per_step], threads=cores)
+        total_t, total_n = 0.0, 0
+        for s in range(args.steps):
+            lo = (s * per_step) % max(1, len(subsets) - per_step + 1)
+            _, _, t = ev.evaluate(subsets[lo:lo + per_step], threads=cores, return_time=True)
+            total_t += t
+            total_n += per_step
+        v = total_n / total_t
+        sample = "%d chromosomes of the generation per step, %d host threads" % (per_step, cores)
+        print(json.dumps({"impl": "reference", "metric": "chromosome fitness evals/sec (repeated-CV PLS)", "value": v,
+                          "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gaselect_b200 import _capi, evaluators as E
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # every rank scores its own shard of the (500 * N)-chromosome generation
+    subsets = synth.random_subsets(w["p"], w["pop"], w["kmin"], w["kmax"], seed=42 + rank)
+    idx, offsets = _capi.to_csr(subsets)
+    ks = np.diff(offsets.astype(np.int64))
+
+    ev = E.PLSEvaluator(X, y, GA_SEED, device=local_rank, **w["kw"])
+    info = ev.prepare()
+    # the engine works on torch's current stream, so torch.cuda.Event brackets see its kernels
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ev.set_stream(stream.cuda_stream)
+    seg = ev.getSegmentation()
+    lengths = group_lengths(seg, info["inner_segments"])
+    algo_bytes = float(sum(bytes_eval(int(k), lengths) for k in ks))
+
+    fitness = np.zeros(len(subsets), dtype=np.float64)
+    status = np.zeros(len(subsets), dtype=np.int32)
+    ev.upload_population(idx, offsets)
+    f_ptr, s_ptr, npop = ev.device_results()
+
+    class _Dev:  # zero-copy view of the engine's result buffer for NCCL
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    d_fit = torch.as_tensor(_Dev(f_ptr, npop), device=torch.device("cuda", local_rank))
+    gathered = torch.empty(world * npop, dtype=torch.float64, device=d_fit.device) if world > 1 else None
+
+    def step_resident():
+        ev.enqueue_resident()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_fit)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ev.timing()["kernel_launches"] * args.steps
+    # K1 timed live with the engine's CUDA events on the same stream, per step
+    k1_ms, k2_ms = [], []
+    for _ in range(args.steps):
+        ev.evaluate_resident()
+        t = ev.timing()
+        k1_ms.append(t["fit_kernel_ms"])
+        k2_ms.append(t["reduce_kernel_ms"])
+    clocks = sampler.stop() if rank == 0 else None
+    ev.download_results(fitness, status)
+    assert (status == 0).all() and np.isfinite(fitness).all() and (fitness < 0).all()
+
+    # ---- e2e: public call with host buffers ----------------------------------------------------
+    for _ in range(2):
+        ev.evaluate_csr(idx, offsets)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        f2, s2 = ev.evaluate_csr(idx, offsets)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_fit)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+    assert (f2 == fitness).all()
+    h2d = int(idx[: int(offsets[-1])].nbytes + offsets.nbytes + 4 * len(subsets))
+    d2h = int(fitness.nbytes + status.nbytes)
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=d_fit.device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tt[0]), float(tt[1])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        k1 = float(np.mean(k1_ms))
+        achieved = algo_bytes / (k1 * 1e-3) / 1e9
+        line = {
+            "metric": "chromosome fitness evals/sec (repeated-CV PLS)",
+            "value": w["pop"] * world * args.steps / (ms * 1e-3), "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(config, l2="Gram tables gathered by K1 are %.0f MB per GPU (> 126 MB L2), no explicit flush" %
+                           (info["gram_bytes"] / 1e6),
+                           fits_per_evaluation=info["fits_per_evaluation"], distinct_fits=info["distinct_fits"],
+                           setup_ms=info["setup_ms"], gram_dmma_ms=info["gram_dmma_ms"],
+                           gram_tflops=info["gram_flops"] / max(info["gram_dmma_ms"], 1e-9) / 1e9),
+            "e2e": {"value": w["pop"] * world * args.steps / (e2e_ms * 1e-3), "unit": "evals/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "simplsFitKernel (K1), all subset-size classes of a step",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "algorithmic_bytes_per_step": algo_bytes, "k1_ms_per_step": k1,
+                         "k2_ms_per_step": float(np.mean(k2_ms)), "traffic": None},
+        }
+        if not args.no_cpu and world == 1:
+            cb, _, _ = cpu_leg(w, X, y, subsets, args.cpu_seconds)
+            line["cpu_baseline"] = cb
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

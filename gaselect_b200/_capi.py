@@ -75,6 +75,8 @@ SIGNATURES = {
     "gsb_evaluate_bitsets": (C.c_int, [_H, _u64p, C.c_int32, C.c_int32, _f64p, _i32p]),
     "gsb_population_upload": (C.c_int, [_H, _u32p, _u32p, C.c_int32]),
     "gsb_population_evaluate": (C.c_int, [_H]),
+    "gsb_population_enqueue": (C.c_int, [_H]),
+    "gsb_set_stream": (C.c_int, [_H, C.c_void_p]),
     "gsb_population_download": (C.c_int, [_H, _f64p, _i32p]),
     "gsb_population_device_results": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "gsb_last_timing": (C.c_int, [_H, C.POINTER(Timing)]),

@@ -121,7 +121,9 @@ struct gsb_engine {
 	gsb::FitPlan plan;
 
 	// device
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;    // the stream all work is enqueued on
+	cudaStream_t ownStream = nullptr; // created by the engine
+	bool callerStream = false;
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int smCount = 0, smemLimit = 0;
 	int ldz = 0;
@@ -176,8 +178,10 @@ void releaseDevice(gsb_engine* e) {
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
 	for (int i = 0; i < 6; ++i) { if (e->ev[i]) cudaEventDestroy(e->ev[i]); e->ev[i] = nullptr; }
-	if (e->stream) cudaStreamDestroy(e->stream);
+	if (e->ownStream) cudaStreamDestroy(e->ownStream);
+	e->ownStream = nullptr;
 	e->stream = nullptr;
+	e->callerStream = false;
 	e->deviceReady = e->zReady = e->prepared = e->populationReady = e->resultsReady = false;
 }
 
@@ -195,7 +199,8 @@ void ensureDevice(gsb_engine* e) {
 	GSB_CUDA(cudaGetDeviceProperties(&prop, e->cfg.device));
 	e->smCount = prop.multiProcessorCount;
 	e->smemLimit = static_cast<int>(prop.sharedMemPerBlockOptin);
-	GSB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	GSB_CUDA(cudaStreamCreateWithFlags(&e->ownStream, cudaStreamNonBlocking));
+	if (!e->callerStream) e->stream = e->ownStream;
 	for (int i = 0; i < 6; ++i) GSB_CUDA(cudaEventCreate(&e->ev[i]));
 	e->deviceReady = true;
 }
@@ -623,6 +628,19 @@ int gsb_prepare(gsb_engine* e) {
 	return prepareChecked(e);
 }
 
+int gsb_set_stream(gsb_engine* e, void* cuda_stream) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	try {
+		ensureDevice(e);
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		e->callerStream = cuda_stream != nullptr;
+		e->stream = e->callerStream ? static_cast<cudaStream_t>(cuda_stream) : e->ownStream;
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	}
+	return GSB_OK;
+}
+
 int gsb_get_info(const gsb_engine* e, gsb_info* info) {
 	if (!e || !info) return GSB_ERR_INVALID_ARGUMENT;
 	*info = e->info;
@@ -722,13 +740,12 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 	return GSB_OK;
 }
 
-int gsb_population_evaluate(gsb_engine* e) {
-	if (!e) return GSB_ERR_INVALID_ARGUMENT;
-	if (!e->populationReady) return fail(e, GSB_ERR_STATE, "no resident population: call gsb_population_upload first");
-	try {
-		ensureDevice(e);
-		long long ctas = 0;
-		int launches = 0;
+} // extern "C"
+
+namespace {
+
+// K1 per subset-size class, then K2 (or K3 for the LM evaluator); events ev[2..4] bracket them
+void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 		GSB_CUDA(cudaEventRecord(e->ev[2], e->stream));
 		if (e->cfg.evaluator == GSB_EVAL_LM) {
 			gsb::launchMarkEmpty(e->dOffsets.ptr, e->npop, e->dFitness.ptr, e->dStatus.ptr, e->stream);
@@ -810,6 +827,37 @@ int gsb_population_evaluate(gsb_engine* e) {
 			++launches;
 			GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
 		}
+}
+
+} // namespace
+
+extern "C" {
+
+int gsb_population_enqueue(gsb_engine* e) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->populationReady) return fail(e, GSB_ERR_STATE, "no resident population: call gsb_population_upload first");
+	try {
+		ensureDevice(e);
+		long long ctas = 0;
+		int launches = 0;
+		enqueuePopulation(e, ctas, launches);
+		e->timing.fit_ctas = ctas;
+		e->timing.kernel_launches = launches;
+		e->resultsReady = true;
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	}
+	return GSB_OK;
+}
+
+int gsb_population_evaluate(gsb_engine* e) {
+	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->populationReady) return fail(e, GSB_ERR_STATE, "no resident population: call gsb_population_upload first");
+	try {
+		ensureDevice(e);
+		long long ctas = 0;
+		int launches = 0;
+		enqueuePopulation(e, ctas, launches);
 		GSB_CUDA(cudaStreamSynchronize(e->stream));
 		float msFit = 0.f, msRed = 0.f;
 		GSB_CUDA(cudaEventElapsedTime(&msFit, e->ev[2], e->ev[3]));

@@ -170,6 +170,14 @@ class Evaluator:
     def evaluate_resident(self):
         self._check(self._lib.gsb_population_evaluate(self._h))
 
+    def enqueue_resident(self):
+        """Enqueue only (no synchronisation): K1/K2 (or K3) on the engine's stream."""
+        self._check(self._lib.gsb_population_enqueue(self._h))
+
+    def set_stream(self, cuda_stream):
+        """Run the engine's device work on the caller's cudaStream_t (e.g. torch's current stream)."""
+        self._check(self._lib.gsb_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     def download_results(self, fitness, status):
         self._check(self._lib.gsb_population_download(self._h, fitness, status))
 

@@ -161,6 +161,10 @@ int gsb_prepare(gsb_engine* e);
 
 int gsb_get_info(const gsb_engine* e, gsb_info* info);
 
+/* Run all of this engine's device work on the caller's stream (a cudaStream_t, e.g. the host
+ * framework's current stream) instead of the engine's own; NULL restores the engine's stream. */
+int gsb_set_stream(gsb_engine* e, void* cuda_stream);
+
 /* ---- the hot path -------------------------------------------------------------------------- */
 
 /* Evaluator::evaluate(arma::uvec&) over a batch (the loop of src/GenAlg.cpp:312-325):
@@ -183,6 +187,9 @@ int gsb_evaluate_bitsets(gsb_engine* e, const uint64_t* bitsets, int32_t words_p
  * download copies fitness[npop] / status[npop] back.  gsb_evaluate_indices == the three in a row. */
 int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop);
 int gsb_population_evaluate(gsb_engine* e);
+/* gsb_population_evaluate without the final synchronisation and without the timing record: the
+ * kernels are only enqueued on the engine's stream (see gsb_set_stream). */
+int gsb_population_enqueue(gsb_engine* e);
 int gsb_population_download(gsb_engine* e, double* fitness, int32_t* status);
 
 /* Device addresses of the resident results (fitness: npop doubles, status: npop int32) so that a
