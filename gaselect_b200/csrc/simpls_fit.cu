@@ -11,11 +11,16 @@
 // src/PLSSimpls.cpp:152), so the outer refit with optNComp components (src/PLSEvaluator.cpp:316-317)
 // is column optNComp-1 of a fit with A components and every fit of a chromosome is independent.
 //
-// Data movement: the k(k+1)/2 selected entries of the training set's packed Gram are gathered
-// from HBM/L2 into shared memory once (row-wise, no index decoding); the symmetric matrix-vector
-// product reads the packed triangle conflict-free (consecutive rows start at consecutive
-// triangular numbers, which are distinct modulo 16); held-out rows are read as contiguous column
-// segments of the block copy with lanes = rows and the columns split over the warps.
+// Data movement
+//   * gather: the k(k+1)/2 selected entries of the training set's packed Gram go from HBM/L2
+//     straight into shared memory with 8-byte cp.async (LDGSTS): no register staging, every
+//     thread has all of its copies in flight at once;
+//   * the symmetric matrix-vector product reads the packed triangle conflict-free (consecutive
+//     rows start at consecutive triangular numbers, distinct modulo 16); one thread per row,
+//     four independent accumulators, warp-uniform split into "left of the diagonal band" (own
+//     packed row), the 32-wide band, and "below the band" (column access, lane = row);
+//   * held-out rows: the selected column segments of the block copy are staged with 16-byte
+//     cp.async into the (by then dead) Gram area, then lanes = rows, warps split the columns.
 //
 // Reductions per component: ONE round for {S'w, s0'S, V_j'w (j < comp)} and ONE for {v'v, v'S}.
 // The projections on the stored (orthonormal) loadings are therefore taken from w before the
@@ -27,27 +32,33 @@ namespace gsb {
 
 namespace {
 
-constexpr int kChunk = 8;   // components per prediction pass (accumulators held in registers)
+constexpr int kChunk = 10;  // components per prediction pass (accumulators held in registers)
 constexpr int kDots = 6;    // loadings projected in the same reduction round as S'w and s0'S
-constexpr int kRedMax = 16; // widest reduction (values per thread)
+constexpr int kRedMax = 20; // widest reduction (values per thread)
+constexpr int kMaxWarps = 8;
 
 __device__ __forceinline__ double shflXor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-template <int NWARPS>
-__device__ __forceinline__ void ctaSync() {
-	if (NWARPS > 1) __syncthreads(); else __syncwarp();
+__device__ __forceinline__ void cpAsync8(double* dst, const double* src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src));
+}
+__device__ __forceinline__ void cpAsync16(double* dst, const double* src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src));
+}
+__device__ __forceinline__ void cpAsyncWaitAll() {
+	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Sum NV values over the CTA; every thread receives bitwise-identical totals.
-template <int NWARPS, int NV>
-__device__ __forceinline__ void blockSum(double (&v)[NV], double* red, int& phase) {
+// Sum NV values over the CTA (nw warps); every thread receives bitwise-identical totals.
+template <int NV>
+__device__ __forceinline__ void blockSum(double (&v)[NV], double* red, int& phase, int nw) {
 #pragma unroll
 	for (int m = 16; m >= 1; m >>= 1) {
 #pragma unroll
 		for (int i = 0; i < NV; ++i) v[i] += shflXor(v[i], m);
 	}
-	if (NWARPS > 1) {
-		double* buf = red + phase * (NWARPS * kRedMax);
+	if (nw > 1) {
+		double* buf = red + phase * (kMaxWarps * kRedMax);
 		const int warp = threadIdx.x >> 5;
 		if ((threadIdx.x & 31) == 0) {
 #pragma unroll
@@ -55,11 +66,10 @@ __device__ __forceinline__ void blockSum(double (&v)[NV], double* red, int& phas
 		}
 		__syncthreads();
 #pragma unroll
-		for (int i = 0; i < NV; ++i) {
-			double s = buf[i];
+		for (int i = 0; i < NV; ++i) v[i] = buf[i];
+		for (int w = 1; w < nw; ++w) {
 #pragma unroll
-			for (int w = 1; w < NWARPS; ++w) s += buf[w * NV + i];
-			v[i] = s;
+			for (int i = 0; i < NV; ++i) v[i] += buf[w * NV + i];
 		}
 		phase ^= 1;
 	}
@@ -69,31 +79,32 @@ __host__ __device__ inline int roundUp(int v, int m) { return (v + m - 1) / m * 
 
 // shared-memory carve-up (in doubles)
 struct Carve {
-	int P, S, s0, xm, V, coef, b0, red, pred, sel, total;
+	int P, S, s0, xm, V, coef, b0, red, sel, total;
 };
 
-__host__ __device__ inline Carve carve(int k, int A, int nwarps, bool gramInSmem) {
+__host__ __device__ inline Carve carve(int k, int A, bool gramInSmem) {
 	Carve c;
 	const int Apad = roundUp(A, kChunk);
 	int o = 0;
-	c.P = o; o += gramInSmem ? roundUp(k * (k + 1) / 2, 2) : 0;
+	// packed Gram; afterwards the staging area of the held-out rows (>= one 32-row column per warp)
+	c.P = o; o += gramInSmem ? roundUp(max(k * (k + 1) / 2, kMaxWarps * 32 * (kChunk + 1)), 2) : kMaxWarps * 32 * (kChunk + 1);
 	c.S = o; o += roundUp(k, 2);
 	c.s0 = o; o += roundUp(k, 2);
 	c.xm = o; o += roundUp(k, 2);
 	c.V = o; o += roundUp(A * k, 2);
 	c.coef = o; o += k * Apad;
 	c.b0 = o; o += Apad;
-	c.red = o; o += 2 * nwarps * kRedMax;                // double-buffered
-	c.pred = o; o += (nwarps > 1) ? nwarps * 32 * kChunk : 0; // cross-warp prediction partials
-	c.sel = o; o += roundUp(k, 2) / 2 + 1;               // uint32 column ids
+	c.red = o; o += 2 * kMaxWarps * kRedMax;  // double-buffered
+	c.sel = o; o += roundUp(k, 2) / 2 + 1;    // uint32 column ids
 	c.total = o;
 	return c;
 }
 
-template <int NWARPS, int RPT, bool GSMEM>
-__global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams prm) {
-	constexpr int NT = NWARPS * 32;
+// RPT rows of the k x k system per thread (1 on the shared-memory path: blockDim.x >= k)
+template <int RPT, bool GSMEM>
+__global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParams prm) {
 	extern __shared__ __align__(16) double smem[];
+	const int NT = blockDim.x, NW = NT >> 5;
 
 	const int ci = blockIdx.x % prm.bucketCount;
 	const int fi = blockIdx.x / prm.bucketCount;
@@ -105,7 +116,7 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 	const FitDesc fd = prm.fits[fi];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-	const Carve cv = carve(k, A, NWARPS, GSMEM);
+	const Carve cv = carve(k, A, GSMEM);
 	double* __restrict__ P = smem + cv.P;
 	double* __restrict__ S = smem + cv.S;
 	double* __restrict__ s0s = smem + cv.s0;
@@ -114,24 +125,26 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 	double* __restrict__ coef = smem + cv.coef;
 	double* __restrict__ b0 = smem + cv.b0;
 	double* red = smem + cv.red;
-	double* predBuf = smem + cv.pred;
 	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(smem + cv.sel);
 	int phase = 0;
 
 	// ---- gather (PLS::viewSelectColumns + viewSelectRows, as Gram entries) -----------------
 	for (int i = tid; i < k; i += NT) sel[i] = prm.idx[selBegin + i];
-	ctaSync<NWARPS>();
+	__syncthreads();
 	const double* __restrict__ gsrc = prm.gram + fd.gramOff;
 	if (GSMEM) {
-		// packed row a = entries (a, 0..a); rows are dealt to the warps, four rows in flight per pass
-		for (int a0 = warp * 4; a0 < k; a0 += NWARPS * 4) {
+		// packed row a = entries (a, 0..a); rows are dealt to the warps, lanes cover the columns
+		uint32_t selB[kMaxWarps];
 #pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				const int a = a0 + u;
-				if (a < k) {
-					const double* __restrict__ grow = gsrc + tri(sel[a]);
-					double* __restrict__ prow = P + a * (a + 1) / 2;
-					for (int b = lane; b <= a; b += 32) prow[b] = __ldg(grow + sel[b]);
+		for (int j = 0; j < kMaxWarps; ++j) selB[j] = (lane + 32 * j < k) ? sel[lane + 32 * j] : 0u;
+		for (int a = warp; a < k; a += NW) {
+			const double* __restrict__ grow = gsrc + tri(sel[a]);
+			double* __restrict__ prow = P + a * (a + 1) / 2;
+#pragma unroll
+			for (int j = 0; j < kMaxWarps; ++j) {
+				if (32 * j <= a) {
+					const int b = lane + 32 * j;
+					if (b <= a) cpAsync8(prow + b, grow + selB[j]);
 				}
 			}
 		}
@@ -147,23 +160,18 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 		}
 		for (int i = tid; i < k * Apad; i += NT) coef[i] = 0.0;
 	}
-	ctaSync<NWARPS>();
+	cpAsyncWaitAll();
+	__syncthreads();
 
 	// rows of the k x k system owned by this thread
 	int row[RPT];
 	bool valid[RPT];
-	int rowTri[RPT];
-	unsigned long long rowTriG[RPT];
-	uint32_t rowSel[RPT];
 	double sOwn[RPT], s0Own[RPT];
 #pragma unroll
 	for (int u = 0; u < RPT; ++u) {
 		const int r = tid + u * NT;
 		valid[u] = r < k;
 		row[u] = valid[u] ? r : k - 1;
-		rowTri[u] = row[u] * (row[u] + 1) / 2;
-		rowSel[u] = sel[row[u]];
-		rowTriG[u] = tri(rowSel[u]);
 		sOwn[u] = valid[u] ? S[row[u]] : 0.0;
 		s0Own[u] = valid[u] ? s0s[row[u]] : 0.0;
 	}
@@ -172,30 +180,56 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 	int done = A;
 	for (int comp = 0; comp < A; ++comp) {
 		double w[RPT];
-#pragma unroll
-		for (int u = 0; u < RPT; ++u) w[u] = 0.0;
 		if (GSMEM) {
-			int tc = 0;
-#pragma unroll 4
-			for (int c = 0; c < k; ++c) {
-				const double sc = S[c];
 #pragma unroll
-				for (int u = 0; u < RPT; ++u) {
-					const int addr = (c <= row[u]) ? rowTri[u] + c : tc + row[u];
-					w[u] = fma(P[addr], sc, w[u]);
+			for (int u = 0; u < RPT; ++u) {
+				const int r = row[u];
+				// rows of a warp are consecutive: [rlo, rhi] is warp-uniform
+				const int rlo = min(warp * 32 + u * NT, k - 1);
+				const int rhi = min(rlo + 31, k - 1);
+				const double* __restrict__ pr = P + r * (r + 1) / 2;
+				double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+				int c = 0;
+				for (; c + 3 < rlo; c += 4) { // left of the band: own packed row
+					a0 = fma(pr[c], S[c], a0);
+					a1 = fma(pr[c + 1], S[c + 1], a1);
+					a2 = fma(pr[c + 2], S[c + 2], a2);
+					a3 = fma(pr[c + 3], S[c + 3], a3);
 				}
-				tc += c + 1;
+				for (; c < rlo; ++c) a0 = fma(pr[c], S[c], a0);
+				int tc = rlo * (rlo + 1) / 2;
+				for (; c <= rhi; ++c) {       // the band: either side of the diagonal
+					const double g = (c <= r) ? pr[c] : P[tc + r];
+					a1 = fma(g, S[c], a1);
+					tc += c + 1;
+				}
+				const double* __restrict__ pc = P + r; // below the band: column r of rows c
+				for (; c + 3 < k; c += 4) {
+					const int t1 = tc + c + 1, t2 = t1 + c + 2, t3 = t2 + c + 3;
+					a0 = fma(pc[tc], S[c], a0);
+					a1 = fma(pc[t1], S[c + 1], a1);
+					a2 = fma(pc[t2], S[c + 2], a2);
+					a3 = fma(pc[t3], S[c + 3], a3);
+					tc = t3 + c + 4;
+				}
+				for (; c < k; ++c) {
+					a2 = fma(pc[tc], S[c], a2);
+					tc += c + 1;
+				}
+				w[u] = (a0 + a1) + (a2 + a3);
 			}
 		} else {
-			for (int c = 0; c < k; ++c) {
-				const double sc = S[c];
-				const uint32_t selc = sel[c];
-				const unsigned long long tcg = tri(selc);
 #pragma unroll
-				for (int u = 0; u < RPT; ++u) {
-					const unsigned long long addr = (c <= row[u]) ? rowTriG[u] + selc : tcg + rowSel[u];
-					w[u] = fma(__ldg(gsrc + addr), sc, w[u]);
+			for (int u = 0; u < RPT; ++u) {
+				const uint32_t rs = sel[row[u]];
+				const unsigned long long rt = tri(rs);
+				double a0 = 0.0;
+				for (int c = 0; c < k; ++c) {
+					const uint32_t selc = sel[c];
+					const unsigned long long addr = (c <= row[u]) ? rt + selc : tri(selc) + rs;
+					a0 = fma(__ldg(gsrc + addr), S[c], a0);
 				}
+				w[u] = a0;
 			}
 		}
 		// round 1: tn^2 = S'GS = ||Xc S||^2 (:138), q*tn = s0'S (:148), projections V_j'w
@@ -213,7 +247,7 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 				}
 			}
 		}
-		blockSum<NWARPS, 2 + kDots>(r1, red, phase);
+		blockSum<2 + kDots>(r1, red, phase, NW);
 		if (!(r1[0] >= 1e-50)) { // ||t|| < 1e-25 (NORM_TOL, :16,:141-143); also catches NaN / negative rounding
 			done = comp;
 			break;
@@ -241,7 +275,7 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 					for (int u = 0; u < RPT; ++u) if (valid[u]) d[j] = fma(V[(j0 + j) * k + row[u]], w[u], d[j]);
 				}
 			}
-			blockSum<NWARPS, 8>(d, red, phase);
+			blockSum<8>(d, red, phase, NW);
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
 				if (j0 + j < comp) {
@@ -252,10 +286,11 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 		}
 		// cumulative coefficients from S BEFORE deflation (:152-156); v = X't has the factor 1/tn (:145-147)
 		const double f = q / tn;
+		const double rtn = 1.0 / tn;
 		double r2[2] = {0.0, 0.0};
 #pragma unroll
 		for (int u = 0; u < RPT; ++u) {
-			v[u] = v[u] / tn;
+			v[u] = v[u] * rtn;
 			if (valid[u]) {
 				double* cr = coef + row[u] * Apad;
 				cr[comp] = ((comp > 0) ? cr[comp - 1] : 0.0) + sOwn[u] * f;
@@ -264,18 +299,18 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 			}
 		}
 		// round 2: deflate S, normalise v (:160, :70-88)
-		blockSum<NWARPS, 2>(r2, red, phase);
+		blockSum<2>(r2, red, phase, NW);
 		const double dd = r2[1] / r2[0];
-		const double vn = sqrt(r2[0]);
+		const double rvn = 1.0 / sqrt(r2[0]);
 #pragma unroll
 		for (int u = 0; u < RPT; ++u) {
 			if (valid[u]) {
 				sOwn[u] = fma(-v[u], dd, sOwn[u]);
 				S[row[u]] = sOwn[u];
-				V[comp * k + row[u]] = v[u] / vn;
+				V[comp * k + row[u]] = v[u] * rvn;
 			}
 		}
-		ctaSync<NWARPS>();
+		__syncthreads();
 	}
 	if (done < A) {
 		// the reference throws std::underflow_error here; poison the remaining components so
@@ -286,7 +321,7 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 			if (valid[u]) for (int a = done; a < A; ++a) coef[row[u] * Apad + a] = nan;
 		}
 	}
-	ctaSync<NWARPS>();
+	__syncthreads();
 
 	// ---- intercepts b0[a] = ym - xm'coef[:,a] (:162) --------------------------------------
 	for (int a0 = 0; a0 < A; a0 += kChunk) {
@@ -299,7 +334,7 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 #pragma unroll
 			for (int u = 0; u < kChunk; ++u) acc[u] = fma(x, cr[u], acc[u]);
 		}
-		blockSum<NWARPS, kChunk>(acc, red, phase);
+		blockSum<kChunk>(acc, red, phase, NW);
 		if (tid < kChunk) {
 			double mine = 0.0;
 #pragma unroll
@@ -307,7 +342,7 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 			b0[a0 + tid] = fd.ym - mine;
 		}
 	}
-	ctaSync<NWARPS>();
+	__syncthreads();
 
 	if (prm.coefOut != nullptr) { // gsb_simpls: raw coefficients of this fit
 		for (int i = tid; i < k * A; i += NT) prm.coefOut[i] = coef[(i % k) * Apad + (i / k)];
@@ -315,8 +350,11 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 	}
 
 	// ---- held-out prediction and statistics -------------------------------------------------
-	// lanes = rows of the block (coalesced column segments), warps split the selected columns;
-	// the warps' partial predictions meet in shared memory and warp 0 finishes the statistics.
+	// The Gram area is dead now: it stages [column pass][32-row slab] tiles of the held-out block
+	// (16-byte cp.async, everything in flight at once) and, at its end, the warps' partial sums.
+	const int stageCap = GSMEM ? max(k * (k + 1) / 2, kMaxWarps * 32 * (kChunk + 1)) : kMaxWarps * 32 * (kChunk + 1);
+	double* __restrict__ part = P + stageCap - NW * 32 * kChunk; // [warp][u][lane]
+	const int colsPerPass = max(1, min(k, (stageCap - NW * 32 * kChunk) / 32));
 	for (int t = 0; t < fd.taskCount; ++t) {
 		const TaskDesc td = prm.tasks[fd.taskBegin + t];
 		const BlockDesc bd = prm.blocks[td.block];
@@ -329,42 +367,42 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 			for (int r0 = 0; r0 < bd.nrows; r0 += 32) {
 				const int r = r0 + lane;
 				const bool live = r < bd.nrows;
-				const double* __restrict__ zr = zb + (live ? r : 0);
+				const int slab = min(32, bd.ld - r0); // multiple of 4 rows, zero padded in the block copy
 				double acc[kChunk];
 #pragma unroll
 				for (int u = 0; u < kChunk; ++u) acc[u] = 0.0;
-				int c = warp;
-				for (; c + 3 * NWARPS < k; c += 4 * NWARPS) {
-					double x[4];
-#pragma unroll
-					for (int j = 0; j < 4; ++j) x[j] = __ldg(zr + static_cast<size_t>(sel[c + j * NWARPS]) * bd.ld);
-#pragma unroll
-					for (int j = 0; j < 4; ++j) {
-						const double* cr = coef + (c + j * NWARPS) * Apad + a0;
-#pragma unroll
-						for (int u = 0; u < kChunk; ++u) acc[u] = fma(x[j], cr[u], acc[u]);
+				for (int c0 = 0; c0 < k; c0 += colsPerPass) {
+					const int nc = min(colsPerPass, k - c0);
+					const int quads = slab >> 1; // 16-byte pieces per column
+					for (int e = tid; e < nc * quads; e += NT) {
+						const int c = e / quads, piece = e - c * quads;
+						cpAsync16(P + c * 32 + piece * 2, zb + static_cast<size_t>(sel[c0 + c]) * bd.ld + r0 + piece * 2);
 					}
-				}
-				for (; c < k; c += NWARPS) {
-					const double x = __ldg(zr + static_cast<size_t>(sel[c]) * bd.ld);
-					const double* cr = coef + c * Apad + a0;
+					cpAsyncWaitAll();
+					__syncthreads();
+					if (lane < slab) {
+						for (int c = warp; c < nc; c += NW) {
+							const double x = P[c * 32 + lane];
+							const double* cr = coef + (c0 + c) * Apad + a0;
 #pragma unroll
-					for (int u = 0; u < kChunk; ++u) acc[u] = fma(x, cr[u], acc[u]);
+							for (int u = 0; u < kChunk; ++u) acc[u] = fma(x, cr[u], acc[u]);
+						}
+					}
+					__syncthreads(); // staging area free again
 				}
-				if (NWARPS > 1) {
-					__syncthreads(); // previous pass has been consumed
+				if (NW > 1) {
 #pragma unroll
-					for (int u = 0; u < kChunk; ++u) predBuf[(warp * kChunk + u) * 32 + lane] = acc[u];
+					for (int u = 0; u < kChunk; ++u) part[(warp * kChunk + u) * 32 + lane] = acc[u];
 					__syncthreads();
 					if (warp == 0) {
 #pragma unroll
 						for (int u = 0; u < kChunk; ++u) {
-							double s = predBuf[u * 32 + lane];
-#pragma unroll
-							for (int w2 = 1; w2 < NWARPS; ++w2) s += predBuf[(w2 * kChunk + u) * 32 + lane];
+							double s = part[u * 32 + lane];
+							for (int w2 = 1; w2 < NW; ++w2) s += part[(w2 * kChunk + u) * 32 + lane];
 							acc[u] = s;
 						}
 					}
+					__syncthreads();
 				}
 				if (warp == 0 && live) {
 					const double y = __ldg(ycol + r);
@@ -404,58 +442,40 @@ __global__ void __launch_bounds__(NWARPS * 32) simplsFitKernel(const FitParams p
 	}
 }
 
-template <int NWARPS, int RPT, bool GSMEM>
-cudaError_t launchOne(const FitParams& prm, int kMax, int A, cudaStream_t stream, long long* ctas) {
-	const Carve cv = carve(kMax, A, NWARPS, GSMEM);
+template <int RPT, bool GSMEM>
+cudaError_t launchOne(const FitParams& prm, int kMax, int A, int threads, cudaStream_t stream, long long* ctas) {
+	const Carve cv = carve(kMax, A, GSMEM);
 	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double);
-	cudaError_t err = cudaFuncSetAttribute(simplsFitKernel<NWARPS, RPT, GSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	cudaError_t err = cudaFuncSetAttribute(simplsFitKernel<RPT, GSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                       static_cast<int>(bytes));
 	if (err != cudaSuccess) return err;
 	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
 	if (grid <= 0) return cudaSuccess;
 	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-	simplsFitKernel<NWARPS, RPT, GSMEM><<<static_cast<unsigned>(grid), NWARPS * 32, bytes, stream>>>(prm);
+	simplsFitKernel<RPT, GSMEM><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm);
 	if (ctas) *ctas += grid;
 	return cudaGetLastError();
 }
 
-int warpsFor(int kMax) {
-	if (kMax <= 64) return 1;
-	if (kMax <= 128) return 2;
-	if (kMax <= 256) return 4;
-	return 8;
-}
-
 } // namespace
 
-int fitKernelSharedBytes(int k, int A) { return carve(k, A, warpsFor(k), true).total * static_cast<int>(sizeof(double)); }
+int fitKernelSharedBytes(int k, int A) { return carve(k, A, true).total * static_cast<int>(sizeof(double)); }
 
 // largest k whose packed Gram still fits in shared memory next to the loadings
 int fitKernelMaxK(int A, int smemLimit) {
 	int k = 1;
-	while (k < 1024 && carve(k + 1, (A < k + 1) ? A : k + 1, warpsFor(k + 1), true).total * 8 <= smemLimit) ++k;
+	while (k < kMaxWarps * 32 && carve(k + 1, (A < k + 1) ? A : k + 1, true).total * 8 <= smemLimit) ++k;
 	return k;
 }
 
 // One launch for a bucket of chromosomes whose subset sizes are all <= kMax.
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
 	const int Ak = (A < kMax) ? A : kMax;
-	const bool fits = carve(kMax, Ak, warpsFor(kMax), true).total * 8 <= smemLimit;
-	if (fits) {
-		if (kMax <= 32) return launchOne<1, 1, true>(prm, kMax, Ak, stream, ctas);
-		if (kMax <= 64) return launchOne<1, 2, true>(prm, kMax, Ak, stream, ctas);
-		if (kMax <= 128) return launchOne<2, 2, true>(prm, kMax, Ak, stream, ctas);
-		if (kMax <= 256) return launchOne<4, 2, true>(prm, kMax, Ak, stream, ctas);
-		return launchOne<8, 4, true>(prm, kMax, Ak, stream, ctas);
+	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true).total * 8 <= smemLimit) {
+		return launchOne<1, true>(prm, kMax, Ak, roundUp(kMax, 32), stream, ctas); // one thread per row
 	}
-	if (kMax <= 256) {
-		if (carve(kMax, Ak, 4, false).total * 8 > smemLimit) return cudaErrorInvalidValue;
-		return launchOne<4, 2, false>(prm, kMax, Ak, stream, ctas);
-	}
-	if (carve(kMax, Ak, 8, false).total * 8 > smemLimit) return cudaErrorInvalidValue;
-	if (kMax <= 512) return launchOne<8, 2, false>(prm, kMax, Ak, stream, ctas);
-	if (kMax <= 1024) return launchOne<8, 4, false>(prm, kMax, Ak, stream, ctas);
-	return cudaErrorInvalidValue;
+	if (kMax > 4 * kMaxWarps * 32 || carve(kMax, Ak, false).total * 8 > smemLimit) return cudaErrorInvalidValue;
+	return launchOne<4, false>(prm, kMax, Ak, kMaxWarps * 32, stream, ctas);         // Gram read in place (L2)
 }
 
 } // namespace gsb

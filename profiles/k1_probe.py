@@ -1,5 +1,5 @@
 """Small driver for profiling K1: one population of fixed subset size on the cfg3 data set.
-usage: python tools/k1_probe.py K [POP] [STEPS]"""
+usage: python profiles/k1_probe.py K [POP] [STEPS]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
