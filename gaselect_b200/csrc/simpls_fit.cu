@@ -442,6 +442,348 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 	}
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: A <= AREG components, k <= 256.  The per-row state -- S, s0, xm, the stored loadings
+// V[0..A) and the cumulative coefficients -- is only ever touched by the row's own thread
+// (src/PLSSimpls.cpp:150-162 are all row-wise), so it lives in registers; shared memory holds the
+// packed Gram, S (broadcast operand of the matrix-vector product) and the reduction scratch.
+// That halves the footprint of a fit and doubles the CTAs resident per SM.  After the last
+// component the Gram area is dead and takes the coefficients and the held-out staging tiles.
+struct FastCarve {
+	int P, S, red, sel, total;
+	int coef, part, stage, stageCols; // inside the P area, after the fit
+};
+
+__host__ __device__ inline FastCarve fastCarve(int k, int A, int nw) {
+	FastCarve c;
+	const int Apad = roundUp(A, 2);
+	const int ntri = k * (k + 1) / 2;
+	const int coefD = k * Apad, partD = (nw > 1) ? nw * 32 * kChunk : 0;
+	const int minStage = 32 * min(k, 8);
+	const int area = roundUp(max(ntri, coefD + partD + minStage), 2);
+	int o = 0;
+	c.P = o; o += area;
+	c.S = o; o += roundUp(k, 2);
+	c.red = o; o += 2 * kMaxWarps * kRedMax;
+	c.sel = o; o += roundUp(k, 2) / 2 + 1;
+	c.total = o;
+	c.coef = 0;
+	c.part = coefD;
+	c.stage = coefD + partD;
+	c.stageCols = (area - c.stage) / 32;
+	return c;
+}
+
+template <int AREG>
+__global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams prm) {
+	extern __shared__ __align__(16) double smem[];
+	const int NT = blockDim.x, NW = NT >> 5;
+
+	const int ci = blockIdx.x % prm.bucketCount;
+	const int fi = blockIdx.x / prm.bucketCount;
+	const int chrom = prm.bucket[ci];
+	const uint32_t selBegin = prm.offsets[chrom];
+	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
+	const int A = min(prm.maxNComp, k);
+	const int Apad = roundUp(A, 2);
+	const FitDesc fd = prm.fits[fi];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	const FastCarve cv = fastCarve(k, A, NW);
+	double* __restrict__ P = smem + cv.P;
+	double* __restrict__ S = smem + cv.S;
+	double* red = smem + cv.red;
+	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(smem + cv.sel);
+	int phase = 0;
+
+	// ---- gather ------------------------------------------------------------------------------
+	for (int i = tid; i < k; i += NT) sel[i] = prm.idx[selBegin + i];
+	__syncthreads();
+	const double* __restrict__ gsrc = prm.gram + fd.gramOff;
+	{
+		uint32_t selB[kMaxWarps];
+#pragma unroll
+		for (int j = 0; j < kMaxWarps; ++j) selB[j] = (lane + 32 * j < k) ? sel[lane + 32 * j] : 0u;
+		for (int a = warp; a < k; a += NW) {
+			const double* __restrict__ grow = gsrc + tri(sel[a]);
+			double* __restrict__ prow = P + a * (a + 1) / 2;
+#pragma unroll
+			for (int j = 0; j < kMaxWarps; ++j) {
+				if (32 * j <= a) {
+					const int b = lane + 32 * j;
+					if (b <= a) cpAsync8(prow + b, grow + selB[j]);
+				}
+			}
+		}
+	}
+	const bool valid = tid < k;
+	const int r = valid ? tid : k - 1;
+	double sOwn, s0Own, xmOwn;
+	{
+		const uint32_t sr = sel[r];
+		s0Own = __ldg(prm.s0 + static_cast<size_t>(fi) * prm.p + sr);
+		xmOwn = __ldg(prm.xm + static_cast<size_t>(fi) * prm.p + sr);
+		sOwn = s0Own;
+		if (valid) S[r] = sOwn;
+	}
+	double vOwn[AREG], cOwn[AREG];
+#pragma unroll
+	for (int j = 0; j < AREG; ++j) { vOwn[j] = 0.0; cOwn[j] = 0.0; }
+	cpAsyncWaitAll();
+	__syncthreads();
+
+	// rows of a warp are consecutive: [rlo, rhi] is warp-uniform
+	const int rlo = min(warp * 32, k - 1);
+	const int rhi = min(rlo + 31, k - 1);
+	const double* __restrict__ pr = P + r * (r + 1) / 2;
+	const double* __restrict__ pc = P + r;
+	const int triLo = rlo * (rlo + 1) / 2;
+
+	// ---- SIMPLS components -------------------------------------------------------------------
+	int done = A;
+	double cum = 0.0;
+#pragma unroll 1
+	for (int comp = 0; comp < A; ++comp) {
+		double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+		int c = 0;
+		for (; c + 7 < rlo; c += 8) { // left of the band: own packed row
+			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
+			const double2 s45 = *reinterpret_cast<const double2*>(S + c + 4);
+			const double2 s67 = *reinterpret_cast<const double2*>(S + c + 6);
+			a0 = fma(pr[c], s01.x, a0);
+			a1 = fma(pr[c + 1], s01.y, a1);
+			a2 = fma(pr[c + 2], s23.x, a2);
+			a3 = fma(pr[c + 3], s23.y, a3);
+			a0 = fma(pr[c + 4], s45.x, a0);
+			a1 = fma(pr[c + 5], s45.y, a1);
+			a2 = fma(pr[c + 6], s67.x, a2);
+			a3 = fma(pr[c + 7], s67.y, a3);
+		}
+		for (; c < rlo; ++c) a0 = fma(pr[c], S[c], a0);
+		int tc = triLo;
+		for (; c + 1 <= rhi; c += 2) { // the band: either side of the diagonal
+			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+			const int t1 = tc + c + 1;
+			const double g0 = (c <= r) ? pr[c] : pc[tc];
+			const double g1 = (c + 1 <= r) ? pr[c + 1] : pc[t1];
+			a0 = fma(g0, s01.x, a0);
+			a1 = fma(g1, s01.y, a1);
+			tc = t1 + c + 2;
+		}
+		for (; c <= rhi; ++c) {
+			const double g = (c <= r) ? pr[c] : pc[tc];
+			a2 = fma(g, S[c], a2);
+			tc += c + 1;
+		}
+		for (; c + 7 < k; c += 8) {   // below the band: column r of rows c
+			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
+			const double2 s45 = *reinterpret_cast<const double2*>(S + c + 4);
+			const double2 s67 = *reinterpret_cast<const double2*>(S + c + 6);
+			const int t1 = tc + c + 1, t2 = t1 + c + 2, t3 = t2 + c + 3, t4 = t3 + c + 4;
+			const int t5 = t4 + c + 5, t6 = t5 + c + 6, t7 = t6 + c + 7;
+			a0 = fma(pc[tc], s01.x, a0);
+			a1 = fma(pc[t1], s01.y, a1);
+			a2 = fma(pc[t2], s23.x, a2);
+			a3 = fma(pc[t3], s23.y, a3);
+			a0 = fma(pc[t4], s45.x, a0);
+			a1 = fma(pc[t5], s45.y, a1);
+			a2 = fma(pc[t6], s67.x, a2);
+			a3 = fma(pc[t7], s67.y, a3);
+			tc = t7 + c + 8;
+		}
+		for (; c < k; ++c) {
+			a3 = fma(pc[tc], S[c], a3);
+			tc += c + 1;
+		}
+		const double w = (a0 + a1) + (a2 + a3);
+
+		// round 1: tn^2 = S'GS (:138), q*tn = s0'S (:148), projections V_j'w
+		double r1[2 + kDots];
+#pragma unroll
+		for (int i = 0; i < 2 + kDots; ++i) r1[i] = 0.0;
+		if (valid) {
+			r1[0] = sOwn * w;
+			r1[1] = s0Own * sOwn;
+#pragma unroll
+			for (int j = 0; j < kDots; ++j) if (j < comp) r1[2 + j] = vOwn[j] * w;
+		}
+		blockSum<2 + kDots>(r1, red, phase, NW);
+		if (!(r1[0] >= 1e-50)) { // ||t|| < 1e-25 (NORM_TOL, :16,:141-143); also NaN / negative rounding
+			done = comp;
+			break;
+		}
+		const double tn = sqrt(r1[0]);
+		const double rtn = 1.0 / tn;
+		const double q = r1[1] * rtn;
+		double v = w;
+#pragma unroll
+		for (int j = 0; j < kDots; ++j) if (j < comp) v = fma(-vOwn[j], r1[2 + j], v);
+		if (AREG > kDots && comp > kDots) { // loadings kDots .. comp-1: one more round
+			double d[AREG - kDots > 0 ? AREG - kDots : 1];
+#pragma unroll
+			for (int j = kDots; j < AREG; ++j) d[j - kDots] = (valid && j < comp) ? vOwn[j] * w : 0.0;
+			blockSum<(AREG - kDots > 0 ? AREG - kDots : 1)>(d, red, phase, NW);
+#pragma unroll
+			for (int j = kDots; j < AREG; ++j) if (j < comp) v = fma(-vOwn[j], d[j - kDots], v);
+		}
+		// cumulative coefficients from S BEFORE deflation (:152-156); v = X't carries 1/tn (:145-147)
+		v *= rtn;
+		cum += sOwn * (q * rtn);
+		double r2[2];
+		r2[0] = valid ? v * v : 0.0;
+		r2[1] = valid ? v * sOwn : 0.0;
+		blockSum<2>(r2, red, phase, NW); // round 2: deflate S, normalise v (:160, :70-88)
+		const double dd = r2[1] / r2[0];
+		const double rvn = rsqrt(r2[0]);
+		sOwn = fma(-v, dd, sOwn);
+		if (valid) S[r] = sOwn;
+#pragma unroll
+		for (int j = 0; j < AREG; ++j) {
+			if (j == comp) { vOwn[j] = v * rvn; cOwn[j] = cum; }
+		}
+		__syncthreads();
+	}
+	// the reference throws std::underflow_error: poison the remaining components so that the
+	// epilogue reports GSB_STATUS_UNDERFLOW where the reference would have thrown
+#pragma unroll
+	for (int j = 0; j < AREG; ++j) if (j >= done) cOwn[j] = __longlong_as_double(0x7ff8000000000000LL);
+
+	// ---- coefficients to the (dead) Gram area, intercepts b0[a] = ym - xm'coef[:,a] (:162) ----
+	double* __restrict__ coef = P + cv.coef;
+	__syncthreads();
+	if (valid) {
+#pragma unroll
+		for (int j = 0; j < AREG; ++j) if (j < Apad) coef[r * Apad + j] = (j < A) ? cOwn[j] : 0.0;
+	}
+	double b0v[AREG];
+#pragma unroll
+	for (int j = 0; j < AREG; ++j) b0v[j] = (valid && j < A) ? xmOwn * cOwn[j] : 0.0;
+	blockSum<AREG>(b0v, red, phase, NW);
+#pragma unroll
+	for (int j = 0; j < AREG; ++j) b0v[j] = fd.ym - b0v[j];
+	__syncthreads();
+
+	if (prm.coefOut != nullptr) { // gsb_simpls: raw coefficients of this fit
+		for (int i = tid; i < k * A; i += NT) prm.coefOut[i] = coef[(i % k) * Apad + (i / k)];
+		if (tid == 0) {
+#pragma unroll
+			for (int j = 0; j < AREG; ++j) if (j < A) prm.coefOut[k * A + j] = b0v[j];
+		}
+	}
+
+	// ---- held-out prediction and statistics -------------------------------------------------
+	double* __restrict__ part = P + cv.part;   // [warp][u][lane]
+	double* __restrict__ stage = P + cv.stage; // [column][32 rows]
+	const int colsPerPass = max(1, min(k, cv.stageCols));
+	for (int t = 0; t < fd.taskCount; ++t) {
+		const TaskDesc td = prm.tasks[fd.taskBegin + t];
+		const BlockDesc bd = prm.blocks[td.block];
+		const double* __restrict__ zb = prm.zpool + bd.zOff;
+		const double* __restrict__ ycol = zb + static_cast<size_t>(prm.p) * bd.ld;
+		double st[2 * AREG];
+#pragma unroll
+		for (int u = 0; u < 2 * AREG; ++u) st[u] = 0.0;
+		for (int r0 = 0; r0 < bd.nrows; r0 += 32) {
+			const int tr = r0 + lane;
+			const bool live = tr < bd.nrows;
+			const int slab = min(32, bd.ld - r0); // multiple of 4 rows, zero padded in the block copy
+			double acc[AREG];
+#pragma unroll
+			for (int u = 0; u < AREG; ++u) acc[u] = 0.0;
+			for (int c0 = 0; c0 < k; c0 += colsPerPass) {
+				const int nc = min(colsPerPass, k - c0);
+				const int pieces = slab >> 1; // 16-byte pieces per column
+				for (int e = tid; e < nc * pieces; e += NT) {
+					const int c = e / pieces, piece = e - c * pieces;
+					cpAsync16(stage + c * 32 + piece * 2, zb + static_cast<size_t>(sel[c0 + c]) * bd.ld + r0 + piece * 2);
+				}
+				cpAsyncWaitAll();
+				__syncthreads();
+				if (lane < slab) {
+					for (int c = warp; c < nc; c += NW) {
+						const double x = stage[c * 32 + lane];
+						const double* cr = coef + (c0 + c) * Apad;
+#pragma unroll
+						for (int u = 0; u < AREG; u += 2) {
+							if (u < Apad) {
+								const double2 cc = *reinterpret_cast<const double2*>(cr + u);
+								acc[u] = fma(x, cc.x, acc[u]);
+								if (u + 1 < AREG) acc[u + 1] = fma(x, cc.y, acc[u + 1]);
+							}
+						}
+					}
+				}
+				__syncthreads(); // staging area free again
+			}
+			if (NW > 1) {
+#pragma unroll
+				for (int u = 0; u < AREG; ++u) part[(warp * kChunk + u) * 32 + lane] = acc[u];
+				__syncthreads();
+				if (warp == 0) {
+#pragma unroll
+					for (int u = 0; u < AREG; ++u) {
+						double s = part[u * 32 + lane];
+						for (int w2 = 1; w2 < NW; ++w2) s += part[(w2 * kChunk + u) * 32 + lane];
+						acc[u] = s;
+					}
+				}
+				__syncthreads();
+			}
+			if (warp == 0 && live) {
+				const double y = __ldg(ycol + tr);
+#pragma unroll
+				for (int u = 0; u < AREG; ++u) {
+					const double e = y - (acc[u] + b0v[u]);
+					st[u] += e;
+					st[AREG + u] = fma(e, e, st[AREG + u]);
+				}
+			}
+		}
+		if (warp == 0) {
+#pragma unroll
+			for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+				for (int u = 0; u < 2 * AREG; ++u) st[u] += shflXor(st[u], m);
+			}
+			if (lane < A) {
+				double se = 0.0, see = 0.0;
+#pragma unroll
+				for (int u = 0; u < AREG; ++u) {
+					if (u == lane) { se = st[u]; see = st[AREG + u]; }
+				}
+				if (td.kind == 0) {
+					// mean squared error of prediction for this fold (src/PLSEvaluator.cpp:266-268)
+					prm.mse[(static_cast<size_t>(chrom) * prm.innerDests + td.dest) * prm.maxNComp + lane] =
+						see / static_cast<double>(bd.nrows);
+				} else {
+					double* o = prm.ostat + ((static_cast<size_t>(chrom) * prm.outerDests + td.dest) * prm.maxNComp + lane) * 2;
+					o[0] = se;
+					o[1] = see;
+				}
+			}
+		}
+	}
+}
+
+template <int AREG>
+cudaError_t launchFast(const FitParams& prm, int kMax, int A, cudaStream_t stream, long long* ctas) {
+	const int threads = roundUp(kMax, 32);
+	const size_t bytes = static_cast<size_t>(fastCarve(kMax, A, threads / 32).total) * sizeof(double);
+	cudaError_t err = cudaFuncSetAttribute(simplsFitFast<AREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+	if (err != cudaSuccess) return err;
+	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
+	if (grid <= 0) return cudaSuccess;
+	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
+	simplsFitFast<AREG><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm);
+	if (ctas) *ctas += grid;
+	return cudaGetLastError();
+}
+
+constexpr int kFastComponents = 10;
+
 template <int RPT, bool GSMEM>
 cudaError_t launchOne(const FitParams& prm, int kMax, int A, int threads, cudaStream_t stream, long long* ctas) {
 	const Carve cv = carve(kMax, A, GSMEM);
@@ -471,6 +813,10 @@ int fitKernelMaxK(int A, int smemLimit) {
 // One launch for a bucket of chromosomes whose subset sizes are all <= kMax.
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
 	const int Ak = (A < kMax) ? A : kMax;
+	if (Ak <= kFastComponents && kMax <= kMaxWarps * 32 &&
+	    fastCarve(kMax, Ak, roundUp(kMax, 32) / 32).total * 8 <= smemLimit) {
+		return launchFast<kFastComponents>(prm, kMax, Ak, stream, ctas); // per-row state in registers
+	}
 	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true).total * 8 <= smemLimit) {
 		return launchOne<1, true>(prm, kMax, Ak, roundUp(kMax, 32), stream, ctas); // one thread per row
 	}
