@@ -80,6 +80,7 @@ SIGNATURES = {
     "gsb_population_download": (C.c_int, [_H, _f64p, _i32p]),
     "gsb_population_device_results": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "gsb_last_timing": (C.c_int, [_H, C.POINTER(Timing)]),
+    "gsb_debug_trace": (C.c_int, [_H, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), C.c_int32]),
     "gsb_simpls": (C.c_int, [_H, _u32p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, _f64p, _f64p]),
     "gsb_rng_stream": (C.c_int, [_u32p, C.c_int32, _u32p]),
     "gsb_shuffle_all": (C.c_int, [_u32p, C.c_int32, C.c_int32, _u32p]),

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -133,6 +134,7 @@ struct gsb_engine {
 	DeviceArray<gsb::BlockDesc> blocks;
 	DeviceArray<int> outerRows;
 	double ymAllRows = 0.0;
+	int maxTasks = 0, maxBlockLd = 0;
 
 	// resident population
 	int npop = 0, kMaxPop = 0, tableA = 1;
@@ -144,6 +146,7 @@ struct gsb_engine {
 	PinnedArray<uint32_t> hIdx, hOffsets;
 	PinnedArray<int> hBucket, hStatus;
 	PinnedArray<double> hFitness;
+	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
 
 	gsb_info info;
@@ -174,6 +177,7 @@ int failCuda(gsb_engine* e, const CudaFailure& f) {
 void releaseDevice(gsb_engine* e) {
 	e->zpool.release(); e->gram.release(); e->s0.release(); e->xm.release();
 	e->fits.release(); e->tasks.release(); e->blocks.release(); e->outerRows.release();
+	e->traceBuf.release();
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
@@ -202,6 +206,10 @@ void ensureDevice(gsb_engine* e) {
 	GSB_CUDA(cudaStreamCreateWithFlags(&e->ownStream, cudaStreamNonBlocking));
 	if (!e->callerStream) e->stream = e->ownStream;
 	for (int i = 0; i < 6; ++i) GSB_CUDA(cudaEventCreate(&e->ev[i]));
+	if (std::getenv("GSB_TRACE")) { // profiling aid: K1 stamps clock64() at its phase boundaries
+		e->traceBuf.reserve(64);
+		GSB_CUDA(cudaMemset(e->traceBuf.ptr, 0, 64 * sizeof(long long)));
+	}
 	e->deviceReady = true;
 }
 
@@ -409,6 +417,10 @@ void prepareDevice(gsb_engine* e) {
 		tdesc[t].dest = plan.tasks[t].dest;
 		tdesc[t].pad = 0;
 	}
+	e->maxTasks = 0;
+	e->maxBlockLd = 0;
+	for (int f = 0; f < nfits; ++f) e->maxTasks = std::max(e->maxTasks, plan.fits[static_cast<size_t>(f)].taskCount);
+	for (size_t t = 0; t < plan.tasks.size(); ++t) e->maxBlockLd = std::max(e->maxBlockLd, bdesc[static_cast<size_t>(plan.tasks[t].block)].ld);
 	e->fits.upload(fdesc, e->stream);
 	e->tasks.upload(tdesc, e->stream);
 	e->blocks.upload(bdesc, e->stream);
@@ -797,6 +809,9 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.mse = e->dMse.ptr;
 				prm.ostat = e->dOstat.ptr;
 				prm.coefOut = nullptr;
+			prm.trace = e->traceBuf.ptr;
+			prm.maxTasks = e->maxTasks;
+			prm.maxBlockLd = e->maxBlockLd;
 				GSB_CUDA(gsb::launchFitKernel(prm, e->buckets[b].kMax, e->tableA, e->smemLimit, e->stream, &ctas));
 				++launches;
 			}
@@ -952,6 +967,20 @@ int gsb_evaluate_bitsets(gsb_engine* e, const uint64_t* bitsets, int32_t words_p
 	return gsb_evaluate_indices(e, idx.data(), offsets.data(), npop, fitness, status);
 }
 
+int gsb_debug_trace(gsb_engine* e, int64_t* out, int32_t n) {
+	if (!e || !out || n < 0) return GSB_ERR_INVALID_ARGUMENT;
+	for (int i = 0; i < n; ++i) out[i] = 0;
+	if (!e->traceBuf.ptr) return GSB_OK;
+	try {
+		ensureDevice(e);
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		GSB_CUDA(cudaMemcpy(out, e->traceBuf.ptr, sizeof(long long) * static_cast<size_t>(n < 64 ? n : 64), cudaMemcpyDeviceToHost));
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	}
+	return GSB_OK;
+}
+
 int gsb_last_timing(const gsb_engine* e, gsb_timing* t) {
 	if (!e || !t) return GSB_ERR_INVALID_ARGUMENT;
 	*t = e->timing;
@@ -1038,7 +1067,7 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
 		prm.fits = dFit.ptr; prm.tasks = nullptr; prm.blocks = nullptr;
 		prm.idx = dIdx.ptr; prm.offsets = dOff.ptr; prm.bucket = dBucket.ptr; prm.bucketCount = 1; prm.nfits = 1;
 		prm.p = k; prm.maxNComp = A; prm.innerDests = 0; prm.outerDests = 0;
-		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr;
+		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr; prm.trace = nullptr; prm.maxTasks = 0; prm.maxBlockLd = 0;
 		GSB_CUDA(gsb::launchFitKernel(prm, k, A, e->smemLimit, e->stream, nullptr));
 		std::vector<double> out(static_cast<size_t>(k) * A + A);
 		GSB_CUDA(cudaMemcpyAsync(out.data(), dOut.ptr, out.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));

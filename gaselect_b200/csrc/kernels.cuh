@@ -60,6 +60,9 @@ struct FitParams {
 	double* mse;             // [chrom][innerDest][maxNComp]
 	double* ostat;           // [chrom][outerDest][maxNComp][2] = (sum e, sum e^2)
 	double* coefOut;         // optional (gsb_simpls): [k x A] + A intercepts for fit 0 / bucket[0]
+	long long* trace;        // optional (profiling): clock64() stamps of one CTA per launch
+	int maxTasks;            // most prediction tasks any fit has
+	int maxBlockLd;          // largest padded row count of a held-out block
 };
 
 struct ReduceParams {

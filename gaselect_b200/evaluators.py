@@ -134,6 +134,12 @@ class Evaluator:
         self._check(self._lib.gsb_last_timing(self._h, C.byref(t)))
         return t.as_dict()
 
+    def debug_trace(self, n=64):
+        """clock64() stamps of one K1 CTA (profiling aid, needs GSB_TRACE=1 in the environment)."""
+        out = np.zeros(n, dtype=np.int64)
+        self._check(self._lib.gsb_debug_trace(self._h, out, n))
+        return out
+
     def evaluate_population(self, subsets):
         """fitness, status of every subset; one engine call (src/GenAlg.cpp:312-325)."""
         idx, offsets = _capi.to_csr(subsets)

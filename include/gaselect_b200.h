@@ -198,6 +198,11 @@ int gsb_population_device_results(gsb_engine* e, void** d_fitness, void** d_stat
 
 int gsb_last_timing(const gsb_engine* e, gsb_timing* t);
 
+/* Profiling aid: with GSB_TRACE set in the environment when the engine first touches the device, one
+ * CTA of every K1 launch stamps clock64() at its phase boundaries; this returns the (up to 64)
+ * stamps of the most recent launch.  All zeros when tracing is off. */
+int gsb_debug_trace(gsb_engine* e, int64_t* out, int32_t n);
+
 /* The hidden C_simpls entry (src/GenAlg.cpp:351-371): SIMPLS coefficients of ONE fit on the
  * device.  cols: k ascending column indices; rows: training rows (NULL/0 = all rows).
  * coef: k x ncomp column-major (cumulative columns), intercepts: ncomp.  Needs gsb_set_data only. */

@@ -16,3 +16,7 @@ for _ in range(steps):
     ev.evaluate_resident(); ts.append(ev.timing()["fit_kernel_ms"])
 fits = pop * 150
 print("k=%d pop=%d K1 ms=%s  us/fit-slot(148 SMs)=%.2f" % (k, pop, ["%.3f" % t for t in ts], min(ts) * 1e3 * 148 / fits))
+tr = ev.debug_trace(40)
+if tr.any():
+    d = np.diff(tr[tr > 0])
+    print("phase clocks:", d.tolist(), "total", int(tr[tr > 0][-1] - tr[0]))
