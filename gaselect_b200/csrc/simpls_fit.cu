@@ -76,35 +76,6 @@ __device__ __forceinline__ void blockSum(double (&v)[NV], double* red, int& phas
 }
 
 
-constexpr int kMaxTileWarps = 11; // 352 threads: 325 tiles at k = 200
-
-// blockSum for CTAs of up to kMaxTileWarps warps; scratch: nw * NV doubles
-template <int NV>
-__device__ __forceinline__ void blockSumWide(double (&v)[NV], double* scratch, int& phase, int nw) {
-#pragma unroll
-	for (int m = 16; m >= 1; m >>= 1) {
-#pragma unroll
-		for (int i = 0; i < NV; ++i) v[i] += shflXor(v[i], m);
-	}
-	if (nw > 1) {
-		const int warp = threadIdx.x >> 5;
-		__syncthreads();
-		if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-			for (int i = 0; i < NV; ++i) scratch[warp * NV + i] = v[i];
-		}
-		__syncthreads();
-#pragma unroll
-		for (int i = 0; i < NV; ++i) v[i] = scratch[i];
-		for (int w = 1; w < nw; ++w) {
-#pragma unroll
-			for (int i = 0; i < NV; ++i) v[i] += scratch[w * NV + i];
-		}
-		__syncthreads();
-	}
-	(void) phase;
-}
-
 __host__ __device__ inline int roundUp(int v, int m) { return (v + m - 1) / m * m; }
 
 // shared-memory carve-up (in doubles)
@@ -479,19 +450,35 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 // (src/PLSSimpls.cpp:150-162 are all row-wise), so it lives in registers; shared memory holds the
 // packed Gram, S (broadcast operand of the matrix-vector product) and the reduction scratch.
 // That halves the footprint of a fit and doubles the CTAs resident per SM.  After the last
-// component the Gram area is dead and takes the coefficients and the held-out staging tiles.
+// component the Gram area is dead and takes the coefficients and the held-out rows.
+//
+// Reductions: ONE round per component for {S'w, s0'S, V_j'w for every stored loading} and one for
+// {v'v, v'S}.  A round over 16 values costs 16 shuffle-adds (the lanes halve the value set at every
+// butterfly step) instead of 80, and 1/tn, 1/|v| come from rsqrt (no division, no sqrt).
 struct FastCarve {
 	int P, S, red, sel, total;
 	int coef, part, stage, stageCols; // inside the P area, after the fit
+	int xt;                           // > 0: every held-out block of the fit is staged at once at P + xt
 };
 
-__host__ __device__ inline FastCarve fastCarve(int k, int A, int nw) {
+// wantXt < 0: host decision (stage all blocks at once when that costs no occupancy); else as told
+__host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTasks, int maxBlockLd, int wantXt) {
 	FastCarve c;
 	const int Apad = roundUp(A, 2);
 	const int ntri = k * (k + 1) / 2;
 	const int coefD = k * Apad, partD = (nw > 1) ? nw * 32 * kChunk : 0;
 	const int minStage = 32 * min(k, 8);
-	const int area = roundUp(max(ntri, coefD + partD + minStage), 2);
+	const int plain = roundUp(max(ntri, coefD + partD + minStage), 2);
+	const int xtD = maxTasks * (k + 1) * 32;
+	const int withXt = roundUp(max(ntri, coefD + xtD), 2);
+	bool useXt = wantXt > 0;
+	if (wantXt < 0) {
+		// resident CTAs per SM by shared memory, with and without the one-shot staging
+		const int fixed = roundUp(k, 2) + 2 * kMaxWarps * kRedMax + roundUp(k, 2) / 2 + 1;
+		const int per1 = (plain + fixed) * 8 + 1024, per2 = (withXt + fixed) * 8 + 1024;
+		useXt = maxTasks >= 1 && maxTasks <= 2 && maxBlockLd <= 32 && per2 <= 232448 && (233472 / per2) >= min(233472 / per1, 2048 / (nw * 32));
+	}
+	const int area = useXt ? withXt : plain;
 	int o = 0;
 	c.P = o; o += area;
 	c.S = o; o += roundUp(k, 2);
@@ -502,12 +489,51 @@ __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw) {
 	c.part = coefD;
 	c.stage = coefD + partD;
 	c.stageCols = (area - c.stage) / 32;
+	c.xt = useXt ? coefD : 0;
 	return c;
 }
 
+// Sum 16 values per lane over the warp: afterwards every lane L holds the total of value (L >> 1).
+__device__ __forceinline__ double warpSum16(double (&v)[16], int lane) {
+#pragma unroll
+	for (int h = 8; h >= 1; h >>= 1) {
+		const bool up = (lane & (2 * h)) != 0;
+#pragma unroll
+		for (int i = 0; i < h; ++i) {
+			const double send = up ? v[i] : v[i + h];
+			const double keep = up ? v[i + h] : v[i];
+			v[i] = keep + shflXor(send, 2 * h);
+		}
+	}
+	return v[0] + shflXor(v[0], 1);
+}
+
+// CTA-wide totals of NV <= 16 values; every thread receives all of them, bitwise identical.
+template <int NV>
+__device__ __forceinline__ void blockSum16(double (&x)[NV], double* red, int& phase, int nw, int lane, int warp) {
+	double v[16];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) v[i] = (i < NV) ? x[i] : 0.0;
+	double tot = warpSum16(v, lane);
+	if (nw > 1) {
+		double* buf = red + phase * (kMaxWarps * kRedMax);
+		if ((lane & 1) == 0) buf[warp * 16 + (lane >> 1)] = tot;
+		__syncthreads();
+		tot = buf[lane & 15];
+		for (int w = 1; w < nw; ++w) tot += buf[w * 16 + (lane & 15)];
+		phase ^= 1;
+#pragma unroll
+		for (int i = 0; i < NV; ++i) x[i] = __shfl_sync(0xffffffffu, tot, i);
+	} else {
+#pragma unroll
+		for (int i = 0; i < NV; ++i) x[i] = __shfl_sync(0xffffffffu, tot, 2 * i);
+	}
+}
+
 template <int AREG>
-__global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams prm) {
+__global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams prm, const int stageAll) {
 	extern __shared__ __align__(16) double smem[];
+	static_assert(AREG % 2 == 0 && AREG + 2 <= 16, "one reduction round holds tn^2, q*tn and every projection");
 	const int NT = blockDim.x, NW = NT >> 5;
 
 	const int ci = blockIdx.x % prm.bucketCount;
@@ -520,12 +546,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 	const FitDesc fd = prm.fits[fi];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-	const FastCarve cv = fastCarve(k, A, NW);
+	const FastCarve cv = fastCarve(k, A, NW, prm.maxTasks, prm.maxBlockLd, stageAll);
 	double* __restrict__ P = smem + cv.P;
 	double* __restrict__ S = smem + cv.S;
 	double* red = smem + cv.red;
 	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(smem + cv.sel);
 	int phase = 0;
+
+	const bool tracing = prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
+	int stamp = 0;
+#define GSB_STAMP() do { if (tracing) prm.trace[stamp++] = clock64(); } while (0)
+	GSB_STAMP();
 
 	// ---- gather ------------------------------------------------------------------------------
 	for (int i = tid; i < k; i += NT) sel[i] = prm.idx[selBegin + i];
@@ -547,6 +578,19 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 			}
 		}
 	}
+	// descriptors of the held-out blocks this fit predicts (needed much later: load them now)
+	TaskDesc td[2];
+	BlockDesc bd[2];
+#pragma unroll
+	for (int t = 0; t < 2; ++t) {
+		if (t < fd.taskCount) {
+			td[t] = prm.tasks[fd.taskBegin + t];
+			bd[t] = prm.blocks[td[t].block];
+		} else {
+			td[t].block = 0; td[t].kind = 0; td[t].dest = 0; td[t].pad = 0;
+			bd[t].zOff = 0; bd[t].ld = 0; bd[t].nrows = 0;
+		}
+	}
 	const bool valid = tid < k;
 	const int r = valid ? tid : k - 1;
 	double sOwn, s0Own, xmOwn;
@@ -562,6 +606,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 	for (int j = 0; j < AREG; ++j) { vOwn[j] = 0.0; cOwn[j] = 0.0; }
 	cpAsyncWaitAll();
 	__syncthreads();
+	GSB_STAMP(); // 1: gather done
 
 	// rows of a warp are consecutive: [rlo, rhi] is warp-uniform
 	const int rlo = min(warp * 32, k - 1);
@@ -569,9 +614,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 	const double* __restrict__ pr = P + r * (r + 1) / 2;
 	const double* __restrict__ pc = P + r;
 	const int triLo = rlo * (rlo + 1) / 2;
+	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 
 	// ---- SIMPLS components -------------------------------------------------------------------
-	int done = A;
 	double cum = 0.0;
 #pragma unroll 1
 	for (int comp = 0; comp < A; ++comp) {
@@ -630,456 +675,73 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 		}
 		const double w = (a0 + a1) + (a2 + a3);
 
-		// round 1: tn^2 = S'GS (:138), q*tn = s0'S (:148), projections V_j'w
-		double r1[2 + kDots];
+		// ONE round: tn^2 = S'GS (:138), q*tn = s0'S (:148), projections V_j'w on every stored loading
+		double r1[2 + AREG];
+		r1[0] = valid ? sOwn * w : 0.0;
+		r1[1] = valid ? s0Own * sOwn : 0.0;
 #pragma unroll
-		for (int i = 0; i < 2 + kDots; ++i) r1[i] = 0.0;
-		if (valid) {
-			r1[0] = sOwn * w;
-			r1[1] = s0Own * sOwn;
-#pragma unroll
-			for (int j = 0; j < kDots; ++j) if (j < comp) r1[2 + j] = vOwn[j] * w;
-		}
-		blockSum<2 + kDots>(r1, red, phase, NW);
-		if (!(r1[0] >= 1e-50)) { // ||t|| < 1e-25 (NORM_TOL, :16,:141-143); also NaN / negative rounding
-			done = comp;
-			break;
-		}
-		const double tn = sqrt(r1[0]);
-		const double rtn = 1.0 / tn;
+		for (int j = 0; j < AREG; ++j) r1[2 + j] = (valid && j < comp) ? vOwn[j] * w : 0.0;
+		blockSum16<2 + AREG>(r1, red, phase, NW, lane, warp);
+		const bool under = !(r1[0] >= 1e-50); // ||t|| < 1e-25 (NORM_TOL, :16,:141-143); also NaN / negative rounding
+		const double rtn = rsqrt(r1[0]);      // 1/tn; tn itself is never needed
 		const double q = r1[1] * rtn;
 		double v = w;
 #pragma unroll
-		for (int j = 0; j < kDots; ++j) if (j < comp) v = fma(-vOwn[j], r1[2 + j], v);
-		if (AREG > kDots && comp > kDots) { // loadings kDots .. comp-1: one more round
-			double d[AREG - kDots > 0 ? AREG - kDots : 1];
-#pragma unroll
-			for (int j = kDots; j < AREG; ++j) d[j - kDots] = (valid && j < comp) ? vOwn[j] * w : 0.0;
-			blockSum<(AREG - kDots > 0 ? AREG - kDots : 1)>(d, red, phase, NW);
-#pragma unroll
-			for (int j = kDots; j < AREG; ++j) if (j < comp) v = fma(-vOwn[j], d[j - kDots], v);
-		}
+		for (int j = 0; j < AREG; ++j) v = fma(-vOwn[j], r1[2 + j], v);
 		// cumulative coefficients from S BEFORE deflation (:152-156); v = X't carries 1/tn (:145-147)
 		v *= rtn;
 		cum += sOwn * (q * rtn);
 		double r2[2];
 		r2[0] = valid ? v * v : 0.0;
 		r2[1] = valid ? v * sOwn : 0.0;
-		blockSum<2>(r2, red, phase, NW); // round 2: deflate S, normalise v (:160, :70-88)
-		const double dd = r2[1] / r2[0];
+		blockSum16<2>(r2, red, phase, NW, lane, warp); // second round: deflate S, normalise v (:160, :70-88)
 		const double rvn = rsqrt(r2[0]);
+		const double dd = (r2[1] * rvn) * rvn;
 		sOwn = fma(-v, dd, sOwn);
+		if (under) { sOwn = nanv; cum = nanv; } // the reference throws: poison this and every later component
 		if (valid) S[r] = sOwn;
 #pragma unroll
 		for (int j = 0; j < AREG; ++j) {
 			if (j == comp) { vOwn[j] = v * rvn; cOwn[j] = cum; }
 		}
 		__syncthreads();
+		GSB_STAMP(); // 2 + comp
 	}
-	// the reference throws std::underflow_error: poison the remaining components so that the
-	// epilogue reports GSB_STATUS_UNDERFLOW where the reference would have thrown
-#pragma unroll
-	for (int j = 0; j < AREG; ++j) if (j >= done) cOwn[j] = __longlong_as_double(0x7ff8000000000000LL);
 
-	// ---- coefficients to the (dead) Gram area, intercepts b0[a] = ym - xm'coef[:,a] (:162) ----
+	// ---- the Gram area is dead: coefficients go there, the held-out rows are fetched ---------------
 	double* __restrict__ coef = P + cv.coef;
-	__syncthreads();
-	if (valid) {
+	const bool staged = cv.xt > 0;
+	double* __restrict__ XT = P + cv.xt; // [task][column c <= k][32 rows]; column k is the block's y
+	if (staged) {
 #pragma unroll
-		for (int j = 0; j < AREG; ++j) if (j < Apad) coef[r * Apad + j] = (j < A) ? cOwn[j] : 0.0;
-	}
-	double b0v[AREG];
-#pragma unroll
-	for (int j = 0; j < AREG; ++j) b0v[j] = (valid && j < A) ? xmOwn * cOwn[j] : 0.0;
-	blockSum<AREG>(b0v, red, phase, NW);
-#pragma unroll
-	for (int j = 0; j < AREG; ++j) b0v[j] = fd.ym - b0v[j];
-	__syncthreads();
-
-	if (prm.coefOut != nullptr) { // gsb_simpls: raw coefficients of this fit
-		for (int i = tid; i < k * A; i += NT) prm.coefOut[i] = coef[(i % k) * Apad + (i / k)];
-		if (tid == 0) {
-#pragma unroll
-			for (int j = 0; j < AREG; ++j) if (j < A) prm.coefOut[k * A + j] = b0v[j];
-		}
-	}
-
-	// ---- held-out prediction and statistics -------------------------------------------------
-	double* __restrict__ part = P + cv.part;   // [warp][u][lane]
-	double* __restrict__ stage = P + cv.stage; // [column][32 rows]
-	const int colsPerPass = max(1, min(k, cv.stageCols));
-	for (int t = 0; t < fd.taskCount; ++t) {
-		const TaskDesc td = prm.tasks[fd.taskBegin + t];
-		const BlockDesc bd = prm.blocks[td.block];
-		const double* __restrict__ zb = prm.zpool + bd.zOff;
-		const double* __restrict__ ycol = zb + static_cast<size_t>(prm.p) * bd.ld;
-		double st[2 * AREG];
-#pragma unroll
-		for (int u = 0; u < 2 * AREG; ++u) st[u] = 0.0;
-		for (int r0 = 0; r0 < bd.nrows; r0 += 32) {
-			const int tr = r0 + lane;
-			const bool live = tr < bd.nrows;
-			const int slab = min(32, bd.ld - r0); // multiple of 4 rows, zero padded in the block copy
-			double acc[AREG];
-#pragma unroll
-			for (int u = 0; u < AREG; ++u) acc[u] = 0.0;
-			for (int c0 = 0; c0 < k; c0 += colsPerPass) {
-				const int nc = min(colsPerPass, k - c0);
-				const int pieces = slab >> 1; // 16-byte pieces per column
-				for (int e = tid; e < nc * pieces; e += NT) {
-					const int c = e / pieces, piece = e - c * pieces;
-					cpAsync16(stage + c * 32 + piece * 2, zb + static_cast<size_t>(sel[c0 + c]) * bd.ld + r0 + piece * 2);
-				}
-				cpAsyncWaitAll();
-				__syncthreads();
-				if (lane < slab) {
-					for (int c = warp; c < nc; c += NW) {
-						const double x = stage[c * 32 + lane];
-						const double* cr = coef + (c0 + c) * Apad;
-#pragma unroll
-						for (int u = 0; u < AREG; u += 2) {
-							if (u < Apad) {
-								const double2 cc = *reinterpret_cast<const double2*>(cr + u);
-								acc[u] = fma(x, cc.x, acc[u]);
-								if (u + 1 < AREG) acc[u + 1] = fma(x, cc.y, acc[u + 1]);
-							}
-						}
+		for (int t = 0; t < 2; ++t) {
+			if (t < fd.taskCount) {
+				const double* __restrict__ zb = prm.zpool + bd[t].zOff;
+				const int pieces = bd[t].ld >> 1; // 16-byte pieces per column
+				double* __restrict__ dst = XT + t * (k + 1) * 32;
+				for (int e = tid; e < (k + 1) * 16; e += NT) {
+					const int c = e >> 4, piece = e & 15;
+					if (piece < pieces) {
+						const size_t col = (c < k) ? sel[c] : static_cast<size_t>(prm.p);
+						cpAsync16(dst + c * 32 + piece * 2, zb + col * bd[t].ld + piece * 2);
 					}
-				}
-				__syncthreads(); // staging area free again
-			}
-			if (NW > 1) {
-#pragma unroll
-				for (int u = 0; u < AREG; ++u) part[(warp * kChunk + u) * 32 + lane] = acc[u];
-				__syncthreads();
-				if (warp == 0) {
-#pragma unroll
-					for (int u = 0; u < AREG; ++u) {
-						double s = part[u * 32 + lane];
-						for (int w2 = 1; w2 < NW; ++w2) s += part[(w2 * kChunk + u) * 32 + lane];
-						acc[u] = s;
-					}
-				}
-				__syncthreads();
-			}
-			if (warp == 0 && live) {
-				const double y = __ldg(ycol + tr);
-#pragma unroll
-				for (int u = 0; u < AREG; ++u) {
-					const double e = y - (acc[u] + b0v[u]);
-					st[u] += e;
-					st[AREG + u] = fma(e, e, st[AREG + u]);
-				}
-			}
-		}
-		if (warp == 0) {
-#pragma unroll
-			for (int m = 16; m >= 1; m >>= 1) {
-#pragma unroll
-				for (int u = 0; u < 2 * AREG; ++u) st[u] += shflXor(st[u], m);
-			}
-			if (lane < A) {
-				double se = 0.0, see = 0.0;
-#pragma unroll
-				for (int u = 0; u < AREG; ++u) {
-					if (u == lane) { se = st[u]; see = st[AREG + u]; }
-				}
-				if (td.kind == 0) {
-					// mean squared error of prediction for this fold (src/PLSEvaluator.cpp:266-268)
-					prm.mse[(static_cast<size_t>(chrom) * prm.innerDests + td.dest) * prm.maxNComp + lane] =
-						see / static_cast<double>(bd.nrows);
-				} else {
-					double* o = prm.ostat + ((static_cast<size_t>(chrom) * prm.outerDests + td.dest) * prm.maxNComp + lane) * 2;
-					o[0] = se;
-					o[1] = see;
-				}
-			}
-		}
-	}
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Register-tile path (A <= AREG, 32 < k <= 200): the packed Gram lives in REGISTERS.
-//
-// The k x k Gram is cut into 8 x 8 tiles; the nb(nb+1)/2 tiles on or below the diagonal are owned
-// by one thread each (64 doubles), loaded straight from the Gram table into registers once per fit
-// (64 independent loads per thread in flight) and reused by all A matrix-vector products.  Every
-// off-diagonal tile T(I,J) serves BOTH  w_I += T S_J  and  w_J += T' S_I, so each Gram entry costs
-// no shared-memory traffic at all and feeds two FMAs.  Partial products meet in a [nb][k] shared
-// buffer (every slot written by exactly one thread: deterministic), the thread that owns row r sums
-// its nb partials and runs the row-wise SIMPLS updates (src/PLSSimpls.cpp:150-162) on registers.
-// Only the warps that own rows take part in the two reductions per component (named barrier);
-// tile-only warps wait at the CTA barrier for the deflated S.
-constexpr int kTileB = 8;
-
-struct TileCarve {
-	int S, V, coef, W, red, sel, xt, total;
-	int ldw, part, stage, stageCols, xtSlabs; // xtSlabs > 0: the held-out blocks are prefetched into xt
-};
-
-// xtBudget: doubles available for prefetching the held-out blocks ([task][slab][k + 1 columns][32 rows])
-// wantXt < 0: decide from the limit (host, with the bucket's largest k); 0 / 1: as told (device)
-__host__ __device__ inline TileCarve tileCarve(int k, int A, int nw, int maxTasks, int maxBlockLd, int limitDoubles, int wantXt) {
-	TileCarve c;
-	const int nb = (k + kTileB - 1) / kTileB;
-	const int Apad = roundUp(A, 2);
-	c.ldw = nb * kTileB + 8; // row stride of the partial buffer
-	const int partD = (nw > 1) ? nw * 32 * 2 * kChunk : 0;
-	const int wD = roundUp(max(nb * c.ldw, partD + 32 * min(k + 1, 16)), 2);
-	int o = 0;
-	c.S = o; o += nb * kTileB;           // zero padded to whole tiles
-	c.V = o; o += roundUp(A * k, 2);
-	c.coef = o; o += k * Apad;
-	c.W = o; o += wD;
-	c.red = o; o += 2 * kMaxTileWarps * kRedMax;
-	c.sel = o; o += (nb * kTileB) / 2 + 2; // uint32 column ids, padded, + the y column
-	c.sel = roundUp(c.sel, 2);
-	o = roundUp(o, 2);
-	c.xt = o;
-	const int slabs = (maxBlockLd + 31) / 32;
-	const int xtD = maxTasks * slabs * (k + 1) * 32;
-	const bool fitsXt = maxTasks > 0 && maxTasks <= 2 && slabs == 1 && o + xtD <= limitDoubles;
-	c.xtSlabs = (wantXt < 0 ? fitsXt : wantXt != 0) ? slabs : 0;
-	if (c.xtSlabs > 0) o += xtD;
-	c.total = o;
-	c.part = 0;
-	c.stage = partD;
-	c.stageCols = (wD - partD) / 32;
-	return c;
-}
-
-__device__ __forceinline__ void namedBarrier(int id, int threads) {
-	asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
-}
-
-// blockSum over the first `nw` warps only (the row owners), synchronised on named barrier 1
-template <int NV>
-__device__ __forceinline__ void ownerSum(double (&v)[NV], double* red, int& phase, int nw) {
-#pragma unroll
-	for (int m = 16; m >= 1; m >>= 1) {
-#pragma unroll
-		for (int i = 0; i < NV; ++i) v[i] += shflXor(v[i], m);
-	}
-	if (nw > 1) {
-		double* buf = red + phase * (kMaxTileWarps * kRedMax);
-		const int warp = threadIdx.x >> 5;
-		if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-			for (int i = 0; i < NV; i += 2) *reinterpret_cast<double2*>(buf + warp * NV + i) = make_double2(v[i], v[i + 1]);
-		}
-		namedBarrier(1, nw * 32);
-#pragma unroll
-		for (int i = 0; i < NV; i += 2) {
-			const double2 t = *reinterpret_cast<const double2*>(buf + i);
-			v[i] = t.x; v[i + 1] = t.y;
-		}
-		for (int w = 1; w < nw; ++w) {
-#pragma unroll
-			for (int i = 0; i < NV; i += 2) {
-				const double2 t = *reinterpret_cast<const double2*>(buf + w * NV + i);
-				v[i] += t.x; v[i + 1] += t.y;
-			}
-		}
-		phase ^= 1;
-	}
-}
-
-template <int AREG, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) simplsFitTile(const FitParams prm, const int prefetch) {
-	extern __shared__ __align__(16) double smem[];
-	constexpr int B = kTileB;
-	static_assert(AREG % 2 == 0, "component registers come in pairs");
-	const int NT = blockDim.x, NW = NT >> 5;
-
-	const int ci = blockIdx.x % prm.bucketCount;
-	const int fi = blockIdx.x / prm.bucketCount;
-	const int chrom = prm.bucket[ci];
-	const uint32_t selBegin = prm.offsets[chrom];
-	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
-	const int A = min(prm.maxNComp, k);
-	const int Apad = roundUp(A, 2);
-	const FitDesc fd = prm.fits[fi];
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int nb = (k + B - 1) / B, ntiles = nb * (nb + 1) / 2;
-	const int ownerWarps = (k + 31) >> 5;
-
-	const TileCarve cv = tileCarve(k, A, NW, prm.maxTasks, prm.maxBlockLd, 0, prefetch);
-	double* __restrict__ S = smem + cv.S;
-	double* __restrict__ V = smem + cv.V;
-	double* __restrict__ coef = smem + cv.coef;
-	double* __restrict__ W = smem + cv.W;
-	double* red = smem + cv.red;
-	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(smem + cv.sel);
-	double* __restrict__ XT = smem + cv.xt;
-	const int ldw = cv.ldw;
-	const bool prefetched = cv.xtSlabs > 0;
-
-	const bool tracing = prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
-	int stamp = 0;
-#define GSB_STAMP() do { if (tracing) prm.trace[stamp++] = clock64(); } while (0)
-	GSB_STAMP();
-	for (int i = tid; i < nb * B; i += NT) sel[i] = (i < k) ? prm.idx[selBegin + i] : 0xffffffffu;
-	__syncthreads();
-
-	// ---- held-out blocks: start the copies now, they land while the fit runs ----------------------
-	// XT[task][column c <= k][32 rows]; column k is the block's y
-	if (prefetched) {
-		for (int t = 0; t < fd.taskCount; ++t) {
-			const BlockDesc bd = prm.blocks[prm.tasks[fd.taskBegin + t].block];
-			const double* __restrict__ zb = prm.zpool + bd.zOff;
-			const int pieces = bd.ld >> 1; // 16-byte pieces per column
-			double* __restrict__ dst = XT + t * (k + 1) * 32;
-			for (int e = tid; e < (k + 1) * 16; e += NT) {
-				const int c = e >> 4, piece = e & 15;
-				if (piece < pieces) {
-					const size_t col = (c < k) ? sel[c] : static_cast<size_t>(prm.p);
-					cpAsync16(dst + c * 32 + piece * 2, zb + col * bd.ld + piece * 2);
 				}
 			}
 		}
 		asm volatile("cp.async.commit_group;\n" ::: "memory");
 	}
-
-	// ---- tile ownership and gather straight into registers -------------------------------------
-	const bool hasTile = tid < ntiles;
-	int TI = 0, TJ = 0;
-	if (hasTile) {
-		TI = static_cast<int>((sqrtf(8.0f * static_cast<float>(tid) + 1.0f) - 1.0f) * 0.5f);
-		while ((TI + 1) * (TI + 2) / 2 <= tid) ++TI;
-		while (TI * (TI + 1) / 2 > tid) --TI;
-		TJ = tid - TI * (TI + 1) / 2;
+	if (valid) {
+#pragma unroll
+		for (int j = 0; j < AREG; ++j) if (j < Apad) coef[r * Apad + j] = (j < A) ? cOwn[j] : 0.0;
 	}
-	const bool diag = TI == TJ;
-	double T[B][B];
-	{
-		const double* __restrict__ gsrc = prm.gram + fd.gramOff;
-		uint32_t sr[B], sc[B];
-#pragma unroll
-		for (int i = 0; i < B; ++i) { sr[i] = sel[TI * B + i]; sc[i] = sel[TJ * B + i]; }
-#pragma unroll
-		for (int i = 0; i < B; ++i) {
-#pragma unroll
-			for (int j = 0; j < B; ++j) {
-				// padded rows/columns (sel == ~0) contribute zeros; on diagonal tiles take the symmetric entry
-				const uint32_t a = max(sr[i], sc[j]), b = min(sr[i], sc[j]);
-				T[i][j] = (hasTile && a != 0xffffffffu) ? __ldg(gsrc + tri(a) + b) : 0.0;
-			}
-		}
-	}
-
-	// ---- per-row state of the row owners ---------------------------------------------------------
-	const bool owner = tid < k;
-	const int r = owner ? tid : k - 1;
-	double sOwn = 0.0, s0Own = 0.0, xmOwn = 0.0;
-	if (warp < ownerWarps) {
-		const uint32_t srow = sel[r];
-		s0Own = __ldg(prm.s0 + static_cast<size_t>(fi) * prm.p + srow);
-		xmOwn = __ldg(prm.xm + static_cast<size_t>(fi) * prm.p + srow);
-		sOwn = s0Own;
-	}
-	if (tid < nb * B) S[tid] = owner ? sOwn : 0.0; // NT >= nb * B: padding rows stay zero
-	__syncthreads();
-	GSB_STAMP(); // 1: gather done
-
-	// ---- SIMPLS components ---------------------------------------------------------------------
-	int phase = 0;
-	double cum = 0.0;
-	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll 1
-	for (int comp = 0; comp < A; ++comp) {
-		// phase 1: every tile thread forms its two partial products
-		if (hasTile) {
-			double sI[B], sJ[B], uI[B], uJ[B];
-#pragma unroll
-			for (int i = 0; i < B; i += 2) {
-				const double2 a = *reinterpret_cast<const double2*>(S + TI * B + i);
-				const double2 b = *reinterpret_cast<const double2*>(S + TJ * B + i);
-				sI[i] = a.x; sI[i + 1] = a.y; sJ[i] = b.x; sJ[i + 1] = b.y;
-			}
-#pragma unroll
-			for (int i = 0; i < B; ++i) { uI[i] = 0.0; uJ[i] = 0.0; }
-#pragma unroll
-			for (int j = 0; j < B; ++j) {
-#pragma unroll
-				for (int i = 0; i < B; ++i) {
-					uI[i] = fma(T[i][j], sJ[j], uI[i]);
-					uJ[j] = fma(T[i][j], sI[i], uJ[j]);
-				}
-			}
-			double* wI = W + TJ * ldw + TI * B; // slot "other block = TJ" of the rows of block TI
-#pragma unroll
-			for (int i = 0; i < B; i += 2) *reinterpret_cast<double2*>(wI + i) = make_double2(uI[i], uI[i + 1]);
-			if (!diag) {
-				double* wJ = W + TI * ldw + TJ * B;
-#pragma unroll
-				for (int i = 0; i < B; i += 2) *reinterpret_cast<double2*>(wJ + i) = make_double2(uJ[i], uJ[i + 1]);
-			}
-		}
-		__syncthreads();
-		GSB_STAMP(); // 2 + 2*comp: tile products done
-		// phase 2: row owners
-		if (warp < ownerWarps) {
-			double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-			const double* __restrict__ wr = W + r;
-			int o = 0;
-			for (; o + 3 < nb; o += 4) {
-				a0 += wr[o * ldw];
-				a1 += wr[(o + 1) * ldw];
-				a2 += wr[(o + 2) * ldw];
-				a3 += wr[(o + 3) * ldw];
-			}
-			for (; o < nb; ++o) a0 += wr[o * ldw];
-			const double w = (a0 + a1) + (a2 + a3);
-
-			// ONE round: tn^2 = S'GS (:138), q*tn = s0'S (:148), projections V_j'w for every stored loading
-			double r1[2 + AREG];
-			double vj[AREG];
-#pragma unroll
-			for (int j = 0; j < AREG; ++j) vj[j] = (j < comp) ? V[j * k + r] : 0.0;
-			r1[0] = owner ? sOwn * w : 0.0;
-			r1[1] = owner ? s0Own * sOwn : 0.0;
-#pragma unroll
-			for (int j = 0; j < AREG; ++j) r1[2 + j] = owner ? vj[j] * w : 0.0;
-			ownerSum<2 + AREG>(r1, red, phase, ownerWarps);
-			const bool under = !(r1[0] >= 1e-50); // ||t|| < 1e-25 (NORM_TOL, :16,:141-143); also NaN / negative rounding
-			const double rtn = rsqrt(r1[0]);      // 1/tn; tn itself is never needed
-			const double q = r1[1] * rtn;
-			double v = w;
-#pragma unroll
-			for (int j = 0; j < AREG; ++j) v = fma(-vj[j], r1[2 + j], v);
-			// cumulative coefficients from S BEFORE deflation (:152-156); v = X't carries 1/tn (:145-147)
-			v *= rtn;
-			cum += sOwn * (q * rtn);
-			double r2[2];
-			r2[0] = owner ? v * v : 0.0;
-			r2[1] = owner ? v * sOwn : 0.0;
-			ownerSum<2>(r2, red, phase, ownerWarps); // second round: deflate S, normalise v (:160, :70-88)
-			const double rvn = rsqrt(r2[0]);
-			const double dd = (r2[1] * rvn) * rvn;
-			sOwn = fma(-v, dd, sOwn);
-			if (under) { sOwn = nanv; cum = nanv; } // poisons this and every later component
-			if (owner) {
-				S[r] = sOwn;
-				V[comp * k + r] = v * rvn;
-				coef[r * Apad + comp] = cum;
-			}
-		}
-		__syncthreads();
-		GSB_STAMP(); // 3 + 2*comp: row updates done
-	}
-
-	// ---- intercepts b0[a] = ym - xm'coef[:,a] (:162) ---------------------------------------------
-	if (owner && (Apad > A)) coef[r * Apad + A] = 0.0;
+	// intercepts b0[a] = ym - xm'coef[:,a] (:162)
 	double b0v[AREG];
 #pragma unroll
-	for (int j = 0; j < AREG; ++j) b0v[j] = (owner && j < A) ? xmOwn * coef[r * Apad + j] : 0.0;
-	{
-		int ph = 0;
-		blockSumWide<AREG>(b0v, W, ph, NW);
-	}
+	for (int j = 0; j < AREG; ++j) b0v[j] = (valid && j < A) ? xmOwn * cOwn[j] : 0.0;
+	blockSum16<AREG>(b0v, red, phase, NW, lane, warp);
 #pragma unroll
 	for (int j = 0; j < AREG; ++j) b0v[j] = fd.ym - b0v[j];
+	__syncthreads();
 
 	if (prm.coefOut != nullptr) { // gsb_simpls: raw coefficients of this fit
 		for (int i = tid; i < k * A; i += NT) prm.coefOut[i] = coef[(i % k) * Apad + (i / k)];
@@ -1091,97 +753,79 @@ __global__ void __launch_bounds__(MAXT, MINB) simplsFitTile(const FitParams prm,
 	GSB_STAMP(); // intercepts done
 
 	// ---- held-out prediction and statistics -------------------------------------------------
-	double* __restrict__ part = W + cv.part;   // [warp][task*AREG + u][lane]
-	if (prefetched) {
-		// both tasks in one pass over the prefetched tiles: lanes = rows, warps split the columns
+	if (staged) {
+		// work unit = (task, half of the component counts): no partial sums cross warps
 		cpAsyncWaitAll();
 		__syncthreads();
-		double acc[2][AREG];
+		constexpr int H = (AREG / 2 + 1) & ~1; // components per unit, even (6 of 10)
+		const int units = fd.taskCount * 2;
+		for (int u = warp; u < units; u += NW) {
+			const int t = u >> 1, base = (u & 1) * H;
+			if (base >= A) continue;
+			const double* __restrict__ xt = XT + t * (k + 1) * 32 + lane;
+			double acc[H];
 #pragma unroll
-		for (int t = 0; t < 2; ++t)
+			for (int i = 0; i < H; ++i) acc[i] = 0.0;
+#pragma unroll 4
+			for (int c = 0; c < k; ++c) {
+				const double x = xt[c * 32];
+				const double* cr = coef + c * Apad + base;
 #pragma unroll
-			for (int u = 0; u < AREG; ++u) acc[t][u] = 0.0;
-		const int ntask = fd.taskCount;
-		for (int c = warp; c < k; c += NW) {
-			const double x0 = XT[c * 32 + lane];
-			const double x1 = (ntask > 1) ? XT[(k + 1 + c) * 32 + lane] : 0.0;
-			const double* cr = coef + c * Apad;
-#pragma unroll
-			for (int u = 0; u < AREG; u += 2) {
-				if (u < Apad) {
-					const double2 cc = *reinterpret_cast<const double2*>(cr + u);
-					acc[0][u] = fma(x0, cc.x, acc[0][u]);
-					acc[0][u + 1] = fma(x0, cc.y, acc[0][u + 1]);
-					acc[1][u] = fma(x1, cc.x, acc[1][u]);
-					acc[1][u + 1] = fma(x1, cc.y, acc[1][u + 1]);
+				for (int i = 0; i < H; i += 2) {
+					if (base + i < AREG) {
+						const double2 cc = (base + i < Apad) ? *reinterpret_cast<const double2*>(cr + i) : make_double2(0.0, 0.0);
+						acc[i] = fma(x, cc.x, acc[i]);
+						acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+					}
 				}
 			}
-		}
-		if (NW > 1) {
+			const int nrows = (t == 0) ? bd[0].nrows : bd[1].nrows;
+			const int kind = (t == 0) ? td[0].kind : td[1].kind;
+			const int dest = (t == 0) ? td[0].dest : td[1].dest;
+			const double y = xt[k * 32];
+			double st[16];
 #pragma unroll
-			for (int t = 0; t < 2; ++t)
+			for (int i = 0; i < 16; ++i) st[i] = 0.0;
 #pragma unroll
-				for (int u = 0; u < AREG; ++u) part[(warp * 2 * AREG + t * AREG + u) * 32 + lane] = acc[t][u];
-			__syncthreads();
-		}
-		// warp t finishes task t (a single warp takes both when the CTA has only one)
-		for (int t = warp; t < ntask; t += NW) {
-			const TaskDesc td = prm.tasks[fd.taskBegin + t];
-			const int nrows = prm.blocks[td.block].nrows;
-			double st[2 * AREG];
+			for (int i = 0; i < H; ++i) {
+				double b0i = 0.0;
 #pragma unroll
-			for (int u = 0; u < AREG; ++u) {
-				double sum;
-				if (NW > 1) {
-					sum = part[(t * AREG + u) * 32 + lane];
-					for (int w2 = 1; w2 < NW; ++w2) sum += part[(w2 * 2 * AREG + t * AREG + u) * 32 + lane];
-				} else {
-					sum = (t == 0) ? acc[0][u] : acc[1][u];
-				}
-				const double e = (lane < nrows) ? XT[(t * (k + 1) + k) * 32 + lane] - (sum + b0v[u]) : 0.0;
-				st[u] = e;
-				st[AREG + u] = e * e;
+				for (int j = 0; j < AREG; ++j) if (j == base + i) b0i = b0v[j];
+				const double e = (lane < nrows) ? y - (acc[i] + b0i) : 0.0;
+				st[i] = e;
+				st[H + i] = e * e;
 			}
-#pragma unroll
-			for (int m = 16; m >= 1; m >>= 1) {
-#pragma unroll
-				for (int u = 0; u < 2 * AREG; ++u) st[u] += shflXor(st[u], m);
-			}
-			if (lane < A) {
-				double se = 0.0, see = 0.0;
-#pragma unroll
-				for (int u = 0; u < AREG; ++u) {
-					if (u == lane) { se = st[u]; see = st[AREG + u]; }
-				}
-				if (td.kind == 0) {
-					// mean squared error of prediction for this fold (src/PLSEvaluator.cpp:266-268)
-					prm.mse[(static_cast<size_t>(chrom) * prm.innerDests + td.dest) * prm.maxNComp + lane] =
-						see / static_cast<double>(nrows);
-				} else {
-					double* o = prm.ostat + ((static_cast<size_t>(chrom) * prm.outerDests + td.dest) * prm.maxNComp + lane) * 2;
-					o[0] = se;
-					o[1] = see;
+			const double tot = warpSum16(st, lane); // lane L: value (L >> 1): sum e (< H), sum e^2 (H ..)
+			const int j = lane >> 1;
+			if ((lane & 1) == 0 && j < 2 * H) {
+				const int a = base + (j < H ? j : j - H);
+				if (a < A) {
+					if (kind == 0) {
+						// mean squared error of prediction for this fold (src/PLSEvaluator.cpp:266-268)
+						if (j >= H) prm.mse[(static_cast<size_t>(chrom) * prm.innerDests + dest) * prm.maxNComp + a] = tot / static_cast<double>(nrows);
+					} else {
+						prm.ostat[((static_cast<size_t>(chrom) * prm.outerDests + dest) * prm.maxNComp + a) * 2 + (j >= H ? 1 : 0)] = tot;
+					}
 				}
 			}
 		}
 		GSB_STAMP();
 	} else {
-		// large blocks: stage [column pass][32-row slab] tiles in the (now free) partial buffer
-		__syncthreads();
-		double* __restrict__ stage = W + cv.stage; // [column][32 rows]
+		double* __restrict__ part = P + cv.part;   // [warp][u][lane]
+		double* __restrict__ stage = P + cv.stage; // [column][32 rows]
 		const int colsPerPass = max(1, min(k, cv.stageCols));
 		for (int t = 0; t < fd.taskCount; ++t) {
-			const TaskDesc td = prm.tasks[fd.taskBegin + t];
-			const BlockDesc bd = prm.blocks[td.block];
-			const double* __restrict__ zb = prm.zpool + bd.zOff;
-			const double* __restrict__ ycol = zb + static_cast<size_t>(prm.p) * bd.ld;
+			const TaskDesc tdt = prm.tasks[fd.taskBegin + t];
+			const BlockDesc bdt = prm.blocks[tdt.block];
+			const double* __restrict__ zb = prm.zpool + bdt.zOff;
+			const double* __restrict__ ycol = zb + static_cast<size_t>(prm.p) * bdt.ld;
 			double st[2 * AREG];
 #pragma unroll
 			for (int u = 0; u < 2 * AREG; ++u) st[u] = 0.0;
-			for (int r0 = 0; r0 < bd.nrows; r0 += 32) {
+			for (int r0 = 0; r0 < bdt.nrows; r0 += 32) {
 				const int tr = r0 + lane;
-				const bool live = tr < bd.nrows;
-				const int slab = min(32, bd.ld - r0); // multiple of 4 rows, zero padded in the block copy
+				const bool live = tr < bdt.nrows;
+				const int slab = min(32, bdt.ld - r0); // multiple of 4 rows, zero padded in the block copy
 				double acc[AREG];
 #pragma unroll
 				for (int u = 0; u < AREG; ++u) acc[u] = 0.0;
@@ -1190,7 +834,7 @@ __global__ void __launch_bounds__(MAXT, MINB) simplsFitTile(const FitParams prm,
 					const int pieces = slab >> 1; // 16-byte pieces per column
 					for (int e = tid; e < nc * 16; e += NT) {
 						const int c = e >> 4, piece = e & 15;
-						if (piece < pieces) cpAsync16(stage + c * 32 + piece * 2, zb + static_cast<size_t>(sel[c0 + c]) * bd.ld + r0 + piece * 2);
+						if (piece < pieces) cpAsync16(stage + c * 32 + piece * 2, zb + static_cast<size_t>(sel[c0 + c]) * bdt.ld + r0 + piece * 2);
 					}
 					cpAsyncWaitAll();
 					__syncthreads();
@@ -1212,13 +856,13 @@ __global__ void __launch_bounds__(MAXT, MINB) simplsFitTile(const FitParams prm,
 				}
 				if (NW > 1) {
 #pragma unroll
-					for (int u = 0; u < AREG; ++u) part[(warp * 2 * AREG + u) * 32 + lane] = acc[u];
+					for (int u = 0; u < AREG; ++u) part[(warp * kChunk + u) * 32 + lane] = acc[u];
 					__syncthreads();
 					if (warp == 0) {
 #pragma unroll
 						for (int u = 0; u < AREG; ++u) {
 							double sum = part[u * 32 + lane];
-							for (int w2 = 1; w2 < NW; ++w2) sum += part[(w2 * 2 * AREG + u) * 32 + lane];
+							for (int w2 = 1; w2 < NW; ++w2) sum += part[(w2 * kChunk + u) * 32 + lane];
 							acc[u] = sum;
 						}
 					}
@@ -1246,11 +890,11 @@ __global__ void __launch_bounds__(MAXT, MINB) simplsFitTile(const FitParams prm,
 					for (int u = 0; u < AREG; ++u) {
 						if (u == lane) { se = st[u]; see = st[AREG + u]; }
 					}
-					if (td.kind == 0) {
-						prm.mse[(static_cast<size_t>(chrom) * prm.innerDests + td.dest) * prm.maxNComp + lane] =
-							see / static_cast<double>(bd.nrows);
+					if (tdt.kind == 0) {
+						prm.mse[(static_cast<size_t>(chrom) * prm.innerDests + tdt.dest) * prm.maxNComp + lane] =
+							see / static_cast<double>(bdt.nrows);
 					} else {
-						double* o = prm.ostat + ((static_cast<size_t>(chrom) * prm.outerDests + td.dest) * prm.maxNComp + lane) * 2;
+						double* o = prm.ostat + ((static_cast<size_t>(chrom) * prm.outerDests + tdt.dest) * prm.maxNComp + lane) * 2;
 						o[0] = se;
 						o[1] = see;
 					}
@@ -1262,38 +906,17 @@ __global__ void __launch_bounds__(MAXT, MINB) simplsFitTile(const FitParams prm,
 #undef GSB_STAMP
 }
 
-inline int tileThreads(int k) {
-	const int nb = (k + kTileB - 1) / kTileB;
-	return roundUp(max(nb * (nb + 1) / 2, k), 32);
-}
-
-template <int AREG, int MAXT, int MINB>
-cudaError_t launchTile(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
-	const int threads = tileThreads(kMax);
-	// shared memory per CTA: what lets MINB CTAs share an SM (minus the 1 KB the system reserves per CTA)
-	const int limitDoubles = (min(smemLimit, (233472 / MINB) - 1024)) / 8;
-	const TileCarve cv = tileCarve(kMax, A, threads / 32, prm.maxTasks, prm.maxBlockLd, limitDoubles, -1);
-	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double);
-	cudaError_t err = cudaFuncSetAttribute(simplsFitTile<AREG, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
-	if (err != cudaSuccess) return err;
-	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
-	if (grid <= 0) return cudaSuccess;
-	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-	simplsFitTile<AREG, MAXT, MINB><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtSlabs > 0 ? 1 : 0);
-	if (ctas) *ctas += grid;
-	return cudaGetLastError();
-}
-
 template <int AREG>
 cudaError_t launchFast(const FitParams& prm, int kMax, int A, cudaStream_t stream, long long* ctas) {
 	const int threads = roundUp(kMax, 32);
-	const size_t bytes = static_cast<size_t>(fastCarve(kMax, A, threads / 32).total) * sizeof(double);
+	const FastCarve cv = fastCarve(kMax, A, threads / 32, prm.maxTasks, prm.maxBlockLd, -1);
+	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double);
 	cudaError_t err = cudaFuncSetAttribute(simplsFitFast<AREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 	if (err != cudaSuccess) return err;
 	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
 	if (grid <= 0) return cudaSuccess;
 	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-	simplsFitFast<AREG><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm);
+	simplsFitFast<AREG><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xt > 0 ? 1 : 0);
 	if (ctas) *ctas += grid;
 	return cudaGetLastError();
 }
@@ -1329,17 +952,8 @@ int fitKernelMaxK(int A, int smemLimit) {
 // One launch for a bucket of chromosomes whose subset sizes are all <= kMax.
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
 	const int Ak = (A < kMax) ? A : kMax;
-	if (Ak <= kFastComponents && kMax > 32 && kMax <= 200) {
-		const int threads = tileThreads(kMax);
-		if (tileCarve(kMax, Ak, threads / 32, 0, 0, 0, 0).total * 8 <= smemLimit) {
-			if (threads <= 96) return launchTile<kFastComponents, 96, 3>(prm, kMax, Ak, smemLimit, stream, ctas);
-			if (threads <= 160) return launchTile<kFastComponents, 160, 2>(prm, kMax, Ak, smemLimit, stream, ctas);
-			if (threads <= 224) return launchTile<kFastComponents, 224, 1>(prm, kMax, Ak, smemLimit, stream, ctas);
-			return launchTile<kFastComponents, 352, 1>(prm, kMax, Ak, smemLimit, stream, ctas);
-		}
-	}
 	if (Ak <= kFastComponents && kMax <= kMaxWarps * 32 &&
-	    fastCarve(kMax, Ak, roundUp(kMax, 32) / 32).total * 8 <= smemLimit) {
+	    fastCarve(kMax, Ak, roundUp(kMax, 32) / 32, prm.maxTasks, prm.maxBlockLd, -1).total * 8 <= smemLimit) {
 		return launchFast<kFastComponents>(prm, kMax, Ak, stream, ctas); // per-row state in registers
 	}
 	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true).total * 8 <= smemLimit) {
