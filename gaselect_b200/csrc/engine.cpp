@@ -125,6 +125,11 @@ struct gsb_engine {
 	cudaStream_t stream = nullptr;    // the stream all work is enqueued on
 	cudaStream_t ownStream = nullptr; // created by the engine
 	bool callerStream = false;
+	// K1 launches of different subset-size classes run concurrently: CTAs of small subsets fill the
+	// shared memory / issue slots that the one or two resident CTAs of a large subset leave idle
+	static constexpr int kSideStreams = 4;
+	cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t evFork = nullptr, evJoin[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int smCount = 0, smemLimit = 0;
 	int ldz = 0;
@@ -182,6 +187,14 @@ void releaseDevice(gsb_engine* e) {
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
 	for (int i = 0; i < 6; ++i) { if (e->ev[i]) cudaEventDestroy(e->ev[i]); e->ev[i] = nullptr; }
+	for (int i = 0; i < gsb_engine::kSideStreams; ++i) {
+		if (e->side[i]) cudaStreamDestroy(e->side[i]);
+		if (e->evJoin[i]) cudaEventDestroy(e->evJoin[i]);
+		e->side[i] = nullptr;
+		e->evJoin[i] = nullptr;
+	}
+	if (e->evFork) cudaEventDestroy(e->evFork);
+	e->evFork = nullptr;
 	if (e->ownStream) cudaStreamDestroy(e->ownStream);
 	e->ownStream = nullptr;
 	e->stream = nullptr;
@@ -206,6 +219,11 @@ void ensureDevice(gsb_engine* e) {
 	GSB_CUDA(cudaStreamCreateWithFlags(&e->ownStream, cudaStreamNonBlocking));
 	if (!e->callerStream) e->stream = e->ownStream;
 	for (int i = 0; i < 6; ++i) GSB_CUDA(cudaEventCreate(&e->ev[i]));
+	for (int i = 0; i < gsb_engine::kSideStreams; ++i) {
+		GSB_CUDA(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking));
+		GSB_CUDA(cudaEventCreateWithFlags(&e->evJoin[i], cudaEventDisableTiming));
+	}
+	GSB_CUDA(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
 	if (std::getenv("GSB_TRACE")) { // profiling aid: K1 stamps clock64() at its phase boundaries
 		e->traceBuf.reserve(64);
 		GSB_CUDA(cudaMemset(e->traceBuf.ptr, 0, 64 * sizeof(long long)));
@@ -788,7 +806,16 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
 		} else {
 			const int innerDests = e->plan.groups * e->plan.innerPerGroup;
-			for (size_t b = 0; b < e->buckets.size(); ++b) {
+			// largest subsets first, classes dealt round-robin to the side streams (fork / join on events)
+			const int nside = (e->buckets.size() > 1 && !std::getenv("GSB_SERIAL")) ? gsb_engine::kSideStreams : 0;
+			if (nside) {
+				GSB_CUDA(cudaEventRecord(e->evFork, e->stream));
+				for (int i = 0; i < nside; ++i) GSB_CUDA(cudaStreamWaitEvent(e->side[i], e->evFork, 0));
+			}
+			int slot = 0;
+			for (size_t bi = e->buckets.size(); bi-- > 0; ++slot) {
+				const size_t b = bi;
+				cudaStream_t launchStream = nside ? e->side[slot % nside] : e->stream;
 				gsb::FitParams prm;
 				prm.gram = e->gram.ptr;
 				prm.s0 = e->s0.ptr;
@@ -809,11 +836,15 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.mse = e->dMse.ptr;
 				prm.ostat = e->dOstat.ptr;
 				prm.coefOut = nullptr;
-			prm.trace = e->traceBuf.ptr;
-			prm.maxTasks = e->maxTasks;
-			prm.maxBlockLd = e->maxBlockLd;
-				GSB_CUDA(gsb::launchFitKernel(prm, e->buckets[b].kMax, e->tableA, e->smemLimit, e->stream, &ctas));
+				prm.trace = e->traceBuf.ptr;
+				prm.maxTasks = e->maxTasks;
+				prm.maxBlockLd = e->maxBlockLd;
+				GSB_CUDA(gsb::launchFitKernel(prm, e->buckets[b].kMax, e->tableA, e->smemLimit, launchStream, &ctas));
 				++launches;
+			}
+			for (int i = 0; i < nside; ++i) {
+				GSB_CUDA(cudaEventRecord(e->evJoin[i], e->side[i]));
+				GSB_CUDA(cudaStreamWaitEvent(e->stream, e->evJoin[i], 0));
 			}
 			GSB_CUDA(cudaEventRecord(e->ev[3], e->stream));
 			gsb::ReduceParams rp;
