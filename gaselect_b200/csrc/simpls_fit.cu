@@ -458,10 +458,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 struct FastCarve {
 	int P, S, red, sel, total;
 	int coef, part, stage, stageCols; // inside the P area, after the fit
-	int xt;                           // > 0: every held-out block of the fit is staged at once at P + xt
+	int xt;                           // > 0: whole held-out blocks are staged at P + xt ...
+	int xtTasks;                      // ... this many per pass (1 or 2)
 };
 
-// wantXt < 0: host decision (stage all blocks at once when that costs no occupancy); else as told
+// wantXt < 0: host decision; else the number of held-out blocks staged per pass (0, 1 or 2), as told
 __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTasks, int maxBlockLd, int wantXt) {
 	FastCarve c;
 	const int Apad = roundUp(A, 2);
@@ -469,16 +470,25 @@ __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTask
 	const int coefD = k * Apad, partD = (nw > 1) ? nw * 32 * kChunk : 0;
 	const int minStage = 32 * min(k, 8);
 	const int plain = roundUp(max(ntri, coefD + partD + minStage), 2);
-	const int xtD = maxTasks * (k + 1) * 32;
-	const int withXt = roundUp(max(ntri, coefD + xtD), 2);
-	bool useXt = wantXt > 0;
+	const int xt1 = (k + 1) * 32;
+	int stagedTasks = wantXt;
 	if (wantXt < 0) {
-		// resident CTAs per SM by shared memory, with and without the one-shot staging
-		const int fixed = roundUp(k, 2) + 2 * kMaxWarps * kRedMax + roundUp(k, 2) / 2 + 1;
-		const int per1 = (plain + fixed) * 8 + 1024, per2 = (withXt + fixed) * 8 + 1024;
-		useXt = maxTasks >= 1 && maxTasks <= 2 && maxBlockLd <= 32 && per2 <= 232448 && (233472 / per2) >= min(233472 / per1, 2048 / (nw * 32));
+		// stage both blocks at once when that keeps the CTAs per SM, else one block per pass when the
+		// footprint grows by at most a third; large blocks (more than 32 rows) take the slab path
+		stagedTasks = 0;
+		if (maxTasks >= 1 && maxTasks <= 2 && maxBlockLd <= 32) {
+			const int fixed = roundUp(k, 2) + 2 * kMaxWarps * kRedMax + roundUp(k, 2) / 2 + 1;
+			const int perPlain = (plain + fixed) * 8 + 1024;
+			const int residentPlain = min(233472 / perPlain, 2048 / (nw * 32));
+			for (int tasks = maxTasks; tasks >= 1 && stagedTasks == 0; --tasks) {
+				const int area = roundUp(max(ntri, coefD + tasks * xt1), 2);
+				const int per = (area + fixed) * 8 + 1024;
+				if (per > 232448) continue;
+				if (233472 / per >= residentPlain || (tasks == 1 && 3 * area <= 4 * plain)) stagedTasks = tasks;
+			}
+		}
 	}
-	const int area = useXt ? withXt : plain;
+	const int area = stagedTasks > 0 ? roundUp(max(ntri, coefD + stagedTasks * xt1), 2) : plain;
 	int o = 0;
 	c.P = o; o += area;
 	c.S = o; o += roundUp(k, 2);
@@ -489,7 +499,8 @@ __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTask
 	c.part = coefD;
 	c.stage = coefD + partD;
 	c.stageCols = (area - c.stage) / 32;
-	c.xt = useXt ? coefD : 0;
+	c.xt = stagedTasks > 0 ? coefD : 0;
+	c.xtTasks = stagedTasks;
 	return c;
 }
 
@@ -711,14 +722,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 	// ---- the Gram area is dead: coefficients go there, the held-out rows are fetched ---------------
 	double* __restrict__ coef = P + cv.coef;
 	const bool staged = cv.xt > 0;
-	double* __restrict__ XT = P + cv.xt; // [task][column c <= k][32 rows]; column k is the block's y
-	if (staged) {
+	const int tasksPerPass = cv.xtTasks;
+	double* __restrict__ XT = P + cv.xt; // [slot][column c <= k][32 rows]; column k is the block's y
+	auto stageBlocks = [&](int firstTask) {
 #pragma unroll
 		for (int t = 0; t < 2; ++t) {
-			if (t < fd.taskCount) {
+			if (t >= firstTask && t < firstTask + tasksPerPass && t < fd.taskCount) {
 				const double* __restrict__ zb = prm.zpool + bd[t].zOff;
 				const int pieces = bd[t].ld >> 1; // 16-byte pieces per column
-				double* __restrict__ dst = XT + t * (k + 1) * 32;
+				double* __restrict__ dst = XT + (t - firstTask) * (k + 1) * 32;
 				for (int e = tid; e < (k + 1) * 16; e += NT) {
 					const int c = e >> 4, piece = e & 15;
 					if (piece < pieces) {
@@ -729,7 +741,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 			}
 		}
 		asm volatile("cp.async.commit_group;\n" ::: "memory");
-	}
+	};
+	if (staged) stageBlocks(0);
 	if (valid) {
 #pragma unroll
 		for (int j = 0; j < AREG; ++j) if (j < Apad) coef[r * Apad + j] = (j < A) ? cOwn[j] : 0.0;
@@ -755,27 +768,59 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 	// ---- held-out prediction and statistics -------------------------------------------------
 	if (staged) {
 		// work unit = (task, half of the component counts): no partial sums cross warps
+		constexpr int H = (AREG / 2 + 1) & ~1; // components of the first half, even (6 of 10); second half AREG - H
+		for (int firstTask = 0; firstTask < fd.taskCount; firstTask += tasksPerPass) {
+		if (firstTask > 0) {
+			__syncthreads(); // previous pass consumed
+			stageBlocks(firstTask);
+		}
 		cpAsyncWaitAll();
 		__syncthreads();
-		constexpr int H = (AREG / 2 + 1) & ~1; // components per unit, even (6 of 10)
-		const int units = fd.taskCount * 2;
+		const int units = min(tasksPerPass, fd.taskCount - firstTask) * 2;
 		for (int u = warp; u < units; u += NW) {
-			const int t = u >> 1, base = (u & 1) * H;
+			const int t = firstTask + (u >> 1);
+			const bool second = (u & 1) != 0;
+			const int base = second ? H : 0;
 			if (base >= A) continue;
-			const double* __restrict__ xt = XT + t * (k + 1) * 32 + lane;
+			const double* __restrict__ xt = XT + (u >> 1) * (k + 1) * 32 + lane;
+			const double* __restrict__ cr = coef + base;
 			double acc[H];
 #pragma unroll
 			for (int i = 0; i < H; ++i) acc[i] = 0.0;
+			// Apad is even and >= A; the pairs of this half that lie inside Apad (warp-uniform count)
+			const int pairs = min((second ? AREG - H : H), Apad - base) >> 1;
+			if (pairs == H / 2) {
 #pragma unroll 4
-			for (int c = 0; c < k; ++c) {
-				const double x = xt[c * 32];
-				const double* cr = coef + c * Apad + base;
+				for (int c = 0; c < k; ++c) {
+					const double x = xt[c * 32];
 #pragma unroll
-				for (int i = 0; i < H; i += 2) {
-					if (base + i < AREG) {
-						const double2 cc = (base + i < Apad) ? *reinterpret_cast<const double2*>(cr + i) : make_double2(0.0, 0.0);
+					for (int i = 0; i < H; i += 2) {
+						const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
 						acc[i] = fma(x, cc.x, acc[i]);
 						acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+					}
+				}
+			} else if (pairs == (AREG - H) / 2) {
+#pragma unroll 4
+				for (int c = 0; c < k; ++c) {
+					const double x = xt[c * 32];
+#pragma unroll
+					for (int i = 0; i < AREG - H; i += 2) {
+						const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
+						acc[i] = fma(x, cc.x, acc[i]);
+						acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+					}
+				}
+			} else {
+				for (int c = 0; c < k; ++c) {
+					const double x = xt[c * 32];
+#pragma unroll
+					for (int i = 0; i < H; i += 2) {
+						if ((i >> 1) < pairs) {
+							const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
+							acc[i] = fma(x, cc.x, acc[i]);
+							acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+						}
 					}
 				}
 			}
@@ -790,7 +835,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 			for (int i = 0; i < H; ++i) {
 				double b0i = 0.0;
 #pragma unroll
-				for (int j = 0; j < AREG; ++j) if (j == base + i) b0i = b0v[j];
+				for (int j = 0; j < AREG; ++j) if (j == (second ? H : 0) + i) b0i = b0v[j];
 				const double e = (lane < nrows) ? y - (acc[i] + b0i) : 0.0;
 				st[i] = e;
 				st[H + i] = e * e;
@@ -808,6 +853,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 					}
 				}
 			}
+		}
 		}
 		GSB_STAMP();
 	} else {
@@ -916,7 +962,7 @@ cudaError_t launchFast(const FitParams& prm, int kMax, int A, cudaStream_t strea
 	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
 	if (grid <= 0) return cudaSuccess;
 	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-	simplsFitFast<AREG><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xt > 0 ? 1 : 0);
+	simplsFitFast<AREG><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks);
 	if (ctas) *ctas += grid;
 	return cudaGetLastError();
 }

@@ -1,0 +1,75 @@
+"""Turn the ncu outputs of a round (gpurun_out/) into the small, committed summaries under profiles/.
+
+usage: python profiles/summarize.py r01
+  gpurun_out/<round>_launches.csv      (ncu --metrics gpu__time_duration.sum ... python bench.py ...)
+  gpurun_out/<round>_k1_full.ncu-rep   (ncu --set full ... -k regex:simplsFit ... python bench.py ...)
+"""
+import collections, csv, io, os, subprocess, sys
+
+rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+out = []
+
+path = os.path.join(root, "gpurun_out", rnd + "_launches.csv")
+if os.path.exists(path):
+    lines = [l for l in open(path).read().splitlines() if l.startswith('"')]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for row in csv.DictReader(io.StringIO("\n".join(lines))):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(row["Metric Unit"], 1e-6)
+        name = row["Kernel Name"].split("(")[0].replace("void gsb::<unnamed>::", "")
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    out.append("== launch list (ncu --metrics gpu__time_duration.sum, cold-cache serialised launches; compare SHARES) ==")
+    out.append("command: python bench.py --steps 3 --warmup 3 --no-cpu   (first 400 launches)")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append("%-44s launches=%4d  total=%9.3f ms  share=%5.1f%%" % (k[:44], v[0], v[1], 100 * v[1] / tot))
+    with open(os.path.join(root, "profiles", rnd + "_launches.csv"), "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+
+rep = os.path.join(root, "gpurun_out", rnd + "_k1_full.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr = rows[0]
+    want = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+            "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+            "lts__t_sectors_op_read.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum"]
+    idx = [(w, hdr.index(w)) for w in want if w in hdr]
+    with open(os.path.join(root, "profiles", rnd + "_k1_metrics.csv"), "w") as fh:
+        w = csv.writer(fh)
+        w.writerow([n for n, _ in idx] + ["unit row: " + " | ".join(rows[1][i] for _, i in idx)])
+        for r in rows[2:]:
+            w.writerow([r[i].replace("void gsb::<unnamed>::", "") for _, i in idx])
+    out.append("")
+    out.append("== K1 (simplsFitFast) per size class, ncu --set full --clock-control none (one generation, 14 launches) ==")
+    out.append("%-10s %-8s %9s %10s %10s %6s %7s %7s %7s %7s %7s" % ("block", "grid", "time ms", "dram rd MB", "dram wr MB", "regs", "smem KB", "warps%", "issue%", "fp64%", "lds%"))
+    g = dict(idx)
+    tot_t = tot_rd = tot_wr = 0.0
+    for r in rows[2:]:
+        def f(name, d=0.0):
+            try:
+                return float(r[g[name]].replace(",", ""))
+            except (KeyError, ValueError):
+                return d
+        tot_t += f("gpu__time_duration.sum"); tot_rd += f("dram__bytes_read.sum"); tot_wr += f("dram__bytes_write.sum")
+        out.append("%-10s %-8s %9.3f %10.1f %10.1f %6.0f %7.1f %7.1f %7.1f %7.1f %7.1f" % (
+            r[g["Block Size"]].replace(" ", ""), r[g["Grid Size"]].split(",")[0].strip("("), f("gpu__time_duration.sum"),
+            f("dram__bytes_read.sum"), f("dram__bytes_write.sum"), f("launch__registers_per_thread"),
+            f("launch__shared_mem_per_block_dynamic"), f("sm__warps_active.avg.pct_of_peak_sustained_active"),
+            f("smsp__issue_active.avg.pct_of_peak_sustained_active"), f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")))
+    units = {n: rows[1][i] for n, i in idx}
+    out.append("sum over the generation: time %.3f %s (serialised under ncu), dram read %.1f %s, dram write %.1f %s" % (
+        tot_t, units.get("gpu__time_duration.sum", ""), tot_rd, units.get("dram__bytes_read.sum", ""), tot_wr, units.get("dram__bytes_write.sum", "")))
+
+text = "\n".join(out) + "\n"
+with open(os.path.join(root, "profiles", rnd + "_summary.txt"), "w") as fh:
+    fh.write(text)
+print(text)
