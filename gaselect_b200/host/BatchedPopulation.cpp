@@ -1,0 +1,183 @@
+// BatchedPopulation.cpp -- see BatchedPopulation.h.
+#include "BatchedPopulation.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <utility>
+
+namespace {
+
+std::string keyOf(const arma::uvec& cols) {
+	std::string key(cols.n_elem * sizeof(uint32_t), '\0');
+	for (arma::uword i = 0; i < cols.n_elem; ++i) {
+		const uint32_t v = static_cast<uint32_t>(cols[i]);
+		std::memcpy(&key[i * sizeof(uint32_t)], &v, sizeof(uint32_t));
+	}
+	return key;
+}
+
+} // namespace
+
+// Everything one generation reads and writes besides the (protected) elite of the base class.
+struct BatchedPopulation::LoopState {
+	RNG rng;
+	ShuffledSet shuffledSet;
+	double sumFitness = 0.0;
+	double minFitness = 0.0;
+	uint8_t tries1 = 0, tries2 = 0;           // persist across generations like the reference's locals
+	std::pair<bool, bool> duplicated{false, false};
+	LoopState(const std::vector<uint32_t>& seed, arma::uword chromosomeSize) : rng(seed), shuffledSet(chromosomeSize) {}
+};
+
+BatchedPopulation::BatchedPopulation(const Control& ctrl, GpuEvaluator& evaluator, const std::vector<uint32_t>& seed)
+	: Population(ctrl, evaluator, seed), gpu(evaluator) {}
+
+BatchedPopulation::~BatchedPopulation() {
+	for (size_t i = 0; i < this->slots.size(); ++i) delete this->slots[i];
+}
+
+BatchedPopulation::Lookup BatchedPopulation::lookup(Chromosome& ch) {
+	const arma::uvec cols = ch.toColumnSubset();
+	const std::string key = keyOf(cols);
+	std::unordered_map<std::string, Entry>::const_iterator hit = this->cache.find(key);
+	if (hit != this->cache.end()) {
+		++this->counters.cacheHits;
+		if (hit->second.status != 0) return HIT_FAILED; // the reference's evaluator would have thrown
+		ch.setFitness(hit->second.fitness);
+		return HIT_OK;
+	}
+	if (this->pendingSet.find(key) == this->pendingSet.end()) {
+		this->pendingSet.emplace(key, 1);
+		this->pendingKeys.push_back(key);
+		this->pending.push_back(cols);
+	}
+	ch.setFitness(0.0); // provisional: this pass will be replayed
+	return MISS;
+}
+
+void BatchedPopulation::flush() {
+	std::vector<double> fitness;
+	std::vector<int> status;
+	this->gpu.evaluateBatch(this->pending, fitness, status);
+	for (size_t i = 0; i < this->pending.size(); ++i) {
+		Entry e = {fitness[i], status[i]};
+		this->cache.emplace(this->pendingKeys[i], e);
+	}
+	this->counters.engineEvaluations += this->pending.size();
+	++this->counters.engineCalls;
+	this->pending.clear();
+	this->pendingKeys.clear();
+	this->pendingSet.clear();
+}
+
+// One pass over the initial population (src/SingleThreadPopulation.cpp:73-104).
+void BatchedPopulation::generateInitial(LoopState& st) {
+	while (this->slots.size() < this->ctrl.populationSize && !this->interrupted) {
+		Chromosome* candidate = new Chromosome(this->ctrl, st.shuffledSet, st.rng);
+		bool known = false;
+		for (size_t i = 0; i < this->slots.size() && !known; ++i) known = (*this->slots[i] == *candidate);
+		bool keep = false;
+		if (!known) {
+			const Lookup res = this->lookup(*candidate);
+			keep = res != HIT_FAILED;
+			if (keep) {
+				if (candidate->getFitness() < st.minFitness) st.minFitness = candidate->getFitness();
+				this->addChromosomeToElite(*candidate);
+			}
+		}
+		if (keep) this->slots.push_back(candidate); else delete candidate;
+		if (this->pollInterrupt()) this->interrupted = true;
+	}
+}
+
+// One pass over one generation (the mating loop of src/SingleThreadPopulation.cpp:129-233).
+void BatchedPopulation::mateGeneration(LoopState& st) {
+	const uint32_t maxDiscarded = Population::MAX_DISCARDED_SOLUTIONS_RATIO * this->ctrl.populationSize;
+	uint32_t discarded1 = 0, discarded2 = 0;
+	st.minFitness = 0.0;
+	ChVecIt front = this->slots.begin();   // child 1 fills from the front,
+	ChVecRIt back = this->slots.rbegin();  // child 2 from the back
+	while (front < back.base() && !this->interrupted) {
+		const bool twoChildren = (front + 1 != back.base());
+		Chromosome* parentA = this->drawChromosomeFromCurrentGeneration(st.rng(0.0, st.sumFitness));
+		Chromosome* parentB = this->drawChromosomeFromCurrentGeneration(st.rng(0.0, st.sumFitness), parentA);
+		parentA->mateWith(*parentB, st.rng, **front, **back);
+		const double betterParent = std::max(parentA->getFitness(), parentB->getFitness());
+		(*front)->mutate(st.rng);
+		if (twoChildren) (*back)->mutate(st.rng);
+		// reject children clearly worse than the better parent (the reference calls it minParentFitness)
+		const double cutoff = betterParent - this->ctrl.badSolutionThreshold * std::fabs(betterParent);
+		if (this->ctrl.maxDuplicateEliminationTries > 0) {
+			st.duplicated = Population::checkDuplicated(this->slots.begin(), this->slots.rbegin(), front, back);
+		}
+		for (int which = 0; which < 2; ++which) {
+			if (which == 1 && !twoChildren) break;
+			const bool dup = (which == 0) ? st.duplicated.first : st.duplicated.second;
+			uint8_t& tries = (which == 0) ? st.tries1 : st.tries2;
+			uint32_t& discarded = (which == 0) ? discarded1 : discarded2;
+			Chromosome& child = (which == 0) ? **front : **back;
+			if (dup && !(++tries > this->ctrl.maxDuplicateEliminationTries)) continue; // try this slot again
+			if (dup) child.randomlyReset(st.rng, st.shuffledSet); // too many duplicate tries: random restart
+			tries = 0;
+			const Lookup res = this->lookup(child);
+			if (res == HIT_FAILED) continue; // EvaluatorException: the slot is drawn again
+			const bool accepted = (res == MISS) || (child.getFitness() > cutoff) || (discarded > maxDiscarded);
+			if (accepted) {
+				if (child.getFitness() < st.minFitness) st.minFitness = child.getFitness();
+				this->addChromosomeToElite(child);
+				if (which == 0) ++front; else ++back;
+				discarded = 0;
+			} else {
+				++discarded;
+			}
+		}
+		if (this->pollInterrupt()) this->interrupted = true;
+	}
+}
+
+void BatchedPopulation::run() {
+	LoopState st(this->seed, this->ctrl.chromosomeSize);
+
+	// ---- initial population: speculate, evaluate in one call, replay until a pass has no miss --------
+	{
+		const LoopState before = st;
+		const SortedChromosomes eliteBefore = this->elite;
+		const double minEliteBefore = this->minEliteFitness;
+		for (;;) {
+			++this->counters.passes;
+			this->generateInitial(st);
+			if (this->pending.empty()) break;
+			this->flush();
+			for (size_t i = 0; i < this->slots.size(); ++i) delete this->slots[i];
+			this->slots.clear();
+			st = before;
+			this->elite = eliteBefore;
+			this->minEliteFitness = minEliteBefore;
+		}
+	}
+	this->initCurrentGeneration(st.shuffledSet, st.rng);
+	st.sumFitness = this->updateCurrentGeneration(this->slots, st.minFitness, true);
+
+	// ---- generations ------------------------------------------------------------------------------------
+	std::vector<Chromosome> slotsBefore;
+	for (int g = this->ctrl.numGenerations; g > 0 && !this->interrupted; --g) {
+		const LoopState before = st;
+		const SortedChromosomes eliteBefore = this->elite;
+		const double minEliteBefore = this->minEliteFitness;
+		slotsBefore.clear();
+		slotsBefore.reserve(this->slots.size());
+		for (size_t i = 0; i < this->slots.size(); ++i) slotsBefore.push_back(*this->slots[i]);
+		for (;;) {
+			++this->counters.passes;
+			this->mateGeneration(st);
+			if (this->pending.empty()) break;
+			this->flush();
+			st = before;
+			this->elite = eliteBefore;
+			this->minEliteFitness = minEliteBefore;
+			for (size_t i = 0; i < this->slots.size(); ++i) *this->slots[i] = slotsBefore[i];
+		}
+		st.sumFitness = this->updateCurrentGeneration(this->slots, st.minFitness, false);
+	}
+}

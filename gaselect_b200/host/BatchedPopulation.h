@@ -1,0 +1,67 @@
+// BatchedPopulation.h -- a Population (src/Population.h:33-420 of dakep/gaselect) that hands a whole
+// generation of candidate chromosomes to the B200 engine in ONE evaluateBatch call and still
+// produces exactly the run of the reference's SingleThreadPopulation (src/SingleThreadPopulation.cpp:43-251):
+// same random stream, same accept / reject decisions, same elite, same result.
+//
+// Why it is not simply "collect, evaluate, continue": inside a generation the reference interleaves
+// RNG draws with decisions that depend on each child's fitness (accept iff fitness > cutoff,
+// src/SingleThreadPopulation.cpp:171-184; EvaluatorException -> the slot is drawn again, :185-189), so
+// the set of candidates is only known after their fitness is.  SURVEY.md Appendix F protocol:
+//   1. snapshot the generation's state (RNG, ShuffledSet, child slots, elite, counters);
+//   2. run the generation against the fitness cache; a chromosome that is not cached yet is recorded
+//      and provisionally treated as accepted;
+//   3. if anything was recorded: evaluate all of it in one engine call, restore the snapshot, go to 2;
+//   4. a pass without a miss IS the reference's generation (fitness is a pure function of the subset).
+// At gaselect's defaults no child is rejected, so every generation costs one engine call.
+//
+// Compiled inside the gaselect package next to the reference sources (it includes the package's own
+// Population.h); selected at src/GenAlg.cpp:173-181 in place of SingleThreadPopulation.  See INTEGRATION.md.
+#ifndef GASELECT_B200_BATCHED_POPULATION_H
+#define GASELECT_B200_BATCHED_POPULATION_H
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "Population.h" // the reference's base class, on the package's include path
+
+#include "GpuEvaluator.h"
+
+class BatchedPopulation : public Population {
+public:
+	BatchedPopulation(const Control& ctrl, GpuEvaluator& evaluator, const std::vector<uint32_t>& seed);
+	~BatchedPopulation();
+
+	void run(); // src/Population.h:96
+
+	// bookkeeping for benchmarks: chromosomes scored by the engine, engine calls, replayed passes
+	struct Stats {
+		unsigned long long engineEvaluations = 0, engineCalls = 0, passes = 0, cacheHits = 0;
+	};
+	const Stats& stats() const { return this->counters; }
+
+	// optional cooperative interrupt (the reference polls R_CheckUserInterrupt, src/SingleThreadPopulation.cpp:30-38)
+	void setInterruptCheck(bool (*check)()) { this->interruptCheck = check; }
+
+private:
+	enum Lookup { HIT_OK, HIT_FAILED, MISS };
+	struct Entry { double fitness; int status; };
+	struct LoopState; // everything a generation mutates outside the base class
+
+	Lookup lookup(Chromosome& ch);
+	void flush();
+	void generateInitial(LoopState& st);
+	void mateGeneration(LoopState& st);
+	bool pollInterrupt() { return this->interruptCheck != nullptr && this->interruptCheck(); }
+
+	GpuEvaluator& gpu;
+	std::unordered_map<std::string, Entry> cache;
+	std::vector<arma::uvec> pending;
+	std::vector<std::string> pendingKeys;
+	std::unordered_map<std::string, char> pendingSet;
+	std::vector<Chromosome*> slots; // the generation being built (owned)
+	bool (*interruptCheck)() = nullptr;
+	Stats counters;
+};
+
+#endif

@@ -2,7 +2,10 @@
 // reference-side binding (gaselect_b200/host/GpuEvaluator) as a plain `Evaluator*`, so that the
 // reference's OWN population drivers (compiled from /root/reference/src into libgaselect_ref.so,
 // entry ref_ga_run of ref_shim.cpp) can be run on top of the CUDA engine: the drop-in test.
+#include "BatchedPopulation.h"
 #include "GpuEvaluator.h"
+
+#include <chrono>
 
 namespace {
 arma::mat wrapMatrix(const double* colmajor, int n, int p) {
@@ -57,5 +60,54 @@ int dropin_evaluate_one(void* evaluator, const uint32_t* cols, int k, double* fi
 }
 
 void dropin_destroy(void* evaluator) { delete static_cast<Evaluator*>(evaluator); }
+
+// genAlg() on the product's BatchedPopulation (same Control as ref_ga_run of ref_shim.cpp builds for the
+// reference's drivers).  stats: engine evaluations, engine calls, passes, cache hits.
+int dropin_ga_run_batched(void* evaluator, int chromosomeSize, int popSize, int numGenerations, int elitism, int minVariables,
+                          int maxVariables, double mutationProb, int maxDuplicateEliminationTries, double badSolutionThreshold,
+                          double convergenceThreshold, int convergenceGenerations, int crossover, int fitnessScaling,
+                          const uint32_t* seedvec, int resultCapacity, long long idxCapacity, int* nResult, uint32_t* resIdx,
+                          uint32_t* resOffsets, double* resFitness, int evolutionCapacity, int* nEvolution,
+                          double* fitnessEvolution, unsigned long long* stats, long long* elapsed_ns) {
+	try {
+		GpuEvaluator* gpu = dynamic_cast<GpuEvaluator*>(static_cast<Evaluator*>(evaluator));
+		if (!gpu) return 3;
+		Control ctrl(static_cast<uint16_t>(chromosomeSize), static_cast<uint16_t>(popSize), static_cast<uint16_t>(numGenerations),
+		             static_cast<uint16_t>(elitism), static_cast<uint16_t>(minVariables), static_cast<uint16_t>(maxVariables),
+		             mutationProb, 1, static_cast<uint16_t>(maxDuplicateEliminationTries), badSolutionThreshold,
+		             convergenceThreshold, static_cast<uint16_t>(convergenceGenerations), static_cast<CrossoverType>(crossover),
+		             static_cast<FitnessScaling>(fitnessScaling), OFF);
+		const std::vector<uint32_t> seed(seedvec, seedvec + 624);
+		BatchedPopulation pop(ctrl, *gpu, seed);
+		const auto t0 = std::chrono::steady_clock::now();
+		pop.run();
+		const auto t1 = std::chrono::steady_clock::now();
+		if (elapsed_ns) *elapsed_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+		if (stats) {
+			stats[0] = pop.stats().engineEvaluations;
+			stats[1] = pop.stats().engineCalls;
+			stats[2] = pop.stats().passes;
+			stats[3] = pop.stats().cacheHits;
+		}
+		int rc = 0, count = 0;
+		long long pos = 0;
+		const Population::SortedChromosomes result = pop.getResult();
+		for (Population::SortedChromosomes::const_iterator it = result.begin(); it != result.end(); ++it) {
+			const arma::uvec cols = it->toColumnSubset();
+			if (count >= resultCapacity || pos + static_cast<long long>(cols.n_elem) > idxCapacity) { rc = 1; break; }
+			resOffsets[count] = static_cast<uint32_t>(pos);
+			for (arma::uword j = 0; j < cols.n_elem; ++j) resIdx[pos++] = static_cast<uint32_t>(cols[j]);
+			resFitness[count++] = it->getFitness();
+		}
+		resOffsets[count] = static_cast<uint32_t>(pos);
+		*nResult = count;
+		const std::vector<double>& evo = pop.getFitnessEvolution();
+		*nEvolution = static_cast<int>(std::min<size_t>(evo.size(), static_cast<size_t>(evolutionCapacity)));
+		for (int i = 0; i < *nEvolution; ++i) fitnessEvolution[i] = evo[static_cast<size_t>(i)];
+		return rc;
+	} catch (...) {
+		return 2;
+	}
+}
 
 }

@@ -71,3 +71,70 @@ def test_virtual_interface_error_convention(dropin):
         assert dropin.dropin_evaluate_one(h, np.zeros(1, dtype=np.uint32), 0, C.byref(f)) == 1  # EvaluatorException
     finally:
         dropin.dropin_destroy(h)
+
+
+def _batched_run(dropin, handle, seedvec, chromosomeSize, popSize, numGenerations, elitism=10, minVariables=1, maxVariables=None,
+                 mutationProb=0.01, maxDup=0, badSolutionThreshold=2.0, crossover=0, fitnessScaling=0):
+    dropin.dropin_ga_run_batched.restype = C.c_int
+    dropin.dropin_ga_run_batched.argtypes = (
+        [C.c_void_p] + [C.c_int] * 6 + [C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _u32p,
+                                        C.c_int, C.c_longlong, C.POINTER(C.c_int), _u32p, _u32p, _f64p, C.c_int,
+                                        C.POINTER(C.c_int), _f64p, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"),
+                                        C.POINTER(C.c_longlong)])
+    maxVariables = int(maxVariables or chromosomeSize)
+    cap = popSize + elitism + 8
+    idx_cap = cap * maxVariables
+    n_res, n_evo, ns = C.c_int(0), C.c_int(0), C.c_longlong(0)
+    res_idx = np.zeros(idx_cap, dtype=np.uint32)
+    res_off = np.zeros(cap + 1, dtype=np.uint32)
+    res_fit = np.zeros(cap, dtype=np.float64)
+    evo = np.zeros(3 * (numGenerations + 2), dtype=np.float64)
+    stats = np.zeros(4, dtype=np.uint64)
+    rc = dropin.dropin_ga_run_batched(handle, chromosomeSize, popSize, numGenerations, elitism, minVariables, maxVariables,
+                                      mutationProb, maxDup, badSolutionThreshold, 1e-6, 0, crossover, fitnessScaling, seedvec,
+                                      cap, idx_cap, C.byref(n_res), res_idx, res_off, res_fit, len(evo), C.byref(n_evo), evo,
+                                      stats, C.byref(ns))
+    assert rc == 0
+    return {"subsets": [res_idx[res_off[i]:res_off[i + 1]].tolist() for i in range(n_res.value)],
+            "fitness": res_fit[:n_res.value].copy(), "evolution": evo[:n_evo.value].reshape(-1, 3).copy(),
+            "engine_evaluations": int(stats[0]), "engine_calls": int(stats[1]), "passes": int(stats[2]),
+            "seconds": ns.value * 1e-9}
+
+
+def test_batched_population_reproduces_golden_single_thread_run(dropin, ref_lib, golden):
+    """The speculate-and-replay driver + one engine call per generation == SingleThreadPopulation."""
+    run = next(r for r in golden["ga_runs"] if r["numThreads"] == 1)
+    X, y = synth.closed_form()
+    sv = ref_lib.make_seedvec(golden["ga_seed"])
+    h = dropin.dropin_pls_create(_colmajor(X), np.ascontiguousarray(y), 40, 30, 2, 5, sv, 4, 3, 0.0, 1.0, 0.0)
+    try:
+        r = _batched_run(dropin, h, sv, 30, 40, 8, elitism=5, minVariables=3, maxVariables=10)
+    finally:
+        dropin.dropin_destroy(h)
+    assert r["subsets"] == run["subsets"]
+    assert rel_err(r["fitness"], run["fitness"]).max() <= 1e-8
+    assert rel_err(r["evolution"][:, 0], run["best"]).max() <= 1e-8
+    assert r["engine_calls"] <= 2 * (8 + 1) and r["engine_evaluations"] <= run["evaluations"]
+
+
+@pytest.mark.parametrize("threshold,dup", [(2.0, 0), (0.1, 0), (2.0, 3)])
+def test_batched_population_against_the_reference_driver_live(dropin, ref_lib, threshold, dup):
+    """BASELINE config 1 shape (n=100, p=200, population 100, evaluatorPLS defaults), fewer generations:
+    reference SingleThreadPopulation + reference PLSEvaluator on the CPU vs BatchedPopulation + engine.
+    threshold 0.1 forces real rejections (replayed passes), dup 3 exercises duplicate elimination."""
+    X, y = synth.gaussian(100, 200, seed=777)
+    sv = ref_lib.make_seedvec(321)
+    kw = dict(elitism=10, minVariables=5, maxVariables=30, badSolutionThreshold=threshold)
+    ev = ref_lib.pls_evaluator(X, y, sv)  # evaluatorPLS() defaults: 30 replications, srCV, 7 segments
+    want = ref_lib.ga_run(ev, sv, 200, 100, 6, numThreads=1, maxDuplicateEliminationTries=dup, **kw)
+    h = dropin.dropin_pls_create(_colmajor(X), np.ascontiguousarray(y), 100, 200, 30, 0, sv, 7, 1, 0.0, 1.0, 0.0)
+    try:
+        got = _batched_run(dropin, h, sv, 200, 100, 6, maxDup=dup, **kw)
+    finally:
+        dropin.dropin_destroy(h)
+    assert got["subsets"] == [s.tolist() for s in want["subsets"]]      # bit-exact chromosomes
+    assert rel_err(got["fitness"], want["fitness"]).max() <= 1e-8
+    assert rel_err(got["evolution"], want["fitnessEvolution"]).max() <= 1e-6  # mean / sd columns amplify 1e-8 differences
+    if threshold >= 2.0:
+        assert got["engine_calls"] == 6 + 1                               # one engine call per generation
+    assert got["engine_evaluations"] <= want["evaluations"]
