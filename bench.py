@@ -121,21 +121,29 @@ def reference_library():
 
 
 def cpu_leg(w, X, y, subsets, budget_s):
-    """The reference's own evaluator on the host cores, bounded sample of the population."""
+    """The reference's own evaluator on the host cores: the generation's chromosomes dealt to all host
+    threads (cloned evaluators over contiguous slices), repeated until about budget_s seconds of work."""
     lib, kind = reference_library()
     cores = os.cpu_count() or 1
     sv = lib.make_seedvec(GA_SEED)
     ev = lib.pls_evaluator(X, y, sv, **w["kw"])
-    probe = subsets[:cores]
-    _, _, t0 = ev.evaluate(probe, threads=cores, return_time=True)
-    per_round = max(t0, 1e-3)
-    rounds = int(max(1, min(len(subsets) // cores - 1, budget_s / per_round)))
-    sample = subsets[cores:cores + rounds * cores] or probe
-    _, st, t = ev.evaluate(sample, threads=cores, return_time=True)
-    return {"value": len(sample) / t, "unit": "evals/s", "cores": cores, "kind": kind,
-            "sample": "%d of the %d chromosomes of one generation (k %d..%d), %d host threads, %.1f s; linear algebra under the "
-                      "reference code is the repo's stand-in for Armadillo/BLAS (no R in the image)" %
-                      (len(sample), len(subsets), w["kmin"], w["kmax"], cores, t)}, len(sample), t
+    ev.evaluate(subsets[:cores], threads=cores)  # warm-up
+    sample = subsets[: max(cores, (len(subsets) // cores) * cores)]
+    done, spent, rounds = 0, 0.0, 0
+    while spent < budget_s and rounds < 1000:
+        _, st, t = ev.evaluate(sample, threads=cores, return_time=True)
+        done += len(sample)
+        spent += t
+        rounds += 1
+    return {"value": done / spent, "unit": "evals/s", "cores": cores, "kind": kind,
+            "sample": "%d x %d of the %d chromosomes of one generation (k %d..%d), %d host threads, %.1f s; linear algebra under "
+                      "the reference code is the repo's stand-in for Armadillo/BLAS (no R in the image)" %
+                      (rounds, len(sample), len(subsets), w["kmin"], w["kmax"], cores, spent)}, done, spent
+
+
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the K1 launches of ONE step from the committed
+# ncu --set full capture (profiles/r01_summary.txt); only valid for the default workload
+MEASURED_TRAFFIC = {("cfg3", 500): 5.685e9}
 
 
 def main():
@@ -146,7 +154,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--pop", type=int, default=0, help="chromosomes per GPU (default: the workload's)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -315,7 +323,9 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "algorithmic_bytes_per_step": algo_bytes, "k1_ms_per_step": k1,
-                         "k2_ms_per_step": float(np.mean(k2_ms)), "traffic": None},
+                         "k2_ms_per_step": float(np.mean(k2_ms)),
+                         "traffic": MEASURED_TRAFFIC.get((args.workload, w["pop"])),
+                         "traffic_source": "profiles/r01_summary.txt (ncu --set full, sum over the K1 launches of one step)"},
         }
         if not args.no_cpu and world == 1:
             cb, _, _ = cpu_leg(w, X, y, subsets, args.cpu_seconds)
