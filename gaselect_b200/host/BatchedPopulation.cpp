@@ -137,6 +137,10 @@ void BatchedPopulation::mateGeneration(LoopState& st) {
 }
 
 void BatchedPopulation::run() {
+	if (this->ctrl.numThreads > 1) this->runVirtualThreads(); else this->runSingle();
+}
+
+void BatchedPopulation::runSingle() {
 	LoopState st(this->seed, this->ctrl.chromosomeSize);
 
 	// ---- initial population: speculate, evaluate in one call, replay until a pass has no miss --------
@@ -179,5 +183,146 @@ void BatchedPopulation::run() {
 			for (size_t i = 0; i < this->slots.size(); ++i) *this->slots[i] = slotsBefore[i];
 		}
 		st.sumFitness = this->updateCurrentGeneration(this->slots, st.minFitness, false);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// numThreads > 1: the workers of MultiThreadedPopulation as virtual threads
+// ---------------------------------------------------------------------------------------------------------
+struct BatchedPopulation::Stream {
+	RNG rng;
+	ShuffledSet shuffledSet;
+	uint16_t offset = 0, count = 0; // the worker's slice of the population
+	Stream(const RNG& rng, arma::uword chromosomeSize) : rng(rng), shuffledSet(chromosomeSize) {}
+};
+
+// A worker's share of the initial population (src/MultiThreadedPopulation.cpp:88-123): duplicates are only
+// looked for inside the worker's own slice.
+void BatchedPopulation::generateInitialSlice(Stream& w) {
+	uint16_t filled = 0;
+	while (filled < w.count && !this->interrupted) {
+		Chromosome* candidate = new Chromosome(this->ctrl, w.shuffledSet, w.rng);
+		bool known = false;
+		for (uint16_t i = 0; i < filled && !known; ++i) known = (*this->slots[w.offset + i] == *candidate);
+		if (!known && this->lookup(*candidate) != HIT_FAILED) {
+			this->slots[w.offset + filled] = candidate;
+			++filled;
+		} else {
+			delete candidate;
+		}
+		if (this->pollInterrupt()) this->interrupted = true;
+	}
+}
+
+// A worker's share of one generation (src/MultiThreadedPopulation.cpp:129-250).  Differences to the
+// single-thread loop: counters are per call, the elite is not touched here, and a slot whose children keep
+// being rejected is eventually accepted as it is (:199-203).
+void BatchedPopulation::mateSlice(Stream& w, double sumFitness) {
+	const ChVecIt sliceBegin = this->slots.begin() + w.offset;
+	const ChVecRIt sliceEnd(sliceBegin + w.count);
+	const uint32_t maxDiscarded = static_cast<uint32_t>(Population::MAX_DISCARDED_SOLUTIONS_RATIO) * w.count;
+	ChVecIt front = sliceBegin;
+	ChVecRIt back = sliceEnd;
+	uint8_t tries[2] = {0, 0};
+	uint32_t discarded[2] = {0, 0};
+	std::pair<bool, bool> duplicated(false, false);
+	while (front < back.base() && !this->interrupted) {
+		const bool twoChildren = (front + 1 != back.base());
+		Chromosome* parentA = this->drawChromosomeFromCurrentGeneration(w.rng(0.0, sumFitness));
+		Chromosome* parentB = this->drawChromosomeFromCurrentGeneration(w.rng(0.0, sumFitness), parentA);
+		parentA->mateWith(*parentB, w.rng, **front, **back);
+		const double betterParent = std::max(parentA->getFitness(), parentB->getFitness());
+		(*front)->mutate(w.rng);
+		if (twoChildren) (*back)->mutate(w.rng);
+		const double cutoff = betterParent - this->ctrl.badSolutionThreshold * std::fabs(betterParent);
+		if (this->ctrl.maxDuplicateEliminationTries > 0) {
+			duplicated = Population::checkDuplicated(sliceBegin, sliceEnd, front, back);
+		}
+		for (int which = 0; which < 2; ++which) {
+			if (which == 1 && !twoChildren) break;
+			const bool dup = (which == 0) ? duplicated.first : duplicated.second;
+			Chromosome& child = (which == 0) ? **front : **back;
+			if (dup && !(++tries[which] > this->ctrl.maxDuplicateEliminationTries)) continue;
+			if (dup) child.randomlyReset(w.rng, w.shuffledSet);
+			tries[which] = 0;
+			const Lookup res = this->lookup(child);
+			if (res == HIT_FAILED) continue; // EvaluatorException: the slot is drawn again
+			bool accepted = (res == MISS) || (child.getFitness() > cutoff);
+			if (!accepted && ++discarded[which] > maxDiscarded) { // "the algorithm may be stuck": keep the child
+				discarded[which] = 0;
+				accepted = true;
+			}
+			if (accepted) { if (which == 0) ++front; else ++back; }
+		}
+		if (this->pollInterrupt()) this->interrupted = true;
+	}
+}
+
+void BatchedPopulation::runVirtualThreads() {
+	const uint16_t T = this->ctrl.numThreads;
+	RNG mainRng(this->seed);
+	ShuffledSet mainSet(this->ctrl.chromosomeSize);
+	this->slots.assign(this->ctrl.populationSize, static_cast<Chromosome*>(nullptr));
+	this->initCurrentGeneration(mainSet, mainRng);
+
+	// slices and seeds in the order the reference hands them out (src/MultiThreadedPopulation.cpp:260-262,301-323)
+	const uint16_t perThread = this->ctrl.populationSize / T;
+	int remaining = this->ctrl.populationSize % T;
+	std::vector<Stream> workers;
+	workers.reserve(T);
+	uint16_t offset = 0;
+	for (int i = T - 2; i >= 0; --i) {
+		const uint32_t workerSeed = mainRng();
+		Stream w(RNG(workerSeed), this->ctrl.chromosomeSize);
+		w.count = perThread;
+		if (remaining > 0) { --remaining; ++w.count; }
+		w.offset = offset;
+		offset += w.count;
+		workers.push_back(w);
+	}
+	{ // the main thread mates the last slice with the stream the seeds were drawn from
+		Stream w(mainRng, this->ctrl.chromosomeSize);
+		w.shuffledSet = mainSet;
+		w.count = perThread;
+		w.offset = offset;
+		workers.push_back(w);
+	}
+	auto minFitnessOfSlots = [&]() {
+		double m = this->slots[0]->getFitness();
+		for (size_t i = 1; i < this->slots.size(); ++i) m = std::min(m, this->slots[i]->getFitness());
+		return m;
+	};
+
+	// ---- initial population ---------------------------------------------------------------------------------
+	{
+		const std::vector<Stream> before = workers;
+		for (;;) {
+			++this->counters.passes;
+			for (size_t t = 0; t < workers.size(); ++t) this->generateInitialSlice(workers[t]);
+			if (this->pending.empty()) break;
+			this->flush();
+			for (size_t i = 0; i < this->slots.size(); ++i) { delete this->slots[i]; this->slots[i] = nullptr; }
+			workers = before;
+		}
+	}
+	if (this->interrupted) return;
+	double sumFitness = this->updateCurrentGeneration(this->slots, minFitnessOfSlots(), true, true);
+
+	// ---- generations ------------------------------------------------------------------------------------------
+	std::vector<Chromosome> slotsBefore;
+	for (int g = this->ctrl.numGenerations; g > 0 && !this->interrupted; --g) {
+		const std::vector<Stream> before = workers;
+		slotsBefore.clear();
+		slotsBefore.reserve(this->slots.size());
+		for (size_t i = 0; i < this->slots.size(); ++i) slotsBefore.push_back(*this->slots[i]);
+		for (;;) {
+			++this->counters.passes;
+			for (size_t t = 0; t < workers.size(); ++t) this->mateSlice(workers[t], sumFitness);
+			if (this->pending.empty()) break;
+			this->flush();
+			workers = before;
+			for (size_t i = 0; i < this->slots.size(); ++i) *this->slots[i] = slotsBefore[i];
+		}
+		sumFitness = this->updateCurrentGeneration(this->slots, minFitnessOfSlots(), false, true);
 	}
 }

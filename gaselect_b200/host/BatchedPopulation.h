@@ -1,7 +1,11 @@
 // BatchedPopulation.h -- a Population (src/Population.h:33-420 of dakep/gaselect) that hands a whole
 // generation of candidate chromosomes to the B200 engine in ONE evaluateBatch call and still
-// produces exactly the run of the reference's SingleThreadPopulation (src/SingleThreadPopulation.cpp:43-251):
-// same random stream, same accept / reject decisions, same elite, same result.
+// produces exactly the run of the reference's drivers: SingleThreadPopulation
+// (src/SingleThreadPopulation.cpp:43-251) when ctrl.numThreads <= 1, MultiThreadedPopulation
+// (src/MultiThreadedPopulation.cpp:255-465) otherwise -- the latter's result depends on numThreads (every
+// worker owns a random stream and a slice of the population, :301-323,:471-482), so the workers are
+// reproduced as "virtual threads": same seeds, same slices, same per-slice loops, run one after the other
+// on the host (they never interact inside a generation).  Same accept / reject decisions, same elite, same result.
 //
 // Why it is not simply "collect, evaluate, continue": inside a generation the reference interleaves
 // RNG draws with decisions that depend on each child's fitness (accept iff fitness > cutoff,
@@ -47,11 +51,16 @@ private:
 	enum Lookup { HIT_OK, HIT_FAILED, MISS };
 	struct Entry { double fitness; int status; };
 	struct LoopState; // everything a generation mutates outside the base class
+	struct Stream;    // one (virtual) worker of the multi-threaded driver
 
 	Lookup lookup(Chromosome& ch);
 	void flush();
 	void generateInitial(LoopState& st);
 	void mateGeneration(LoopState& st);
+	void runSingle();
+	void runVirtualThreads();
+	void generateInitialSlice(Stream& w);
+	void mateSlice(Stream& w, double sumFitness);
 	bool pollInterrupt() { return this->interruptCheck != nullptr && this->interruptCheck(); }
 
 	GpuEvaluator& gpu;

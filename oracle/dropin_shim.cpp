@@ -64,7 +64,7 @@ void dropin_destroy(void* evaluator) { delete static_cast<Evaluator*>(evaluator)
 // genAlg() on the product's BatchedPopulation (same Control as ref_ga_run of ref_shim.cpp builds for the
 // reference's drivers).  stats: engine evaluations, engine calls, passes, cache hits.
 int dropin_ga_run_batched(void* evaluator, int chromosomeSize, int popSize, int numGenerations, int elitism, int minVariables,
-                          int maxVariables, double mutationProb, int maxDuplicateEliminationTries, double badSolutionThreshold,
+                          int maxVariables, double mutationProb, int numThreads, int maxDuplicateEliminationTries, double badSolutionThreshold,
                           double convergenceThreshold, int convergenceGenerations, int crossover, int fitnessScaling,
                           const uint32_t* seedvec, int resultCapacity, long long idxCapacity, int* nResult, uint32_t* resIdx,
                           uint32_t* resOffsets, double* resFitness, int evolutionCapacity, int* nEvolution,
@@ -74,7 +74,7 @@ int dropin_ga_run_batched(void* evaluator, int chromosomeSize, int popSize, int 
 		if (!gpu) return 3;
 		Control ctrl(static_cast<uint16_t>(chromosomeSize), static_cast<uint16_t>(popSize), static_cast<uint16_t>(numGenerations),
 		             static_cast<uint16_t>(elitism), static_cast<uint16_t>(minVariables), static_cast<uint16_t>(maxVariables),
-		             mutationProb, 1, static_cast<uint16_t>(maxDuplicateEliminationTries), badSolutionThreshold,
+		             mutationProb, static_cast<uint16_t>(numThreads), static_cast<uint16_t>(maxDuplicateEliminationTries), badSolutionThreshold,
 		             convergenceThreshold, static_cast<uint16_t>(convergenceGenerations), static_cast<CrossoverType>(crossover),
 		             static_cast<FitnessScaling>(fitnessScaling), OFF);
 		const std::vector<uint32_t> seed(seedvec, seedvec + 624);

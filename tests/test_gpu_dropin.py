@@ -74,10 +74,10 @@ def test_virtual_interface_error_convention(dropin):
 
 
 def _batched_run(dropin, handle, seedvec, chromosomeSize, popSize, numGenerations, elitism=10, minVariables=1, maxVariables=None,
-                 mutationProb=0.01, maxDup=0, badSolutionThreshold=2.0, crossover=0, fitnessScaling=0):
+                 mutationProb=0.01, maxDup=0, badSolutionThreshold=2.0, crossover=0, fitnessScaling=0, numThreads=1):
     dropin.dropin_ga_run_batched.restype = C.c_int
     dropin.dropin_ga_run_batched.argtypes = (
-        [C.c_void_p] + [C.c_int] * 6 + [C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _u32p,
+        [C.c_void_p] + [C.c_int] * 6 + [C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _u32p,
                                         C.c_int, C.c_longlong, C.POINTER(C.c_int), _u32p, _u32p, _f64p, C.c_int,
                                         C.POINTER(C.c_int), _f64p, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"),
                                         C.POINTER(C.c_longlong)])
@@ -91,7 +91,7 @@ def _batched_run(dropin, handle, seedvec, chromosomeSize, popSize, numGeneration
     evo = np.zeros(3 * (numGenerations + 2), dtype=np.float64)
     stats = np.zeros(4, dtype=np.uint64)
     rc = dropin.dropin_ga_run_batched(handle, chromosomeSize, popSize, numGenerations, elitism, minVariables, maxVariables,
-                                      mutationProb, maxDup, badSolutionThreshold, 1e-6, 0, crossover, fitnessScaling, seedvec,
+                                      mutationProb, numThreads, maxDup, badSolutionThreshold, 1e-6, 0, crossover, fitnessScaling, seedvec,
                                       cap, idx_cap, C.byref(n_res), res_idx, res_off, res_fit, len(evo), C.byref(n_evo), evo,
                                       stats, C.byref(ns))
     assert rc == 0
@@ -138,3 +138,36 @@ def test_batched_population_against_the_reference_driver_live(dropin, ref_lib, t
     if threshold >= 2.0:
         assert got["engine_calls"] == 6 + 1                               # one engine call per generation
     assert got["engine_evaluations"] <= want["evaluations"]
+
+
+def test_batched_population_virtual_threads_reproduce_golden_four_thread_run(dropin, ref_lib, golden):
+    """numThreads = 4: MultiThreadedPopulation's result depends on the number of workers (one random stream and
+    one slice each); BatchedPopulation reproduces them as virtual threads, one engine call per generation."""
+    run = next(r for r in golden["ga_runs"] if r["numThreads"] == 4)
+    X, y = synth.closed_form()
+    sv = ref_lib.make_seedvec(golden["ga_seed"])
+    h = dropin.dropin_pls_create(_colmajor(X), np.ascontiguousarray(y), 40, 30, 2, 5, sv, 4, 3, 0.0, 1.0, 0.0)
+    try:
+        r = _batched_run(dropin, h, sv, 30, 40, 8, elitism=5, minVariables=3, maxVariables=10, numThreads=4)
+    finally:
+        dropin.dropin_destroy(h)
+    assert r["subsets"] == run["subsets"]
+    assert rel_err(r["fitness"], run["fitness"]).max() <= 1e-8
+    assert rel_err(r["evolution"][:, 0], run["best"]).max() <= 1e-8
+
+
+@pytest.mark.parametrize("threads,threshold,dup", [(3, 2.0, 0), (7, 0.1, 0), (4, 2.0, 2)])
+def test_batched_population_virtual_threads_against_the_reference_driver_live(dropin, ref_lib, threads, threshold, dup):
+    X, y = synth.gaussian(100, 200, seed=777)
+    sv = ref_lib.make_seedvec(99)
+    kw = dict(elitism=10, minVariables=5, maxVariables=30, badSolutionThreshold=threshold)
+    ev = ref_lib.pls_evaluator(X, y, sv, numReplications=4, innerSegments=5)
+    want = ref_lib.ga_run(ev, sv, 200, 100, 6, numThreads=threads, maxDuplicateEliminationTries=dup, **kw)
+    h = dropin.dropin_pls_create(_colmajor(X), np.ascontiguousarray(y), 100, 200, 4, 0, sv, 5, 1, 0.0, 1.0, 0.0)
+    try:
+        got = _batched_run(dropin, h, sv, 200, 100, 6, maxDup=dup, numThreads=threads, **kw)
+    finally:
+        dropin.dropin_destroy(h)
+    assert got["subsets"] == [s.tolist() for s in want["subsets"]]
+    assert rel_err(got["fitness"], want["fitness"]).max() <= 1e-8
+    assert rel_err(got["evolution"], want["fitnessEvolution"]).max() <= 1e-6
