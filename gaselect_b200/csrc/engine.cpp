@@ -151,6 +151,7 @@ struct gsb_engine {
 	PinnedArray<uint32_t> hIdx, hOffsets;
 	PinnedArray<int> hBucket, hStatus;
 	PinnedArray<double> hFitness;
+	DeviceArray<double> spill;       // Gram rows of very large subsets (K1 spill path), one region per size class
 	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
 
@@ -183,6 +184,7 @@ void releaseDevice(gsb_engine* e) {
 	e->zpool.release(); e->gram.release(); e->s0.release(); e->xm.release();
 	e->fits.release(); e->tasks.release(); e->blocks.release(); e->outerRows.release();
 	e->traceBuf.release();
+	e->spill.release();
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
@@ -812,6 +814,15 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				GSB_CUDA(cudaEventRecord(e->evFork, e->stream));
 				for (int i = 0; i < nside; ++i) GSB_CUDA(cudaStreamWaitEvent(e->side[i], e->evFork, 0));
 			}
+			// size classes whose packed Gram exceeds shared memory spill their last rows to a global scratch
+			std::vector<long long> spillPerCta(e->buckets.size(), 0), spillOffset(e->buckets.size(), 0);
+			long long spillTotal = 0;
+			for (size_t b = 0; b < e->buckets.size(); ++b) {
+				spillPerCta[b] = gsb::fitKernelSpillDoubles(e->buckets[b].kMax, e->tableA, e->smemLimit, e->maxTasks, e->maxBlockLd);
+				spillOffset[b] = spillTotal;
+				spillTotal += spillPerCta[b] * static_cast<long long>(e->buckets[b].count) * static_cast<long long>(e->plan.fits.size());
+			}
+			if (spillTotal > 0) e->spill.reserve(static_cast<size_t>(spillTotal));
 			int slot = 0;
 			for (size_t bi = e->buckets.size(); bi-- > 0; ++slot) {
 				const size_t b = bi;
@@ -839,6 +850,8 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.trace = e->traceBuf.ptr;
 				prm.maxTasks = e->maxTasks;
 				prm.maxBlockLd = e->maxBlockLd;
+				prm.spill = spillPerCta[b] > 0 ? e->spill.ptr + spillOffset[b] : nullptr;
+				prm.spillStride = spillPerCta[b];
 				GSB_CUDA(gsb::launchFitKernel(prm, e->buckets[b].kMax, e->tableA, e->smemLimit, launchStream, &ctas));
 				++launches;
 			}
@@ -1098,7 +1111,7 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
 		prm.fits = dFit.ptr; prm.tasks = nullptr; prm.blocks = nullptr;
 		prm.idx = dIdx.ptr; prm.offsets = dOff.ptr; prm.bucket = dBucket.ptr; prm.bucketCount = 1; prm.nfits = 1;
 		prm.p = k; prm.maxNComp = A; prm.innerDests = 0; prm.outerDests = 0;
-		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr; prm.trace = nullptr; prm.maxTasks = 0; prm.maxBlockLd = 0;
+		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr; prm.trace = nullptr; prm.maxTasks = 0; prm.maxBlockLd = 0; prm.spill = nullptr; prm.spillStride = 0;
 		GSB_CUDA(gsb::launchFitKernel(prm, k, A, e->smemLimit, e->stream, nullptr));
 		std::vector<double> out(static_cast<size_t>(k) * A + A);
 		GSB_CUDA(cudaMemcpyAsync(out.data(), dOut.ptr, out.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));

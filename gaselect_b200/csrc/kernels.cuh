@@ -61,6 +61,8 @@ struct FitParams {
 	double* ostat;           // [chrom][outerDest][maxNComp][2] = (sum e, sum e^2)
 	double* coefOut;         // optional (gsb_simpls): [k x A] + A intercepts for fit 0 / bucket[0]
 	long long* trace;        // optional (profiling): clock64() stamps of one CTA per launch
+	double* spill;           // optional: per-CTA scratch for Gram rows beyond shared memory (large subsets)
+	long long spillStride;   // doubles per CTA
 	int maxTasks;            // most prediction tasks any fit has
 	int maxBlockLd;          // largest padded row count of a held-out block
 };
@@ -119,6 +121,7 @@ void launchBlockGather(const double* z, int ldz, int ncols, const uint32_t* cols
                        double* dst, int ld, cudaStream_t stream);
 int fitKernelSharedBytes(int k, int A);
 int fitKernelMaxK(int A, int smemLimit);
+long long fitKernelSpillDoubles(int kMax, int A, int smemLimit, int maxTasks, int maxBlockLd);
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
 void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream);
 cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream);

@@ -35,7 +35,7 @@ namespace {
 constexpr int kChunk = 10;  // components per prediction pass (accumulators held in registers)
 constexpr int kDots = 6;    // loadings projected in the same reduction round as S'w and s0'S
 constexpr int kRedMax = 20; // widest reduction (values per thread)
-constexpr int kMaxWarps = 8;
+constexpr int kMaxWarps = 12; // 384 threads: subsets up to k = 384 on the spill path
 
 __device__ __forceinline__ double shflXor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
@@ -463,10 +463,12 @@ struct FastCarve {
 };
 
 // wantXt < 0: host decision; else the number of held-out blocks staged per pass (0, 1 or 2), as told
-__host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTasks, int maxBlockLd, int wantXt) {
+// rowsInSmem: packed Gram rows kept in shared memory (k on the plain path; the rest is spilled to an L2 scratch)
+__host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTasks, int maxBlockLd, int wantXt, int rowsInSmem) {
 	FastCarve c;
 	const int Apad = roundUp(A, 2);
-	const int ntri = k * (k + 1) / 2;
+	const int rs = min(k, rowsInSmem);
+	const int ntri = rs * (rs + 1) / 2;
 	const int coefD = k * Apad, partD = (nw > 1) ? nw * 32 * kChunk : 0;
 	const int minStage = 32 * min(k, 8);
 	const int plain = roundUp(max(ntri, coefD + partD + minStage), 2);
@@ -541,8 +543,150 @@ __device__ __forceinline__ void blockSum16(double (&x)[NV], double* red, int& ph
 	}
 }
 
-template <int AREG>
-__global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams prm, const int stageAll) {
+// One row of w = G S from the packed triangle in shared memory.  Thread r owns row r; the rows of a warp
+// are consecutive, [rlo, rhi] is warp-uniform.  Three warp-uniform phases: left of the 32-wide diagonal band
+// (own packed row), the band (either side of the diagonal), below the band (column r of the rows c).
+__device__ __forceinline__ double symvRow(const double* __restrict__ P, const double* __restrict__ S, int k, int r, int rlo, int rhi) {
+	const double* __restrict__ pr = P + r * (r + 1) / 2;
+	const double* __restrict__ pc = P + r;
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+	int c = 0;
+	for (; c + 7 < rlo; c += 8) {
+		const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+		const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
+		const double2 s45 = *reinterpret_cast<const double2*>(S + c + 4);
+		const double2 s67 = *reinterpret_cast<const double2*>(S + c + 6);
+		a0 = fma(pr[c], s01.x, a0);
+		a1 = fma(pr[c + 1], s01.y, a1);
+		a2 = fma(pr[c + 2], s23.x, a2);
+		a3 = fma(pr[c + 3], s23.y, a3);
+		a0 = fma(pr[c + 4], s45.x, a0);
+		a1 = fma(pr[c + 5], s45.y, a1);
+		a2 = fma(pr[c + 6], s67.x, a2);
+		a3 = fma(pr[c + 7], s67.y, a3);
+	}
+	for (; c < rlo; ++c) a0 = fma(pr[c], S[c], a0);
+	int tc = rlo * (rlo + 1) / 2;
+	for (; c + 1 <= rhi; c += 2) {
+		const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+		const int t1 = tc + c + 1;
+		const double g0 = (c <= r) ? pr[c] : pc[tc];
+		const double g1 = (c + 1 <= r) ? pr[c + 1] : pc[t1];
+		a0 = fma(g0, s01.x, a0);
+		a1 = fma(g1, s01.y, a1);
+		tc = t1 + c + 2;
+	}
+	for (; c <= rhi; ++c) {
+		const double g = (c <= r) ? pr[c] : pc[tc];
+		a2 = fma(g, S[c], a2);
+		tc += c + 1;
+	}
+	for (; c + 7 < k; c += 8) {
+		const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+		const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
+		const double2 s45 = *reinterpret_cast<const double2*>(S + c + 4);
+		const double2 s67 = *reinterpret_cast<const double2*>(S + c + 6);
+		const int t1 = tc + c + 1, t2 = t1 + c + 2, t3 = t2 + c + 3, t4 = t3 + c + 4;
+		const int t5 = t4 + c + 5, t6 = t5 + c + 6, t7 = t6 + c + 7;
+		a0 = fma(pc[tc], s01.x, a0);
+		a1 = fma(pc[t1], s01.y, a1);
+		a2 = fma(pc[t2], s23.x, a2);
+		a3 = fma(pc[t3], s23.y, a3);
+		a0 = fma(pc[t4], s45.x, a0);
+		a1 = fma(pc[t5], s45.y, a1);
+		a2 = fma(pc[t6], s67.x, a2);
+		a3 = fma(pc[t7], s67.y, a3);
+		tc = t7 + c + 8;
+	}
+	for (; c < k; ++c) {
+		a3 = fma(pc[tc], S[c], a3);
+		tc += c + 1;
+	}
+	return (a0 + a1) + (a2 + a3);
+}
+
+// The same row when the Gram rows [rs, k) live in the global scratch (rs is a multiple of 32 or k, so a warp's
+// rows are all on one side).  Scratch row a - rs holds entries (a, 0..a) with stride ldS (a multiple of 4).
+__device__ __forceinline__ double symvRowSpill(const double* __restrict__ P, const double* __restrict__ S, const double* spill,
+                                               int k, int rs, int ldS, int r, int rlo, int rhi) {
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+	int c = 0;
+	if (rlo < rs) {
+		// this warp's rows are in shared memory: as symvRow up to the first spilled row ...
+		const double* __restrict__ pr = P + r * (r + 1) / 2;
+		const double* __restrict__ pc = P + r;
+		for (; c + 3 < rlo; c += 4) {
+			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
+			a0 = fma(pr[c], s01.x, a0);
+			a1 = fma(pr[c + 1], s01.y, a1);
+			a2 = fma(pr[c + 2], s23.x, a2);
+			a3 = fma(pr[c + 3], s23.y, a3);
+		}
+		for (; c < rlo; ++c) a0 = fma(pr[c], S[c], a0);
+		int tc = rlo * (rlo + 1) / 2;
+		for (; c <= rhi; ++c) {
+			const double g = (c <= r) ? pr[c] : pc[tc];
+			a1 = fma(g, S[c], a1);
+			tc += c + 1;
+		}
+		for (; c + 3 < rs; c += 4) {
+			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
+			const int t1 = tc + c + 1, t2 = t1 + c + 2, t3 = t2 + c + 3;
+			a0 = fma(pc[tc], s01.x, a0);
+			a1 = fma(pc[t1], s01.y, a1);
+			a2 = fma(pc[t2], s23.x, a2);
+			a3 = fma(pc[t3], s23.y, a3);
+			tc = t3 + c + 4;
+		}
+		for (; c < rs; ++c) {
+			a2 = fma(pc[tc], S[c], a2);
+			tc += c + 1;
+		}
+	} else {
+		// ... this warp's rows are spilled: own row as 32-byte runs from the scratch (L2)
+		const double* gr = spill + static_cast<size_t>(r - rs) * ldS;
+		for (; c + 3 < rlo; c += 4) {
+			const double2 g01 = __ldcg(reinterpret_cast<const double2*>(gr + c));
+			const double2 g23 = __ldcg(reinterpret_cast<const double2*>(gr + c + 2));
+			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
+			a0 = fma(g01.x, s01.x, a0);
+			a1 = fma(g01.y, s01.y, a1);
+			a2 = fma(g23.x, s23.x, a2);
+			a3 = fma(g23.y, s23.y, a3);
+		}
+		for (; c < rlo; ++c) a0 = fma(__ldcg(gr + c), S[c], a0);
+		for (; c <= rhi; ++c) { // the band: (r, c) for c <= r, else (c, r) of another spilled row
+			const double g = (c <= r) ? __ldcg(gr + c) : __ldcg(spill + static_cast<size_t>(c - rs) * ldS + r);
+			a1 = fma(g, S[c], a1);
+		}
+	}
+	// below the band / beyond the shared rows: column r of the spilled rows c (coalesced over the lanes)
+	c = max(c, rs);
+	const double* gc = spill + r;
+	for (; c + 3 < k; c += 4) {
+		const double2 s01 = *reinterpret_cast<const double2*>(S + c);
+		const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
+		const double g0 = __ldcg(gc + static_cast<size_t>(c - rs) * ldS);
+		const double g1 = __ldcg(gc + static_cast<size_t>(c + 1 - rs) * ldS);
+		const double g2 = __ldcg(gc + static_cast<size_t>(c + 2 - rs) * ldS);
+		const double g3 = __ldcg(gc + static_cast<size_t>(c + 3 - rs) * ldS);
+		a0 = fma(g0, s01.x, a0);
+		a1 = fma(g1, s01.y, a1);
+		a2 = fma(g2, s23.x, a2);
+		a3 = fma(g3, s23.y, a3);
+	}
+	for (; c < k; ++c) a3 = fma(__ldcg(gc + static_cast<size_t>(c - rs) * ldS), S[c], a3);
+	return (a0 + a1) + (a2 + a3);
+}
+
+// SPILL: packed Gram rows >= rSplit (a multiple of 32) do not fit in shared memory; they are gathered into a
+// per-CTA scratch in global memory (L2-resident while the CTA runs; row stride roundUp(k, 4)) and read from
+// there by every matrix-vector product: own rows as contiguous per-thread runs, column accesses coalesced.
+template <int AREG, bool SPILL>
+__global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) simplsFitFast(const FitParams prm, const int stageAll, const int rSplit) {
 	extern __shared__ __align__(16) double smem[];
 	static_assert(AREG % 2 == 0 && AREG + 2 <= 16, "one reduction round holds tn^2, q*tn and every projection");
 	const int NT = blockDim.x, NW = NT >> 5;
@@ -557,11 +701,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 	const FitDesc fd = prm.fits[fi];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-	const FastCarve cv = fastCarve(k, A, NW, prm.maxTasks, prm.maxBlockLd, stageAll);
+	const int rs = SPILL ? min(k, rSplit) : k; // Gram rows [0, rs) live in shared memory
+	const FastCarve cv = fastCarve(k, A, NW, prm.maxTasks, prm.maxBlockLd, stageAll, rs);
 	double* __restrict__ P = smem + cv.P;
 	double* __restrict__ S = smem + cv.S;
 	double* red = smem + cv.red;
 	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(smem + cv.sel);
+	const int ldS = roundUp(k, 4);
+	double* spill = SPILL ? prm.spill + static_cast<size_t>(blockIdx.x) * prm.spillStride : nullptr;
 	int phase = 0;
 
 	const bool tracing = prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
@@ -577,7 +724,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 		uint32_t selB[kMaxWarps];
 #pragma unroll
 		for (int j = 0; j < kMaxWarps; ++j) selB[j] = (lane + 32 * j < k) ? sel[lane + 32 * j] : 0u;
-		for (int a = warp; a < k; a += NW) {
+		for (int a = warp; a < rs; a += NW) {
 			const double* __restrict__ grow = gsrc + tri(sel[a]);
 			double* __restrict__ prow = P + a * (a + 1) / 2;
 #pragma unroll
@@ -585,6 +732,19 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 				if (32 * j <= a) {
 					const int b = lane + 32 * j;
 					if (b <= a) cpAsync8(prow + b, grow + selB[j]);
+				}
+			}
+		}
+		if (SPILL) {
+			for (int a = rs + warp; a < k; a += NW) {
+				const double* __restrict__ grow = gsrc + tri(sel[a]);
+				double* srow = spill + static_cast<size_t>(a - rs) * ldS;
+#pragma unroll
+				for (int j = 0; j < kMaxWarps; ++j) {
+					if (32 * j <= a) {
+						const int b = lane + 32 * j;
+						if (b <= a) srow[b] = __ldg(grow + selB[j]);
+					}
 				}
 			}
 		}
@@ -622,69 +782,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 	// rows of a warp are consecutive: [rlo, rhi] is warp-uniform
 	const int rlo = min(warp * 32, k - 1);
 	const int rhi = min(rlo + 31, k - 1);
-	const double* __restrict__ pr = P + r * (r + 1) / 2;
-	const double* __restrict__ pc = P + r;
-	const int triLo = rlo * (rlo + 1) / 2;
 	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 
 	// ---- SIMPLS components -------------------------------------------------------------------
 	double cum = 0.0;
 #pragma unroll 1
 	for (int comp = 0; comp < A; ++comp) {
-		double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-		int c = 0;
-		for (; c + 7 < rlo; c += 8) { // left of the band: own packed row
-			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
-			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
-			const double2 s45 = *reinterpret_cast<const double2*>(S + c + 4);
-			const double2 s67 = *reinterpret_cast<const double2*>(S + c + 6);
-			a0 = fma(pr[c], s01.x, a0);
-			a1 = fma(pr[c + 1], s01.y, a1);
-			a2 = fma(pr[c + 2], s23.x, a2);
-			a3 = fma(pr[c + 3], s23.y, a3);
-			a0 = fma(pr[c + 4], s45.x, a0);
-			a1 = fma(pr[c + 5], s45.y, a1);
-			a2 = fma(pr[c + 6], s67.x, a2);
-			a3 = fma(pr[c + 7], s67.y, a3);
-		}
-		for (; c < rlo; ++c) a0 = fma(pr[c], S[c], a0);
-		int tc = triLo;
-		for (; c + 1 <= rhi; c += 2) { // the band: either side of the diagonal
-			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
-			const int t1 = tc + c + 1;
-			const double g0 = (c <= r) ? pr[c] : pc[tc];
-			const double g1 = (c + 1 <= r) ? pr[c + 1] : pc[t1];
-			a0 = fma(g0, s01.x, a0);
-			a1 = fma(g1, s01.y, a1);
-			tc = t1 + c + 2;
-		}
-		for (; c <= rhi; ++c) {
-			const double g = (c <= r) ? pr[c] : pc[tc];
-			a2 = fma(g, S[c], a2);
-			tc += c + 1;
-		}
-		for (; c + 7 < k; c += 8) {   // below the band: column r of rows c
-			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
-			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
-			const double2 s45 = *reinterpret_cast<const double2*>(S + c + 4);
-			const double2 s67 = *reinterpret_cast<const double2*>(S + c + 6);
-			const int t1 = tc + c + 1, t2 = t1 + c + 2, t3 = t2 + c + 3, t4 = t3 + c + 4;
-			const int t5 = t4 + c + 5, t6 = t5 + c + 6, t7 = t6 + c + 7;
-			a0 = fma(pc[tc], s01.x, a0);
-			a1 = fma(pc[t1], s01.y, a1);
-			a2 = fma(pc[t2], s23.x, a2);
-			a3 = fma(pc[t3], s23.y, a3);
-			a0 = fma(pc[t4], s45.x, a0);
-			a1 = fma(pc[t5], s45.y, a1);
-			a2 = fma(pc[t6], s67.x, a2);
-			a3 = fma(pc[t7], s67.y, a3);
-			tc = t7 + c + 8;
-		}
-		for (; c < k; ++c) {
-			a3 = fma(pc[tc], S[c], a3);
-			tc += c + 1;
-		}
-		const double w = (a0 + a1) + (a2 + a3);
+		const double w = SPILL ? symvRowSpill(P, S, spill, k, rs, ldS, r, rlo, rhi) : symvRow(P, S, k, r, rlo, rhi);
 
 		// ONE round: tn^2 = S'GS (:138), q*tn = s0'S (:148), projections V_j'w on every stored loading
 		double r1[2 + AREG];
@@ -952,17 +1056,36 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitFast(const FitParams 
 #undef GSB_STAMP
 }
 
+// rows of the packed Gram that fit in shared memory next to everything else (a multiple of 32, or k)
+inline int fastRowsInSmem(int k, int A, int maxTasks, int maxBlockLd, int smemLimit) {
+	const int nw = roundUp(k, 32) / 32;
+	if (fastCarve(k, A, nw, maxTasks, maxBlockLd, -1, k).total * 8 <= smemLimit) return k;
+	int rs = (k / 32) * 32;
+	while (rs >= 32 && fastCarve(k, A, nw, maxTasks, maxBlockLd, -1, rs).total * 8 > smemLimit) rs -= 32;
+	return rs >= 32 ? rs : 0;
+}
+
 template <int AREG>
-cudaError_t launchFast(const FitParams& prm, int kMax, int A, cudaStream_t stream, long long* ctas) {
+cudaError_t launchFast(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
 	const int threads = roundUp(kMax, 32);
-	const FastCarve cv = fastCarve(kMax, A, threads / 32, prm.maxTasks, prm.maxBlockLd, -1);
+	const int rs = fastRowsInSmem(kMax, A, prm.maxTasks, prm.maxBlockLd, smemLimit);
+	if (rs <= 0) return cudaErrorInvalidValue;
+	const FastCarve cv = fastCarve(kMax, A, threads / 32, prm.maxTasks, prm.maxBlockLd, -1, rs);
 	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double);
-	cudaError_t err = cudaFuncSetAttribute(simplsFitFast<AREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
-	if (err != cudaSuccess) return err;
 	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
 	if (grid <= 0) return cudaSuccess;
 	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-	simplsFitFast<AREG><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks);
+	cudaError_t err;
+	if (rs >= kMax) {
+		err = cudaFuncSetAttribute(simplsFitFast<AREG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+		if (err != cudaSuccess) return err;
+		simplsFitFast<AREG, false><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
+	} else {
+		if (prm.spill == nullptr) return cudaErrorInvalidValue;
+		err = cudaFuncSetAttribute(simplsFitFast<AREG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+		if (err != cudaSuccess) return err;
+		simplsFitFast<AREG, true><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, rs);
+	}
 	if (ctas) *ctas += grid;
 	return cudaGetLastError();
 }
@@ -995,12 +1118,21 @@ int fitKernelMaxK(int A, int smemLimit) {
 	return k;
 }
 
+// Doubles of global scratch one CTA of a bucket needs for the Gram rows that do not fit in shared memory (0: none).
+long long fitKernelSpillDoubles(int kMax, int A, int smemLimit, int maxTasks, int maxBlockLd) {
+	const int Ak = (A < kMax) ? A : kMax;
+	if (Ak > kFastComponents || kMax > kMaxWarps * 32) return 0;
+	const int rs = fastRowsInSmem(kMax, Ak, maxTasks, maxBlockLd, smemLimit);
+	if (rs <= 0 || rs >= kMax) return 0;
+	return static_cast<long long>(kMax - rs) * roundUp(kMax, 4);
+}
+
 // One launch for a bucket of chromosomes whose subset sizes are all <= kMax.
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
 	const int Ak = (A < kMax) ? A : kMax;
-	if (Ak <= kFastComponents && kMax <= kMaxWarps * 32 &&
-	    fastCarve(kMax, Ak, roundUp(kMax, 32) / 32, prm.maxTasks, prm.maxBlockLd, -1).total * 8 <= smemLimit) {
-		return launchFast<kFastComponents>(prm, kMax, Ak, stream, ctas); // per-row state in registers
+	if (Ak <= kFastComponents && kMax <= kMaxWarps * 32 && fastRowsInSmem(kMax, Ak, prm.maxTasks, prm.maxBlockLd, smemLimit) > 0 &&
+	    (prm.spill != nullptr || fastRowsInSmem(kMax, Ak, prm.maxTasks, prm.maxBlockLd, smemLimit) >= kMax)) {
+		return launchFast<kFastComponents>(prm, kMax, Ak, smemLimit, stream, ctas); // per-row state in registers
 	}
 	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true).total * 8 <= smemLimit) {
 		return launchOne<1, true>(prm, kMax, Ak, roundUp(kMax, 32), stream, ctas); // one thread per row

@@ -211,3 +211,20 @@ def test_cfg4_shape_properties(engine, oracle_lib):
     assert (sg == 0).all() and (fg2[::-1] == fg).all() and (fg < 0).all()
     fo, so = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets[:12], threads=8)
     assert rel_err(fg[:12], fo).max() <= REL_TOL
+
+
+def test_subsets_beyond_shared_memory_spill_to_l2(engine, oracle_lib):
+    """k > 212 (10 components): the last packed Gram rows live in a global scratch (K1 spill path);
+    k > 384 takes the generic path that reads the Gram in place."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(150, 1000, seed=777, noise=1e-2)
+    sv = oracle_lib.make_seedvec(123)
+    sizes = [213, 224, 225, 256, 257, 300, 352, 384, 400]
+    subsets = [synth.random_subsets(1000, 1, k, k, seed=k)[0] for k in sizes] + synth.random_subsets(1000, 6, 150, 330, seed=77)
+    kw = dict(numReplications=2, maxNComp=10, innerSegments=4, outerSegments=5)
+    fo, so = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=8)
+    with E.PLSEvaluator(X, y, sv, **kw) as ev:
+        fg, sg = ev.evaluate_population(subsets)
+        fg2, _ = ev.evaluate_population(subsets[::-1])
+    assert (sg == so).all() and (fg2[::-1] == fg).all()
+    assert rel_err(fg, fo).max() <= REL_TOL
