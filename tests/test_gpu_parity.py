@@ -228,3 +228,29 @@ def test_subsets_beyond_shared_memory_spill_to_l2(engine, oracle_lib):
         fg2, _ = ev.evaluate_population(subsets[::-1])
     assert (sg == so).all() and (fg2[::-1] == fg).all()
     assert rel_err(fg, fo).max() <= REL_TOL
+
+
+def test_underflow_is_reported_where_the_reference_throws(engine, oracle_lib):
+    """A constant response makes X'y vanish: PLSSimpls::fit throws std::underflow_error (||t|| < 1e-25,
+    src/PLSSimpls.cpp:141-143), the evaluators turn it into EvaluatorException (src/PLSEvaluator.cpp:337-340,
+    src/BICEvaluator.cpp:227-230).  The engine reports status 2 for exactly those chromosomes."""
+    from gaselect_b200 import evaluators as E
+    X, _ = synth.closed_form()
+    y = np.full(40, 3.25)
+    sv = oracle_lib.make_seedvec(5)
+    subsets = [[1, 2, 3], [5], [0, 7, 9, 11, 13], list(range(30))]
+    _, so = oracle_lib.pls_evaluator(X, y, sv, numReplications=2, innerSegments=3, maxNComp=4).evaluate(subsets)
+    with E.PLSEvaluator(X, y, sv, numReplications=2, innerSegments=3, maxNComp=4) as ev:
+        _, sg = ev.evaluate_population(subsets)
+        assert sg.tolist() == so.tolist() == [2, 2, 2, 2]
+        with pytest.raises(E.EvaluatorException):
+            ev.evaluate([1, 2, 3])
+    _, so = oracle_lib.fit_evaluator(X, y, sv, numSegments=5, maxNComp=3).evaluate(subsets)
+    with E.BICEvaluator(X, y, sv, numSegments=5, maxNComp=3) as ev:
+        _, sg = ev.evaluate_population(subsets)
+    assert sg.tolist() == so.tolist() == [2, 2, 2, 2]
+    # unconstrained component count (generic kernel path), mixed with healthy data in the same engine call
+    X2, y2 = synth.closed_form()
+    with E.PLSEvaluator(X2, y2, sv, numReplications=2, innerSegments=3) as ev:
+        f, s = ev.evaluate_population(subsets)
+        assert s.tolist() == [0, 0, 0, 0] and np.isfinite(f).all()
