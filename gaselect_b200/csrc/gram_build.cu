@@ -16,9 +16,11 @@ namespace gsb {
 namespace {
 
 constexpr int kTile = 64;   // output tile edge
-constexpr int kRows = 32;   // rows (samples) staged per step
+constexpr int kRows = 32;   // rows (samples) staged per pipeline stage
 constexpr int kLds = kRows + 4; // padded row stride: (4 * col) mod 16 distinct for 4 consecutive cols
+constexpr int kStages = 3;  // TMA pipeline depth
 constexpr int kSyrkThreads = 128;
+constexpr int kStageDoubles = 2 * kTile * kLds; // A panel + B panel
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -26,13 +28,43 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 	             : "d"(a), "d"(b));
 }
 
-// grid.x: lower-triangular tile pair (ti >= tj); grid.y: unit (full data or one block)
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbarInit(uint64_t* bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra WAIT_DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"WAIT_DONE:\n"
+		"}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared (SASS UBLKCP), completion signalled on the mbarrier
+__device__ __forceinline__ void tmaLoad1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smemAddr(dst)),
+	             "l"(src), "r"(bytes), "r"(smemAddr(bar))
+	             : "memory");
+}
+
+// grid.x: lower-triangular tile pair (ti >= tj); grid.y: unit (full data or one block).
+// Operand panels (32 rows x 64 columns of Z_u, column-major: one contiguous 256-byte run per column) are
+// staged by TMA bulk copies into a 3-stage shared-memory ring, each stage guarded by an mbarrier; the four
+// warps (2 x 2, 32 x 32 outputs each) issue FP64 tensor-core MMAs (DMMA.8x8x4) from the stage that has landed
+// while the next two stages are in flight.
 __global__ void __launch_bounds__(kSyrkThreads) gramSyrkKernel(const double* const* __restrict__ unitPtrs,
                                                                const int* __restrict__ unitLd,
                                                                const int* __restrict__ unitRows,
                                                                double* const* __restrict__ outPtrs, int P2, int ldm) {
-	__shared__ __align__(16) double As[kTile * kLds];
-	__shared__ __align__(16) double Bs[kTile * kLds];
+	extern __shared__ __align__(128) double ring[]; // kStages x [A panel | B panel]
+	__shared__ __align__(8) uint64_t full[kStages];
 
 	// decode blockIdx.x -> (ti, tj), tj <= ti
 	int ti = static_cast<int>((sqrtf(8.0f * static_cast<float>(blockIdx.x) + 1.0f) - 1.0f) * 0.5f);
@@ -51,28 +83,45 @@ __global__ void __launch_bounds__(kSyrkThreads) gramSyrkKernel(const double* con
 	const int wi = warp >> 1, wj = warp & 1; // 2 x 2 warps, 32 x 32 outputs each
 	const int group = lane >> 2, tig = lane & 3;
 
+	// thread t < 64 feeds column t of the A panel, thread t >= 64 column t - 64 of the B panel
+	const bool isA = tid < kTile;
+	const int myCol = isA ? i0 + tid : j0 + tid - kTile;
+	const bool myColValid = myCol < P2; // columns past the matrix are never stored: their stage rows may hold anything
+	const int colsA = min(kTile, P2 - i0), colsB = min(kTile, P2 - j0);
+	const double* __restrict__ mySrc = Zu + static_cast<size_t>(myColValid ? myCol : 0) * ld;
+	const int myDst = (isA ? tid : kTile + (tid - kTile)) * kLds;
+
+	if (tid == 0) {
+		for (int s = 0; s < kStages; ++s) mbarInit(&full[s], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+	}
+	__syncthreads();
+
+	const int steps = (nrows + kRows - 1) / kRows;
+	auto issue = [&](int step) {
+		const int stage = step % kStages;
+		const int r0 = step * kRows;
+		const int rowsThis = min(kRows, nrows - r0); // multiple of 4
+		if (tid == 0) mbarExpectTx(&full[stage], static_cast<uint32_t>((colsA + colsB) * rowsThis * sizeof(double)));
+		if (myColValid) tmaLoad1d(ring + stage * kStageDoubles + myDst, mySrc + r0, static_cast<uint32_t>(rowsThis * sizeof(double)), &full[stage]);
+	};
+	for (int s = 0; s < kStages - 1 && s < steps; ++s) issue(s);
+
 	double acc[4][4][2];
 #pragma unroll
 	for (int a = 0; a < 4; ++a)
 #pragma unroll
 		for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-	for (int r0 = 0; r0 < nrows; r0 += kRows) {
-		// stage kRows x 64 columns of both operand panels (coalesced along rows)
-		for (int e = tid; e < kTile * kRows; e += kSyrkThreads) {
-			const int col = e / kRows, r = e % kRows;
-			const int gr = r0 + r;
-			double va = 0.0, vb = 0.0;
-			if (gr < nrows) {
-				if (i0 + col < P2) va = __ldg(Zu + static_cast<size_t>(i0 + col) * ld + gr);
-				if (j0 + col < P2) vb = __ldg(Zu + static_cast<size_t>(j0 + col) * ld + gr);
-			}
-			As[col * kLds + r] = va;
-			Bs[col * kLds + r] = vb;
-		}
-		__syncthreads();
-#pragma unroll
-		for (int kk = 0; kk < kRows / 4; ++kk) {
+	for (int step = 0; step < steps; ++step) {
+		const int stage = step % kStages;
+		// the stage consumed at step - 1 is free (barrier at the end of that step): refill it two steps ahead
+		if (step + kStages - 1 < steps) issue(step + kStages - 1);
+		mbarWait(&full[stage], static_cast<uint32_t>((step / kStages) & 1));
+		const double* __restrict__ As = ring + stage * kStageDoubles;
+		const double* __restrict__ Bs = As + kTile * kLds;
+		const int ksteps = min(kRows, nrows - step * kRows) >> 2;
+		for (int kk = 0; kk < ksteps; ++kk) {
 			double a[4], b[4];
 #pragma unroll
 			for (int m = 0; m < 4; ++m) a[m] = As[(wi * 32 + m * 8 + group) * kLds + kk * 4 + tig];
@@ -83,7 +132,7 @@ __global__ void __launch_bounds__(kSyrkThreads) gramSyrkKernel(const double* con
 #pragma unroll
 				for (int n = 0; n < 4; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], b[n]);
 		}
-		__syncthreads();
+		__syncthreads(); // everyone is done with this stage
 	}
 
 	// C fragment: row = group, cols = 2*tig, 2*tig+1
@@ -163,7 +212,9 @@ void launchGramSyrk(const double* const* unitPtrs, const int* unitLd, const int*
 	if (units <= 0) return;
 	const int tiles = (P2 + kTile - 1) / kTile;
 	dim3 grid(static_cast<unsigned>(tiles * (tiles + 1) / 2), static_cast<unsigned>(units));
-	gramSyrkKernel<<<grid, kSyrkThreads, 0, stream>>>(unitPtrs, unitLd, unitRows, outPtrs, P2, ldm);
+	const int bytes = kStages * kStageDoubles * static_cast<int>(sizeof(double));
+	cudaFuncSetAttribute(gramSyrkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	gramSyrkKernel<<<grid, kSyrkThreads, bytes, stream>>>(unitPtrs, unitLd, unitRows, outPtrs, P2, ldm);
 }
 
 void launchGramCombine(const double* mFull, const double* const* mBlocks, const int* exclIndex, const int* exclCount,
