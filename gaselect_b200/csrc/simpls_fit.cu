@@ -11,6 +11,14 @@
 // src/PLSSimpls.cpp:152), so the outer refit with optNComp components (src/PLSEvaluator.cpp:316-317)
 // is column optNComp-1 of a fit with A components and every fit of a chromosome is independent.
 //
+// Two kernels, one launch per subset-size class of the population (engine.cpp, concurrent streams):
+//   simplsFitFast<10, SPILL>   A <= 10 components, k <= 384 -- everything at BASELINE configs 3-5.  One thread
+//       per Gram row; the per-row SIMPLS state (S, s0, x-bar, the stored loadings, the cumulative
+//       coefficients) lives in registers; shared memory holds the packed Gram, S and reduction scratch.
+//       SPILL: the packed rows that do not fit in shared memory (k > 212) live in an L2-resident scratch.
+//   simplsFitKernel<RPT, GSMEM> the generic path: any number of components (BASELINE config 1 runs up to 30
+//       per fit), loadings and coefficients in shared memory; GSMEM = false reads the Gram in place.
+//
 // Data movement
 //   * gather: the k(k+1)/2 selected entries of the training set's packed Gram go from HBM/L2
 //     straight into shared memory with 8-byte cp.async (LDGSTS): no register staging, every
@@ -19,13 +27,16 @@
 //     rows start at consecutive triangular numbers, distinct modulo 16); one thread per row,
 //     four independent accumulators, warp-uniform split into "left of the diagonal band" (own
 //     packed row), the 32-wide band, and "below the band" (column access, lane = row);
-//   * held-out rows: the selected column segments of the block copy are staged with 16-byte
-//     cp.async into the (by then dead) Gram area, then lanes = rows, warps split the columns.
+//   * held-out rows: after the last component the Gram area is dead; the selected column segments (+ y) of
+//     the fit's 1-2 held-out blocks are staged there with 16-byte cp.async, one or two blocks per pass
+//     (whatever costs no occupancy); work units (block x half of the component counts) run on separate
+//     warps with lanes = rows, so no partial sums cross warps.
 //
-// Reductions per component: ONE round for {S'w, s0'S, V_j'w (j < comp)} and ONE for {v'v, v'S}.
-// The projections on the stored (orthonormal) loadings are therefore taken from w before the
-// subtraction (all at once) rather than one after the other as src/PLSSimpls.cpp:57-63 does; the
-// two orders differ by the loss of orthogonality of V, i.e. at rounding level.
+// Reductions per component: ONE round for {S'w, s0'S, V_j'w (j < comp)} and ONE for {v'v, v'S}; a round over
+// 16 values costs 16 shuffle-adds (the lanes halve the value set at every butterfly step); 1/tn and 1/|v|
+// come from rsqrt.  The projections on the stored (orthonormal) loadings are therefore taken from w before
+// the subtraction (all at once) rather than one after the other as src/PLSSimpls.cpp:57-63 does; the two
+// orders differ by the loss of orthogonality of V, i.e. at rounding level.
 #include "kernels.cuh"
 
 namespace gsb {
