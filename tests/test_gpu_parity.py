@@ -254,3 +254,46 @@ def test_underflow_is_reported_where_the_reference_throws(engine, oracle_lib):
     with E.PLSEvaluator(X2, y2, sv, numReplications=2, innerSegments=3) as ev:
         f, s = ev.evaluate_population(subsets)
         assert s.tolist() == [0, 0, 0, 0] and np.isfinite(f).all()
+
+
+def test_resident_population_api_and_call_order(engine):
+    """upload / evaluate / download == evaluate_indices; state errors are reported, not crashed on."""
+    from gaselect_b200 import evaluators as E, _capi
+    X, y = synth.gaussian(80, 120, seed=2)
+    subsets = synth.random_subsets(120, 50, 1, 40, seed=3)
+    idx, off = _capi.to_csr(subsets)
+    with E.PLSEvaluator(X, y, 11, numReplications=3, innerSegments=4, maxNComp=5) as ev:
+        with pytest.raises(E.EngineError) as err:
+            ev.evaluate_resident()                       # nothing uploaded yet
+        assert err.value.code == _capi.GSB_ERR_STATE
+        f0, s0 = ev.evaluate_csr(idx, off)
+        ev.upload_population(idx, off)
+        with pytest.raises(E.EngineError):
+            ev.download_results(np.zeros(50), np.zeros(50, dtype=np.int32))  # not evaluated yet
+        ev.evaluate_resident()
+        ev.enqueue_resident()                            # asynchronous variant, same results
+        f1, s1 = np.zeros(50), np.zeros(50, dtype=np.int32)
+        ev.download_results(f1, s1)
+        assert (f1 == f0).all() and (s1 == s0).all()
+        fp, sp, n = ev.device_results()
+        assert fp and sp and n == 50
+        t = ev.timing()
+        assert t["fit_ctas"] == 50 * ev.info()["distinct_fits"] and t["fit_kernel_ms"] > 0
+
+
+def test_two_engines_and_a_caller_stream(engine):
+    """Engines are independent; gsb_set_stream moves an engine's work onto the caller's CUDA stream."""
+    import torch
+    from gaselect_b200 import evaluators as E
+    X, y = synth.gaussian(60, 90, seed=4)
+    subsets = synth.random_subsets(90, 30, 2, 30, seed=5)
+    with E.PLSEvaluator(X, y, 7, numReplications=2, innerSegments=3, maxNComp=4) as a, \
+            E.PLSEvaluator(X, y, 7, numReplications=2, innerSegments=3, maxNComp=4) as b, E.LMEvaluator(X, y, "AIC") as c:
+        fa, _ = a.evaluate_population(subsets)
+        stream = torch.cuda.Stream()
+        b.set_stream(stream.cuda_stream)
+        fb, _ = b.evaluate_population(subsets)
+        b.set_stream(None)
+        fb2, _ = b.evaluate_population(subsets)
+        fc, sc = c.evaluate_population(subsets)
+        assert (fa == fb).all() and (fa == fb2).all() and (sc == 0).all() and np.isfinite(fc).all()
