@@ -489,7 +489,7 @@ __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTask
 		// stage both blocks at once when that keeps the CTAs per SM, else one block per pass when the
 		// footprint grows by at most a third; large blocks (more than 32 rows) take the slab path
 		stagedTasks = 0;
-		if (maxTasks >= 1 && maxTasks <= 2 && maxBlockLd <= 32) {
+		if (maxTasks >= 1 && maxTasks <= 2 && maxBlockLd >= 1) {
 			const int fixed = roundUp(k, 2) + 2 * kMaxWarps * kRedMax + roundUp(k, 2) / 2 + 1;
 			const int perPlain = (plain + fixed) * 8 + 1024;
 			const int residentPlain = min(233472 / perPlain, 2048 / (nw * 32));
@@ -839,12 +839,13 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	const bool staged = cv.xt > 0;
 	const int tasksPerPass = cv.xtTasks;
 	double* __restrict__ XT = P + cv.xt; // [slot][column c <= k][32 rows]; column k is the block's y
-	auto stageBlocks = [&](int firstTask) {
+	// slot t - firstTask <- rows [32 * slab, 32 * slab + 32) of the selected columns (+ y) of held-out block t
+	auto stageBlocks = [&](int firstTask, int slab) {
 #pragma unroll
 		for (int t = 0; t < 2; ++t) {
-			if (t >= firstTask && t < firstTask + tasksPerPass && t < fd.taskCount) {
-				const double* __restrict__ zb = prm.zpool + bd[t].zOff;
-				const int pieces = bd[t].ld >> 1; // 16-byte pieces per column
+			if (t >= firstTask && t < firstTask + tasksPerPass && t < fd.taskCount && slab * 32 < bd[t].ld) {
+				const double* __restrict__ zb = prm.zpool + bd[t].zOff + slab * 32;
+				const int pieces = min(32, bd[t].ld - slab * 32) >> 1; // 16-byte pieces per column
 				double* __restrict__ dst = XT + (t - firstTask) * (k + 1) * 32;
 				for (int e = tid; e < (k + 1) * 16; e += NT) {
 					const int c = e >> 4, piece = e & 15;
@@ -857,7 +858,7 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 		}
 		asm volatile("cp.async.commit_group;\n" ::: "memory");
 	};
-	if (staged) stageBlocks(0);
+	if (staged) stageBlocks(0, 0);
 	if (valid) {
 #pragma unroll
 		for (int j = 0; j < AREG; ++j) if (j < Apad) coef[r * Apad + j] = (j < A) ? cOwn[j] : 0.0;
@@ -882,93 +883,120 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 
 	// ---- held-out prediction and statistics -------------------------------------------------
 	if (staged) {
-		// work unit = (task, half of the component counts): no partial sums cross warps
+		// work unit = (task, half of the component counts): no partial sums cross warps.  Blocks of more than 32
+		// rows go through the staging tiles slab by slab; a unit's sums over the slabs stay in its warp's registers.
 		constexpr int H = (AREG / 2 + 1) & ~1; // components of the first half, even (6 of 10); second half AREG - H
 		for (int firstTask = 0; firstTask < fd.taskCount; firstTask += tasksPerPass) {
-		if (firstTask > 0) {
-			__syncthreads(); // previous pass consumed
-			stageBlocks(firstTask);
-		}
-		cpAsyncWaitAll();
-		__syncthreads();
-		const int units = min(tasksPerPass, fd.taskCount - firstTask) * 2;
-		for (int u = warp; u < units; u += NW) {
-			const int t = firstTask + (u >> 1);
-			const bool second = (u & 1) != 0;
-			const int base = second ? H : 0;
-			if (base >= A) continue;
-			const double* __restrict__ xt = XT + (u >> 1) * (k + 1) * 32 + lane;
-			const double* __restrict__ cr = coef + base;
-			double acc[H];
+			const int tasksHere = min(tasksPerPass, fd.taskCount - firstTask);
+			const int units = tasksHere * 2;
+			int maxLd = 0;
 #pragma unroll
-			for (int i = 0; i < H; ++i) acc[i] = 0.0;
-			// Apad is even and >= A; the pairs of this half that lie inside Apad (warp-uniform count)
-			const int pairs = min((second ? AREG - H : H), Apad - base) >> 1;
-			if (pairs == H / 2) {
-#pragma unroll 4
-				for (int c = 0; c < k; ++c) {
-					const double x = xt[c * 32];
-#pragma unroll
-					for (int i = 0; i < H; i += 2) {
-						const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
-						acc[i] = fma(x, cc.x, acc[i]);
-						acc[i + 1] = fma(x, cc.y, acc[i + 1]);
-					}
+			for (int t = 0; t < 2; ++t) if (t >= firstTask && t < firstTask + tasksHere) maxLd = max(maxLd, bd[t].ld);
+			const int slabs = (maxLd + 31) >> 5;
+			double tot[4] = {0.0, 0.0, 0.0, 0.0}; // this lane's value (lane >> 1) of up to 4 units handled by this warp
+			for (int slab = 0; slab < slabs; ++slab) {
+				if (firstTask > 0 || slab > 0) {
+					__syncthreads(); // previous tiles consumed
+					stageBlocks(firstTask, slab);
 				}
-			} else if (pairs == (AREG - H) / 2) {
+				cpAsyncWaitAll();
+				__syncthreads();
+#pragma unroll
+				for (int ui = 0; ui < 4; ++ui) {
+					const int u = warp + ui * NW;
+					if (u >= units) break;
+					const int t = firstTask + (u >> 1);
+					const bool second = (u & 1) != 0;
+					const int base = second ? H : 0;
+					const int nrows = (t == 0) ? bd[0].nrows : bd[1].nrows;
+					const int rowsHere = nrows - slab * 32; // rows of this block in this slab (may be <= 0)
+					if (base >= A || rowsHere <= 0) continue;
+					const double* __restrict__ xt = XT + (u >> 1) * (k + 1) * 32 + lane;
+					const double* __restrict__ cr = coef + base;
+					double acc[H];
+#pragma unroll
+					for (int i = 0; i < H; ++i) acc[i] = 0.0;
+					// Apad is even and >= A; the pairs of this half that lie inside Apad (warp-uniform count)
+					const int pairs = min((second ? AREG - H : H), Apad - base) >> 1;
+					if (pairs == H / 2) {
 #pragma unroll 4
-				for (int c = 0; c < k; ++c) {
-					const double x = xt[c * 32];
+						for (int c = 0; c < k; ++c) {
+							const double x = xt[c * 32];
 #pragma unroll
-					for (int i = 0; i < AREG - H; i += 2) {
-						const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
-						acc[i] = fma(x, cc.x, acc[i]);
-						acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+							for (int i = 0; i < H; i += 2) {
+								const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
+								acc[i] = fma(x, cc.x, acc[i]);
+								acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+							}
+						}
+					} else if (pairs == (AREG - H) / 2) {
+#pragma unroll 4
+						for (int c = 0; c < k; ++c) {
+							const double x = xt[c * 32];
+#pragma unroll
+							for (int i = 0; i < AREG - H; i += 2) {
+								const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
+								acc[i] = fma(x, cc.x, acc[i]);
+								acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+							}
+						}
+					} else {
+						for (int c = 0; c < k; ++c) {
+							const double x = xt[c * 32];
+#pragma unroll
+							for (int i = 0; i < H; i += 2) {
+								if ((i >> 1) < pairs) {
+									const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
+									acc[i] = fma(x, cc.x, acc[i]);
+									acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+								}
+							}
+						}
 					}
-				}
-			} else {
-				for (int c = 0; c < k; ++c) {
-					const double x = xt[c * 32];
+					const double y = xt[k * 32];
+					double st[16];
 #pragma unroll
-					for (int i = 0; i < H; i += 2) {
-						if ((i >> 1) < pairs) {
-							const double2 cc = *reinterpret_cast<const double2*>(cr + c * Apad + i);
-							acc[i] = fma(x, cc.x, acc[i]);
-							acc[i + 1] = fma(x, cc.y, acc[i + 1]);
+					for (int i = 0; i < 16; ++i) st[i] = 0.0;
+#pragma unroll
+					for (int i = 0; i < H; ++i) {
+						double b0i = 0.0;
+#pragma unroll
+						for (int j = 0; j < AREG; ++j) if (j == (second ? H : 0) + i) b0i = b0v[j];
+						const double e = (lane < rowsHere) ? y - (acc[i] + b0i) : 0.0;
+						st[i] = e;
+						st[H + i] = e * e;
+					}
+					// lane L: value (L >> 1): sum e (< H), sum e^2 (H ..); accumulated over the slabs
+					const double slabTot = warpSum16(st, lane);
+#pragma unroll
+					for (int q = 0; q < 4; ++q) if (q == ui) tot[q] += slabTot;
+				}
+			}
+#pragma unroll
+			for (int ui = 0; ui < 4; ++ui) {
+				const int u = warp + ui * NW;
+				if (u >= units) break;
+				const int t = firstTask + (u >> 1);
+				const int base = (u & 1) ? H : 0;
+				const int nrows = (t == 0) ? bd[0].nrows : bd[1].nrows;
+				const int kind = (t == 0) ? td[0].kind : td[1].kind;
+				const int dest = (t == 0) ? td[0].dest : td[1].dest;
+				const int j = lane >> 1;
+				double mine = 0.0;
+#pragma unroll
+				for (int q = 0; q < 4; ++q) if (q == ui) mine = tot[q];
+				if ((lane & 1) == 0 && j < 2 * H) {
+					const int a = base + (j < H ? j : j - H);
+					if (a < A) {
+						if (kind == 0) {
+							// mean squared error of prediction for this fold (src/PLSEvaluator.cpp:266-268)
+							if (j >= H) prm.mse[(static_cast<size_t>(chrom) * prm.innerDests + dest) * prm.maxNComp + a] = mine / static_cast<double>(nrows);
+						} else {
+							prm.ostat[((static_cast<size_t>(chrom) * prm.outerDests + dest) * prm.maxNComp + a) * 2 + (j >= H ? 1 : 0)] = mine;
 						}
 					}
 				}
 			}
-			const int nrows = (t == 0) ? bd[0].nrows : bd[1].nrows;
-			const int kind = (t == 0) ? td[0].kind : td[1].kind;
-			const int dest = (t == 0) ? td[0].dest : td[1].dest;
-			const double y = xt[k * 32];
-			double st[16];
-#pragma unroll
-			for (int i = 0; i < 16; ++i) st[i] = 0.0;
-#pragma unroll
-			for (int i = 0; i < H; ++i) {
-				double b0i = 0.0;
-#pragma unroll
-				for (int j = 0; j < AREG; ++j) if (j == (second ? H : 0) + i) b0i = b0v[j];
-				const double e = (lane < nrows) ? y - (acc[i] + b0i) : 0.0;
-				st[i] = e;
-				st[H + i] = e * e;
-			}
-			const double tot = warpSum16(st, lane); // lane L: value (L >> 1): sum e (< H), sum e^2 (H ..)
-			const int j = lane >> 1;
-			if ((lane & 1) == 0 && j < 2 * H) {
-				const int a = base + (j < H ? j : j - H);
-				if (a < A) {
-					if (kind == 0) {
-						// mean squared error of prediction for this fold (src/PLSEvaluator.cpp:266-268)
-						if (j >= H) prm.mse[(static_cast<size_t>(chrom) * prm.innerDests + dest) * prm.maxNComp + a] = tot / static_cast<double>(nrows);
-					} else {
-						prm.ostat[((static_cast<size_t>(chrom) * prm.outerDests + dest) * prm.maxNComp + a) * 2 + (j >= H ? 1 : 0)] = tot;
-					}
-				}
-			}
-		}
 		}
 		GSB_STAMP();
 	} else {

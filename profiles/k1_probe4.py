@@ -1,0 +1,18 @@
+"""K1 phase clocks at config-4 shape (n=500, p=5000, 100-row held-out blocks).  usage: python profiles/k1_probe4.py K [POP]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from gaselect_b200 import synth, evaluators as E, _capi
+k = int(sys.argv[1]); pop = int(sys.argv[2]) if len(sys.argv) > 2 else 148
+X, y = synth.nir_spectra(500, 5000, seed=778)
+subsets = synth.random_subsets(5000, pop, k, k, seed=1)
+idx, off = _capi.to_csr(subsets)
+ev = E.PLSEvaluator(X, y, 123, numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)
+ev.upload_population(idx, off)
+ts = []
+for _ in range(3):
+    ev.evaluate_resident(); ts.append(ev.timing()["fit_kernel_ms"])
+print("cfg4 k=%d pop=%d K1 ms=%s  us/fit-slot(148 SMs)=%.2f" % (k, pop, ["%.3f" % t for t in ts], min(ts) * 1e3 * 148 / (pop * 150)))
+tr = ev.debug_trace(40)
+if tr.any():
+    d = np.diff(tr[tr > 0]); print("phase clocks:", d.tolist(), "total", int(tr[tr > 0][-1] - tr[0]))
