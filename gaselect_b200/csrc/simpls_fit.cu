@@ -69,7 +69,7 @@ __device__ __forceinline__ void blockSum(double (&v)[NV], double* red, int& phas
 		for (int i = 0; i < NV; ++i) v[i] += shflXor(v[i], m);
 	}
 	if (nw > 1) {
-		double* buf = red + phase * (kMaxWarps * kRedMax);
+		double* buf = red + phase * (nw * kRedMax);
 		const int warp = threadIdx.x >> 5;
 		if ((threadIdx.x & 31) == 0) {
 #pragma unroll
@@ -94,19 +94,22 @@ struct Carve {
 	int P, S, s0, xm, V, coef, b0, red, sel, total;
 };
 
-__host__ __device__ inline Carve carve(int k, int A, bool gramInSmem) {
+// staging area of the generic path after the fit: the warps' partial sums + at least min(k, 32) column tiles
+__host__ __device__ inline int stageMin(int k, int nw) { return nw * 32 * kChunk + 32 * min(k, 32); }
+
+__host__ __device__ inline Carve carve(int k, int A, bool gramInSmem, int nw) {
 	Carve c;
 	const int Apad = roundUp(A, kChunk);
 	int o = 0;
 	// packed Gram; afterwards the staging area of the held-out rows (>= one 32-row column per warp)
-	c.P = o; o += gramInSmem ? roundUp(max(k * (k + 1) / 2, kMaxWarps * 32 * (kChunk + 1)), 2) : kMaxWarps * 32 * (kChunk + 1);
+	c.P = o; o += gramInSmem ? roundUp(max(k * (k + 1) / 2, stageMin(k, nw)), 2) : stageMin(k, nw);
 	c.S = o; o += roundUp(k, 2);
 	c.s0 = o; o += roundUp(k, 2);
 	c.xm = o; o += roundUp(k, 2);
 	c.V = o; o += roundUp(A * k, 2);
 	c.coef = o; o += k * Apad;
 	c.b0 = o; o += Apad;
-	c.red = o; o += 2 * kMaxWarps * kRedMax;  // double-buffered
+	c.red = o; o += 2 * nw * kRedMax;  // double-buffered
 	c.sel = o; o += roundUp(k, 2) / 2 + 1;    // uint32 column ids
 	c.total = o;
 	return c;
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 	const FitDesc fd = prm.fits[fi];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-	const Carve cv = carve(k, A, GSMEM);
+	const Carve cv = carve(k, A, GSMEM, NW);
 	double* __restrict__ P = smem + cv.P;
 	double* __restrict__ S = smem + cv.S;
 	double* __restrict__ s0s = smem + cv.s0;
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 	// ---- held-out prediction and statistics -------------------------------------------------
 	// The Gram area is dead now: it stages [column pass][32-row slab] tiles of the held-out block
 	// (16-byte cp.async, everything in flight at once) and, at its end, the warps' partial sums.
-	const int stageCap = GSMEM ? max(k * (k + 1) / 2, kMaxWarps * 32 * (kChunk + 1)) : kMaxWarps * 32 * (kChunk + 1);
+	const int stageCap = GSMEM ? max(k * (k + 1) / 2, stageMin(k, NW)) : stageMin(k, NW);
 	double* __restrict__ part = P + stageCap - NW * 32 * kChunk; // [warp][u][lane]
 	const int colsPerPass = max(1, min(k, (stageCap - NW * 32 * kChunk) / 32));
 	for (int t = 0; t < fd.taskCount; ++t) {
@@ -490,7 +493,7 @@ __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTask
 		// footprint grows by at most a third; large blocks (more than 32 rows) take the slab path
 		stagedTasks = 0;
 		if (maxTasks >= 1 && maxTasks <= 2 && maxBlockLd >= 1) {
-			const int fixed = roundUp(k, 2) + 2 * kMaxWarps * kRedMax + roundUp(k, 2) / 2 + 1;
+			const int fixed = roundUp(k, 2) + 2 * nw * 16 + roundUp(k, 2) / 2 + 1;
 			const int perPlain = (plain + fixed) * 8 + 1024;
 			const int residentPlain = min(233472 / perPlain, 2048 / (nw * 32));
 			for (int tasks = maxTasks; tasks >= 1 && stagedTasks == 0; --tasks) {
@@ -505,7 +508,7 @@ __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTask
 	int o = 0;
 	c.P = o; o += area;
 	c.S = o; o += roundUp(k, 2);
-	c.red = o; o += 2 * kMaxWarps * kRedMax;
+	c.red = o; o += 2 * nw * 16; // double-buffered partial sums, 16 values per warp
 	c.sel = o; o += roundUp(k, 2) / 2 + 1;
 	c.total = o;
 	c.coef = 0;
@@ -540,7 +543,7 @@ __device__ __forceinline__ void blockSum16(double (&x)[NV], double* red, int& ph
 	for (int i = 0; i < 16; ++i) v[i] = (i < NV) ? x[i] : 0.0;
 	double tot = warpSum16(v, lane);
 	if (nw > 1) {
-		double* buf = red + phase * (kMaxWarps * kRedMax);
+		double* buf = red + phase * (nw * 16);
 		if ((lane & 1) == 0) buf[warp * 16 + (lane >> 1)] = tot;
 		__syncthreads();
 		tot = buf[lane & 15];
@@ -700,6 +703,7 @@ template <int AREG, bool SPILL>
 __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) simplsFitFast(const FitParams prm, const int stageAll, const int rSplit) {
 	extern __shared__ __align__(16) double smem[];
 	static_assert(AREG % 2 == 0 && AREG + 2 <= 16, "one reduction round holds tn^2, q*tn and every projection");
+	constexpr int MAXW = SPILL ? kMaxWarps : 8; // warps a CTA of this instantiation can have (bounds the unrolled gather)
 	const int NT = blockDim.x, NW = NT >> 5;
 
 	const int ci = blockIdx.x % prm.bucketCount;
@@ -732,14 +736,14 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	__syncthreads();
 	const double* __restrict__ gsrc = prm.gram + fd.gramOff;
 	{
-		uint32_t selB[kMaxWarps];
+		uint32_t selB[MAXW];
 #pragma unroll
-		for (int j = 0; j < kMaxWarps; ++j) selB[j] = (lane + 32 * j < k) ? sel[lane + 32 * j] : 0u;
+		for (int j = 0; j < MAXW; ++j) selB[j] = (lane + 32 * j < k) ? sel[lane + 32 * j] : 0u;
 		for (int a = warp; a < rs; a += NW) {
 			const double* __restrict__ grow = gsrc + tri(sel[a]);
 			double* __restrict__ prow = P + a * (a + 1) / 2;
 #pragma unroll
-			for (int j = 0; j < kMaxWarps; ++j) {
+			for (int j = 0; j < MAXW; ++j) {
 				if (32 * j <= a) {
 					const int b = lane + 32 * j;
 					if (b <= a) cpAsync8(prow + b, grow + selB[j]);
@@ -751,7 +755,7 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 				const double* __restrict__ grow = gsrc + tri(sel[a]);
 				double* srow = spill + static_cast<size_t>(a - rs) * ldS;
 #pragma unroll
-				for (int j = 0; j < kMaxWarps; ++j) {
+				for (int j = 0; j < MAXW; ++j) {
 					if (32 * j <= a) {
 						const int b = lane + 32 * j;
 						if (b <= a) srow[b] = __ldg(grow + selB[j]);
@@ -1133,7 +1137,7 @@ constexpr int kFastComponents = 10;
 
 template <int RPT, bool GSMEM>
 cudaError_t launchOne(const FitParams& prm, int kMax, int A, int threads, cudaStream_t stream, long long* ctas) {
-	const Carve cv = carve(kMax, A, GSMEM);
+	const Carve cv = carve(kMax, A, GSMEM, threads / 32);
 	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double);
 	cudaError_t err = cudaFuncSetAttribute(simplsFitKernel<RPT, GSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                       static_cast<int>(bytes));
@@ -1148,12 +1152,12 @@ cudaError_t launchOne(const FitParams& prm, int kMax, int A, int threads, cudaSt
 
 } // namespace
 
-int fitKernelSharedBytes(int k, int A) { return carve(k, A, true).total * static_cast<int>(sizeof(double)); }
+int fitKernelSharedBytes(int k, int A) { return carve(k, A, true, roundUp(k, 32) / 32).total * static_cast<int>(sizeof(double)); }
 
 // largest k whose packed Gram still fits in shared memory next to the loadings
 int fitKernelMaxK(int A, int smemLimit) {
 	int k = 1;
-	while (k < kMaxWarps * 32 && carve(k + 1, (A < k + 1) ? A : k + 1, true).total * 8 <= smemLimit) ++k;
+	while (k < kMaxWarps * 32 && carve(k + 1, (A < k + 1) ? A : k + 1, true, roundUp(k + 1, 32) / 32).total * 8 <= smemLimit) ++k;
 	return k;
 }
 
@@ -1173,10 +1177,10 @@ cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit
 	    (prm.spill != nullptr || fastRowsInSmem(kMax, Ak, prm.maxTasks, prm.maxBlockLd, smemLimit) >= kMax)) {
 		return launchFast<kFastComponents>(prm, kMax, Ak, smemLimit, stream, ctas); // per-row state in registers
 	}
-	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true).total * 8 <= smemLimit) {
+	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true, roundUp(kMax, 32) / 32).total * 8 <= smemLimit) {
 		return launchOne<1, true>(prm, kMax, Ak, roundUp(kMax, 32), stream, ctas); // one thread per row
 	}
-	if (kMax > 4 * kMaxWarps * 32 || carve(kMax, Ak, false).total * 8 > smemLimit) return cudaErrorInvalidValue;
+	if (kMax > 4 * kMaxWarps * 32 || carve(kMax, Ak, false, kMaxWarps).total * 8 > smemLimit) return cudaErrorInvalidValue;
 	return launchOne<4, false>(prm, kMax, Ak, kMaxWarps * 32, stream, ctas);         // Gram read in place (L2)
 }
 
