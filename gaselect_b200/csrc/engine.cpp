@@ -152,6 +152,22 @@ struct gsb_engine {
 	PinnedArray<int> hBucket, hStatus;
 	PinnedArray<double> hFitness;
 	DeviceArray<double> spill;       // Gram rows of very large subsets (K1 spill path), one region per size class
+	// K1b (replication-batched kernel): the packed full-data Gram and the group / pair tables
+	DeviceArray<double> gfull, batchScratch;
+	DeviceArray<int> bGroupFits;
+	DeviceArray<gsb::BatchGroup> bGroups;
+	DeviceArray<gsb::BatchPairGroup> bPgs;
+	DeviceArray<gsb::BatchPair> bPairs;
+	DeviceArray<int2> bUnits;
+	int batchGroups = 0, batchNfMax = 0, batchUDoubles = 0, batchPgp = 2, batchMaxK = 0;
+	// K1x (score-space tensor-core kernel): row-permuted copies of Z per replication and the atom tables
+	DeviceArray<double> xz;
+	DeviceArray<gsb::XRepDesc> xReps;
+	DeviceArray<int> xAtomRows;
+	DeviceArray<gsb::XGroupDesc> xGroups;
+	DeviceArray<gsb::XFitDesc> xFits;
+	DeviceArray<gsb::XTaskDesc> xTasks;
+	int scoreGroups = 0, scoreNr = 0, scoreMaxK = 0;
 	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
 
@@ -185,6 +201,9 @@ void releaseDevice(gsb_engine* e) {
 	e->fits.release(); e->tasks.release(); e->blocks.release(); e->outerRows.release();
 	e->traceBuf.release();
 	e->spill.release();
+	e->gfull.release(); e->batchScratch.release(); e->bGroupFits.release(); e->bGroups.release(); e->bPgs.release();
+	e->bPairs.release(); e->bUnits.release();
+	e->xz.release(); e->xReps.release(); e->xAtomRows.release(); e->xGroups.release(); e->xFits.release(); e->xTasks.release();
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
@@ -447,6 +466,245 @@ void prepareDevice(gsb_engine* e) {
 	e->outerRows.upload(plan.outerRows, e->stream);
 	e->ymAllRows = nfits > 0 ? ym[0] : 0.0;
 	GSB_CUDA(cudaStreamSynchronize(e->stream));
+
+	// ---- K1b: fits grouped per replication, (block, fit) pairs, and the packed full-data Gram
+	e->batchGroups = 0;
+	e->batchMaxK = 0;
+	if (e->cfg.evaluator != GSB_EVAL_LM && nfits > 0) {
+		const int I = std::max(1, plan.innerPerGroup), O = std::max(1, plan.groupsPerReplication);
+		std::vector<int> fitRep(static_cast<size_t>(nfits), 1 << 30);
+		for (size_t t = 0; t < plan.tasks.size(); ++t) {
+			const gsb::PlanTask& pt = plan.tasks[t];
+			const int g = pt.kind == gsb::TASK_OUTER ? pt.dest : pt.dest / I;
+			fitRep[static_cast<size_t>(pt.fit)] = std::min(fitRep[static_cast<size_t>(pt.fit)], g / O);
+		}
+		std::vector<int> order(static_cast<size_t>(nfits));
+		for (int f = 0; f < nfits; ++f) order[static_cast<size_t>(f)] = f;
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fitRep[static_cast<size_t>(a)] < fitRep[static_cast<size_t>(b)]; });
+		std::vector<int> groupFits;
+		std::vector<gsb::BatchGroup> groups;
+		std::vector<gsb::BatchPairGroup> pgs;
+		std::vector<gsb::BatchPair> pairs;
+		std::vector<int2> units;
+		int nfMax = 0, maxPairs = 1, maxSlabs = 0;
+		struct Entry { int block, fitLocal, corr, kind, dest; };
+		for (size_t b0 = 0; b0 < order.size();) {
+			size_t b1 = b0;
+			while (b1 < order.size() && fitRep[static_cast<size_t>(order[b1])] == fitRep[static_cast<size_t>(order[b0])]) ++b1;
+			const size_t count = b1 - b0, chunks = (count + 15) / 16, per = (count + chunks - 1) / chunks;
+			for (size_t c0 = b0; c0 < b1; c0 += per) {
+				const size_t c1 = std::min(b1, c0 + per);
+				gsb::BatchGroup g;
+				g.fitBegin = static_cast<int>(groupFits.size());
+				g.nfits = static_cast<int>(c1 - c0);
+				g.pgBegin = static_cast<int>(pgs.size());
+				g.unitBegin = static_cast<int>(units.size());
+				g.pad0 = g.pad1 = 0;
+				std::vector<Entry> entries;
+				for (size_t x = c0; x < c1; ++x) {
+					const int fit = order[x], fl = static_cast<int>(x - c0);
+					groupFits.push_back(fit);
+					const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(fit)];
+					const size_t first = entries.size();
+					for (size_t q = 0; q < pf.exclBlocks.size(); ++q) {
+						Entry en = {pf.exclBlocks[q], fl, 1, -1, 0};
+						entries.push_back(en);
+					}
+					for (int t = pf.taskBegin; t < pf.taskBegin + pf.taskCount; ++t) {
+						const gsb::PlanTask& pt = plan.tasks[static_cast<size_t>(t)];
+						bool attached = false;
+						for (size_t q = first; q < entries.size() && !attached; ++q) {
+							if (entries[q].block == pt.block && entries[q].kind < 0) {
+								entries[q].kind = pt.kind;
+								entries[q].dest = pt.dest;
+								attached = true;
+							}
+						}
+						if (!attached) {
+							Entry en = {pt.block, fl, 0, pt.kind, pt.dest};
+							entries.push_back(en);
+						}
+					}
+				}
+				std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.block < b.block; });
+				int slabs = 0;
+				for (size_t q0 = 0; q0 < entries.size();) {
+					size_t q1 = q0;
+					while (q1 < entries.size() && q1 - q0 < 8 && entries[q1].block == entries[q0].block) ++q1;
+					gsb::BatchPairGroup pg;
+					pg.block = entries[q0].block;
+					pg.npairs = static_cast<int>(q1 - q0);
+					pg.pairBegin = static_cast<int>(pairs.size());
+					pg.slabBegin = slabs;
+					pg.nslabs = (bdesc[static_cast<size_t>(pg.block)].ld + 31) / 32;
+					pg.ncorr = 0;
+					pg.pad0 = pg.pad1 = 0;
+					for (size_t q = q0; q < q1; ++q) {
+						gsb::BatchPair bp = {entries[q].fitLocal, entries[q].corr, entries[q].kind, entries[q].dest};
+						pairs.push_back(bp);
+						pg.ncorr += entries[q].corr ? 1 : 0;
+					}
+					for (int sl = 0; sl < pg.nslabs; ++sl) units.push_back(make_int2(static_cast<int>(pgs.size()), sl));
+					slabs += pg.nslabs;
+					maxPairs = std::max(maxPairs, pg.npairs);
+					pgs.push_back(pg);
+					q0 = q1;
+				}
+				g.npg = static_cast<int>(pgs.size()) - g.pgBegin;
+				g.nunits = static_cast<int>(units.size()) - g.unitBegin;
+				maxSlabs = std::max(maxSlabs, slabs);
+				nfMax = std::max(nfMax, g.nfits);
+				groups.push_back(g);
+			}
+			b0 = b1;
+		}
+		e->batchPgp = roundUp(maxPairs, 2);
+		e->batchUDoubles = maxSlabs * 32 * e->batchPgp;
+		e->batchNfMax = nfMax;
+		e->batchGroups = static_cast<int>(groups.size());
+		e->batchMaxK = gsb::batchKernelMaxK(nfMax, e->batchUDoubles, e->smemLimit);
+		e->bGroupFits.upload(groupFits, e->stream);
+		e->bGroups.upload(groups, e->stream);
+		e->bPgs.upload(pgs, e->stream);
+		e->bPairs.upload(pairs, e->stream);
+		e->bUnits.upload(units, e->stream);
+
+		// packed Z'Z over all rows: the combination kernel with no excluded block
+		DeviceArray<int> dZero2, dZero1, dN1;
+		DeviceArray<unsigned long long> dOff0;
+		DeviceArray<double> dS0x, dXmx, dYmx;
+		const int zeros2[2] = {0, 0};
+		const int zero1 = 0;
+		const unsigned long long off0 = 0;
+		dZero2.upload(zeros2, 2, e->stream);
+		dZero1.upload(&zero1, 1, e->stream);
+		dN1.upload(&n, 1, e->stream);
+		dOff0.upload(&off0, 1, e->stream);
+		dS0x.reserve(static_cast<size_t>(p));
+		dXmx.reserve(static_cast<size_t>(p));
+		dYmx.reserve(1);
+		e->gfull.reserve(triP);
+		gsb::launchGramCombine(mPool.ptr, dMOfBlock.ptr, dZero2.ptr, dZero1.ptr, dZero1.ptr, dN1.ptr, 1, p, ldm, e->gfull.ptr, dOff0.ptr,
+		                       dS0x.ptr, dXmx.ptr, dYmx.ptr, e->stream);
+		GSB_CUDA(cudaGetLastError());
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+	}
+
+	// ---- K1x: atoms (disjoint row blocks) per replication, fits as masks of excluded atoms
+	e->scoreGroups = 0;
+	e->scoreMaxK = 0;
+	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && n <= gsb::kScoreMaxRows && !std::getenv("GSB_NO_SCORES")) {
+		const int I = std::max(1, plan.innerPerGroup), O = std::max(1, plan.groupsPerReplication);
+		const int R = std::max(1, plan.groups / O);
+		std::vector<int> fitRep(static_cast<size_t>(nfits), 1 << 30);
+		for (size_t t = 0; t < plan.tasks.size(); ++t) {
+			const gsb::PlanTask& pt = plan.tasks[t];
+			const int g = pt.kind == gsb::TASK_OUTER ? pt.dest : pt.dest / I;
+			fitRep[static_cast<size_t>(pt.fit)] = std::min(fitRep[static_cast<size_t>(pt.fit)], g / O);
+		}
+		const int nr = roundUp(n, 8);
+		std::vector<gsb::XRepDesc> reps(static_cast<size_t>(R));
+		std::vector<int> atomRows;
+		std::vector<gsb::XGroupDesc> groups;
+		std::vector<gsb::XFitDesc> xfits;
+		std::vector<gsb::XTaskDesc> xtasks;
+		std::vector<uint32_t> permRows; // R x n
+		bool ok = true;
+		for (int r = 0; r < R && ok; ++r) {
+			std::vector<int> fitsHere;
+			for (int f = 0; f < nfits; ++f) if (fitRep[static_cast<size_t>(f)] == r) fitsHere.push_back(f);
+			if (fitsHere.empty()) { ok = false; break; }
+			// atoms: every block some fit of the replication excludes or predicts; they must be pairwise disjoint
+			std::vector<int> atomBlocks;
+			for (size_t x = 0; x < fitsHere.size(); ++x) {
+				const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(fitsHere[x])];
+				for (size_t q = 0; q < pf.exclBlocks.size(); ++q) atomBlocks.push_back(pf.exclBlocks[q]);
+				for (int t = pf.taskBegin; t < pf.taskBegin + pf.taskCount; ++t) atomBlocks.push_back(plan.tasks[static_cast<size_t>(t)].block);
+			}
+			std::sort(atomBlocks.begin(), atomBlocks.end());
+			atomBlocks.erase(std::unique(atomBlocks.begin(), atomBlocks.end()), atomBlocks.end());
+			std::vector<int> owner(static_cast<size_t>(n), -1);
+			for (size_t a = 0; a < atomBlocks.size() && ok; ++a) {
+				const gsb::PlanBlock& pb = plan.blocks[static_cast<size_t>(atomBlocks[a])];
+				for (size_t i = 0; i < pb.rows.size(); ++i) {
+					if (owner[pb.rows[i]] >= 0) { ok = false; break; }
+					owner[pb.rows[i]] = static_cast<int>(a);
+				}
+			}
+			if (!ok) break;
+			int natoms = static_cast<int>(atomBlocks.size());
+			bool rest = false;
+			for (int i = 0; i < n; ++i) if (owner[static_cast<size_t>(i)] < 0) { owner[static_cast<size_t>(i)] = natoms; rest = true; }
+			if (rest) ++natoms;
+			if (natoms > gsb::kScoreMaxAtoms) { ok = false; break; }
+			gsb::XRepDesc& rd = reps[static_cast<size_t>(r)];
+			rd.zOff = static_cast<unsigned long long>(r) * nr * P2;
+			rd.atomBegin = static_cast<int>(atomRows.size());
+			rd.natoms = natoms;
+			int at = 0;
+			for (int a = 0; a < natoms; ++a) {
+				atomRows.push_back(at);
+				for (int i = 0; i < n; ++i) if (owner[static_cast<size_t>(i)] == a) { permRows.push_back(static_cast<uint32_t>(i)); ++at; }
+			}
+			atomRows.push_back(at);
+			// fits in chunks of at most 8, balanced
+			const size_t count = fitsHere.size(), chunks = (count + 7) / 8, per = (count + chunks - 1) / chunks;
+			for (size_t c0 = 0; c0 < count && ok; c0 += per) {
+				const size_t c1 = std::min(count, c0 + per);
+				gsb::XGroupDesc g;
+				g.rep = r;
+				g.nfits = static_cast<int>(c1 - c0);
+				g.fitBegin = static_cast<int>(xfits.size());
+				g.pad = 0;
+				for (size_t x = c0; x < c1; ++x) {
+					const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(fitsHere[x])];
+					gsb::XFitDesc xf;
+					xf.exclMask = 0u;
+					xf.taskBegin = static_cast<int>(xtasks.size());
+					xf.ntasks = pf.taskCount;
+					xf.pad = 0;
+					size_t exclRows = 0;
+					for (size_t q = 0; q < pf.exclBlocks.size(); ++q) {
+						const int a = static_cast<int>(std::lower_bound(atomBlocks.begin(), atomBlocks.end(), pf.exclBlocks[q]) - atomBlocks.begin());
+						xf.exclMask |= 1u << a;
+						exclRows += plan.blocks[static_cast<size_t>(pf.exclBlocks[q])].rows.size();
+					}
+					if (exclRows + pf.rows.size() != static_cast<size_t>(n)) ok = false;
+					for (int t = pf.taskBegin; t < pf.taskBegin + pf.taskCount; ++t) {
+						const gsb::PlanTask& pt = plan.tasks[static_cast<size_t>(t)];
+						gsb::XTaskDesc td;
+						td.atom = static_cast<int>(std::lower_bound(atomBlocks.begin(), atomBlocks.end(), pt.block) - atomBlocks.begin());
+						td.kind = pt.kind;
+						td.dest = pt.dest;
+						td.pad = 0;
+						if (!((xf.exclMask >> td.atom) & 1u)) ok = false; // a predicted block must be held out of the fit
+						xtasks.push_back(td);
+					}
+					xfits.push_back(xf);
+				}
+				groups.push_back(g);
+			}
+		}
+		if (ok) {
+			e->xz.reserve(static_cast<size_t>(R) * nr * P2);
+			DeviceArray<uint32_t> dPerm;
+			dPerm.upload(permRows, e->stream);
+			for (int r = 0; r < R; ++r) {
+				gsb::launchBlockGather(e->zpool.ptr, ldz, P2, nullptr, dPerm.ptr + static_cast<size_t>(r) * n, n,
+				                       e->xz.ptr + static_cast<size_t>(r) * nr * P2, nr, e->stream);
+			}
+			GSB_CUDA(cudaGetLastError());
+			e->xReps.upload(reps, e->stream);
+			e->xAtomRows.upload(atomRows, e->stream);
+			e->xGroups.upload(groups, e->stream);
+			e->xFits.upload(xfits, e->stream);
+			e->xTasks.upload(xtasks, e->stream);
+			GSB_CUDA(cudaStreamSynchronize(e->stream));
+			e->scoreGroups = static_cast<int>(groups.size());
+			e->scoreNr = nr;
+			e->scoreMaxK = std::max(gsb::scoreKernelMaxK(n, 1, e->smemLimit), gsb::scoreKernelMaxK(n, 2, e->smemLimit));
+		}
+	}
 
 	mPool.release(); // give the SYRK scratch back before the population tables are allocated
 
@@ -817,16 +1075,91 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			// size classes whose packed Gram exceeds shared memory spill their last rows to a global scratch
 			std::vector<long long> spillPerCta(e->buckets.size(), 0), spillOffset(e->buckets.size(), 0);
 			long long spillTotal = 0;
+			// size classes the replication-batched kernel takes (K1b): every group of fits of a chromosome in one CTA
+			const bool batchOn = e->batchGroups > 0 && e->tableA <= gsb::kBatchComponents && std::getenv("GSB_BATCH");
+			std::vector<char> useBatch(e->buckets.size(), 0);
+			std::vector<long long> scratchPerCta(e->buckets.size(), 0), scratchOffset(e->buckets.size(), 0);
+			long long scratchTotal = 0;
+			const bool scoresOn = e->scoreGroups > 0 && e->tableA <= gsb::kScoreComponents && !std::getenv("GSB_NO_SCORES");
+			std::vector<char> useScores(e->buckets.size(), 0);
 			for (size_t b = 0; b < e->buckets.size(); ++b) {
+				useScores[b] = scoresOn && e->buckets[b].kMax <= e->scoreMaxK;
+				useBatch[b] = !useScores[b] && batchOn && e->buckets[b].kMax <= e->batchMaxK;
+				if (!useBatch[b]) continue;
+				scratchPerCta[b] = gsb::batchKernelScratchDoubles(e->buckets[b].kMax, e->batchNfMax, e->batchUDoubles);
+				scratchOffset[b] = scratchTotal;
+				scratchTotal += scratchPerCta[b] * static_cast<long long>(e->buckets[b].count) * e->batchGroups;
+			}
+			for (size_t b = 0; b < e->buckets.size(); ++b) {
+				if (useBatch[b] || useScores[b]) continue;
 				spillPerCta[b] = gsb::fitKernelSpillDoubles(e->buckets[b].kMax, e->tableA, e->smemLimit, e->maxTasks, e->maxBlockLd);
 				spillOffset[b] = spillTotal;
 				spillTotal += spillPerCta[b] * static_cast<long long>(e->buckets[b].count) * static_cast<long long>(e->plan.fits.size());
 			}
+			if (scratchTotal > 0) e->batchScratch.reserve(static_cast<size_t>(scratchTotal));
 			if (spillTotal > 0) e->spill.reserve(static_cast<size_t>(spillTotal));
 			int slot = 0;
 			for (size_t bi = e->buckets.size(); bi-- > 0; ++slot) {
 				const size_t b = bi;
 				cudaStream_t launchStream = nside ? e->side[slot % nside] : e->stream;
+				if (useScores[b]) {
+					gsb::XParams xp;
+					xp.zpool = e->xz.ptr;
+					xp.reps = e->xReps.ptr;
+					xp.atomRows = e->xAtomRows.ptr;
+					xp.groups = e->xGroups.ptr;
+					xp.xfits = e->xFits.ptr;
+					xp.xtasks = e->xTasks.ptr;
+					xp.idx = e->dIdx.ptr;
+					xp.offsets = e->dOffsets.ptr;
+					xp.bucket = e->dBucket.ptr + e->buckets[b].begin;
+					xp.bucketCount = e->buckets[b].count;
+					xp.ngroups = e->scoreGroups;
+					xp.n = e->n;
+					xp.nr = e->scoreNr;
+					xp.p = e->p;
+					xp.maxNComp = e->tableA;
+					xp.innerDests = innerDests;
+					xp.outerDests = e->plan.groups;
+					xp.mse = e->dMse.ptr;
+					xp.ostat = e->dOstat.ptr;
+					GSB_CUDA(gsb::launchScoreKernel(xp, e->buckets[b].kMax, e->tableA, e->smemLimit, launchStream, &ctas));
+					++launches;
+					continue;
+				}
+				if (useBatch[b]) {
+					gsb::BatchParams bp;
+					bp.gfull = e->gfull.ptr;
+					bp.s0 = e->s0.ptr;
+					bp.xm = e->xm.ptr;
+					bp.zpool = e->zpool.ptr;
+					bp.fits = e->fits.ptr;
+					bp.blocks = e->blocks.ptr;
+					bp.groupFits = e->bGroupFits.ptr;
+					bp.groups = e->bGroups.ptr;
+					bp.pgs = e->bPgs.ptr;
+					bp.pairs = e->bPairs.ptr;
+					bp.units = e->bUnits.ptr;
+					bp.idx = e->dIdx.ptr;
+					bp.offsets = e->dOffsets.ptr;
+					bp.bucket = e->dBucket.ptr + e->buckets[b].begin;
+					bp.bucketCount = e->buckets[b].count;
+					bp.ngroups = e->batchGroups;
+					bp.p = e->p;
+					bp.maxNComp = e->tableA;
+					bp.innerDests = innerDests;
+					bp.outerDests = e->plan.groups;
+					bp.mse = e->dMse.ptr;
+					bp.ostat = e->dOstat.ptr;
+					bp.scratch = e->batchScratch.ptr + scratchOffset[b];
+					bp.scratchStride = scratchPerCta[b];
+					bp.uDoubles = e->batchUDoubles;
+					bp.pgp = e->batchPgp;
+					bp.nfMax = e->batchNfMax;
+					GSB_CUDA(gsb::launchBatchKernel(bp, e->buckets[b].kMax, e->tableA, e->smemLimit, launchStream, &ctas));
+					++launches;
+					continue;
+				}
 				gsb::FitParams prm;
 				prm.gram = e->gram.ptr;
 				prm.s0 = e->s0.ptr;

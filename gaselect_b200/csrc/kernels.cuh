@@ -109,6 +109,123 @@ struct OlsParams {
 	int* status;
 };
 
+
+// ---- K1b (simpls_batch.cu): all fits of a replication in one CTA ------------------------------------------
+// A "group" is a set of <= 16 training sets (fits) of the plan, normally the fits of one CV replication.  Every
+// fit's training Gram is the full-data Gram minus its <= 2 excluded row blocks, so the group shares ONE gathered
+// Gram in shared memory; what differs per fit are rank-|block| corrections applied from the block rows.
+// A "pair" is (block, fit): the block rows times the fit's direction vector.  It feeds the Gram correction of
+// the fit (corr != 0: the block is excluded from the fit's training rows) and / or a prediction task.
+struct BatchGroup {
+	int fitBegin;  // into groupFits
+	int nfits;
+	int pgBegin;   // into pgs
+	int npg;
+	int unitBegin; // into units: (pair-group, 32-row slab)
+	int nunits;
+	int pad0, pad1;
+};
+
+struct BatchPairGroup {
+	int block;
+	int npairs;    // <= 8, all on `block`
+	int pairBegin; // into pairs
+	int slabBegin; // first 32-row slab of this pair-group in the group's U buffer
+	int nslabs;
+	int ncorr;     // pairs with corr != 0
+	int pad0, pad1;
+};
+
+struct BatchPair {
+	int fitLocal; // index of the fit inside its group
+	int corr;     // the block is excluded from the fit's training rows
+	int kind;     // -1: no prediction task; 0 inner (MSEP table); 1 outer (pooled residual statistics)
+	int dest;
+};
+
+struct BatchParams {
+	const double* gfull; // packed lower triangle of Z'Z over all rows
+	const double* s0;    // nfits x p
+	const double* xm;    // nfits x p
+	const double* zpool;
+	const FitDesc* fits;
+	const BlockDesc* blocks;
+	const int* groupFits;
+	const BatchGroup* groups;
+	const BatchPairGroup* pgs;
+	const BatchPair* pairs;
+	const int2* units;
+	const uint32_t* idx;
+	const uint32_t* offsets;
+	const int* bucket;
+	int bucketCount;
+	int ngroups;
+	int p;
+	int maxNComp;
+	int innerDests;
+	int outerDests;
+	double* mse;
+	double* ostat;
+	double* scratch;          // per-CTA: stored loadings, per-fit s0 / x-bar columns, running predictions
+	long long scratchStride;  // doubles per CTA
+	int uDoubles;             // doubles of the U buffer (largest group)
+	int pgp;                  // row stride of U (pairs per pair-group, even)
+	int nfMax;                // largest group
+};
+
+// ---- K1x (simpls_scores.cu): score-space SIMPLS on the FP64 tensor cores, 8 fits of one replication per CTA --
+// Applies when the training sets of a replication are unions of a few disjoint row blocks ("atoms": the outer
+// segments of a nested CV whose inner segments coincide with them, plus the never-held-out rest).  Rows are kept in
+// atom order (one row-permuted copy of Z per replication); a fit is a bit mask of excluded atoms.
+struct XRepDesc {
+	unsigned long long zOff; // row-permuted copy of Z for this replication: ldg x (p + 2), column-major
+	int atomBegin;           // into atomRows: natoms + 1 row offsets
+	int natoms;
+};
+
+struct XFitDesc {
+	uint32_t exclMask; // atoms that are NOT training rows of this fit
+	int taskBegin;     // into xtasks
+	int ntasks;
+	int pad;
+};
+
+struct XTaskDesc {
+	int atom;
+	int kind; // 0 inner (MSEP table), 1 outer (pooled residual statistics)
+	int dest;
+	int pad;
+};
+
+struct XGroupDesc {
+	int rep;
+	int nfits;    // <= 8
+	int fitBegin; // into xfits
+	int pad;
+};
+
+struct XParams {
+	const double* zpool;
+	const XRepDesc* reps;
+	const int* atomRows;
+	const XGroupDesc* groups;
+	const XFitDesc* xfits;
+	const XTaskDesc* xtasks;
+	const uint32_t* idx;
+	const uint32_t* offsets;
+	const int* bucket;
+	int bucketCount;
+	int ngroups;
+	int n;        // rows
+	int nr;       // rows padded to a multiple of 8 (= leading dimension of the permuted copies)
+	int p;
+	int maxNComp;
+	int innerDests;
+	int outerDests;
+	double* mse;
+	double* ostat;
+};
+
 __host__ __device__ inline unsigned long long tri(unsigned long long i) { return i * (i + 1ull) / 2ull; }
 
 // launchers (definitions next to the kernels)
@@ -123,6 +240,15 @@ int fitKernelSharedBytes(int k, int A);
 int fitKernelMaxK(int A, int smemLimit);
 long long fitKernelSpillDoubles(int kMax, int A, int smemLimit, int maxTasks, int maxBlockLd);
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
+int batchKernelMaxK(int nfMax, int uDoubles, int smemLimit);
+long long batchKernelScratchDoubles(int kMax, int nfMax, int uDoubles);
+cudaError_t launchBatchKernel(const BatchParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
+constexpr int kBatchComponents = 10;
+int scoreKernelMaxK(int n, int clusterSize, int smemLimit);
+cudaError_t launchScoreKernel(const XParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
+constexpr int kScoreComponents = 10;
+constexpr int kScoreMaxRows = 192;
+constexpr int kScoreMaxAtoms = 32;
 void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream);
 cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream);
 int olsKernelMaxK(int smemLimit);

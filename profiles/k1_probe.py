@@ -15,7 +15,7 @@ ts = []
 for _ in range(steps):
     ev.evaluate_resident(); ts.append(ev.timing()["fit_kernel_ms"])
 fits = pop * 150
-print("k=%d pop=%d K1 ms=%s  us/fit-slot(148 SMs)=%.2f" % (k, pop, ["%.3f" % t for t in ts], min(ts) * 1e3 * 148 / fits))
+print("k=%d pop=%d K1 ms=%s  us/fit-slot(148 SMs)=%.2f ctas=%d" % (k, pop, ["%.3f" % t for t in ts], min(ts) * 1e3 * 148 / fits, ev.timing()["fit_ctas"]))
 tr = ev.debug_trace(40)
 if tr.any():
     d = np.diff(tr[tr > 0])
