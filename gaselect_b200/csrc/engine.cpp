@@ -99,7 +99,7 @@ struct Bucket {
 // subset-size classes: one K1 launch per class, shared memory sized for the class maximum
 int bucketCeil(int k) {
 	if (k <= 64) return roundUp(k, 8);
-	if (k <= 128) return roundUp(k, 16);
+	if (k <= 256) return roundUp(k, 16);
 	return roundUp(k, 32);
 }
 
@@ -161,13 +161,12 @@ struct gsb_engine {
 	DeviceArray<int2> bUnits;
 	int batchGroups = 0, batchNfMax = 0, batchUDoubles = 0, batchPgp = 2, batchMaxK = 0;
 	// K1x (score-space tensor-core kernel): row-permuted copies of Z per replication and the atom tables
-	DeviceArray<double> xz;
+	DeviceArray<double> xz, scoreScratch;
 	DeviceArray<gsb::XRepDesc> xReps;
-	DeviceArray<int> xAtomRows;
-	DeviceArray<gsb::XGroupDesc> xGroups;
+	DeviceArray<gsb::XGroupDesc> xGroups8, xGroups16;
 	DeviceArray<gsb::XFitDesc> xFits;
 	DeviceArray<gsb::XTaskDesc> xTasks;
-	int scoreGroups = 0, scoreNr = 0, scoreMaxK = 0;
+	int scoreGroups8 = 0, scoreGroups16 = 0, scoreNr = 0;
 	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
 
@@ -203,7 +202,7 @@ void releaseDevice(gsb_engine* e) {
 	e->spill.release();
 	e->gfull.release(); e->batchScratch.release(); e->bGroupFits.release(); e->bGroups.release(); e->bPgs.release();
 	e->bPairs.release(); e->bUnits.release();
-	e->xz.release(); e->xReps.release(); e->xAtomRows.release(); e->xGroups.release(); e->xFits.release(); e->xTasks.release();
+	e->xz.release(); e->scoreScratch.release(); e->xReps.release(); e->xGroups8.release(); e->xGroups16.release(); e->xFits.release(); e->xTasks.release();
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
@@ -591,9 +590,8 @@ void prepareDevice(gsb_engine* e) {
 	}
 
 	// ---- K1x: atoms (disjoint row blocks) per replication, fits as masks of excluded atoms
-	e->scoreGroups = 0;
-	e->scoreMaxK = 0;
-	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && n <= gsb::kScoreMaxRows && !std::getenv("GSB_NO_SCORES")) {
+	e->scoreGroups8 = e->scoreGroups16 = 0;
+	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && !std::getenv("GSB_NO_SCORES")) {
 		const int I = std::max(1, plan.innerPerGroup), O = std::max(1, plan.groupsPerReplication);
 		const int R = std::max(1, plan.groups / O);
 		std::vector<int> fitRep(static_cast<size_t>(nfits), 1 << 30);
@@ -602,13 +600,12 @@ void prepareDevice(gsb_engine* e) {
 			const int g = pt.kind == gsb::TASK_OUTER ? pt.dest : pt.dest / I;
 			fitRep[static_cast<size_t>(pt.fit)] = std::min(fitRep[static_cast<size_t>(pt.fit)], g / O);
 		}
-		const int nr = roundUp(n, 8);
 		std::vector<gsb::XRepDesc> reps(static_cast<size_t>(R));
-		std::vector<int> atomRows;
-		std::vector<gsb::XGroupDesc> groups;
+		std::vector<gsb::XGroupDesc> groups8, groups16;
 		std::vector<gsb::XFitDesc> xfits;
 		std::vector<gsb::XTaskDesc> xtasks;
-		std::vector<uint32_t> permRows; // R x n
+		std::vector<std::vector<uint32_t> > permRows(static_cast<size_t>(R)); // 32 x slots each, 0xffffffff = zero row
+		int maxSlots = 0;
 		bool ok = true;
 		for (int r = 0; r < R && ok; ++r) {
 			std::vector<int> fitsHere;
@@ -636,73 +633,95 @@ void prepareDevice(gsb_engine* e) {
 			bool rest = false;
 			for (int i = 0; i < n; ++i) if (owner[static_cast<size_t>(i)] < 0) { owner[static_cast<size_t>(i)] = natoms; rest = true; }
 			if (rest) ++natoms;
-			if (natoms > gsb::kScoreMaxAtoms) { ok = false; break; }
+			if (natoms > 32) { ok = false; break; }
+			// every atom starts a new 32-row slot
 			gsb::XRepDesc& rd = reps[static_cast<size_t>(r)];
-			rd.zOff = static_cast<unsigned long long>(r) * nr * P2;
-			rd.atomBegin = static_cast<int>(atomRows.size());
 			rd.natoms = natoms;
-			int at = 0;
-			for (int a = 0; a < natoms; ++a) {
-				atomRows.push_back(at);
-				for (int i = 0; i < n; ++i) if (owner[static_cast<size_t>(i)] == a) { permRows.push_back(static_cast<uint32_t>(i)); ++at; }
-			}
-			atomRows.push_back(at);
-			// fits in chunks of at most 8, balanced
-			const size_t count = fitsHere.size(), chunks = (count + 7) / 8, per = (count + chunks - 1) / chunks;
-			for (size_t c0 = 0; c0 < count && ok; c0 += per) {
-				const size_t c1 = std::min(count, c0 + per);
-				gsb::XGroupDesc g;
-				g.rep = r;
-				g.nfits = static_cast<int>(c1 - c0);
-				g.fitBegin = static_cast<int>(xfits.size());
-				g.pad = 0;
-				for (size_t x = c0; x < c1; ++x) {
-					const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(fitsHere[x])];
-					gsb::XFitDesc xf;
-					xf.exclMask = 0u;
-					xf.taskBegin = static_cast<int>(xtasks.size());
-					xf.ntasks = pf.taskCount;
-					xf.pad = 0;
-					size_t exclRows = 0;
-					for (size_t q = 0; q < pf.exclBlocks.size(); ++q) {
-						const int a = static_cast<int>(std::lower_bound(atomBlocks.begin(), atomBlocks.end(), pf.exclBlocks[q]) - atomBlocks.begin());
-						xf.exclMask |= 1u << a;
-						exclRows += plan.blocks[static_cast<size_t>(pf.exclBlocks[q])].rows.size();
-					}
-					if (exclRows + pf.rows.size() != static_cast<size_t>(n)) ok = false;
-					for (int t = pf.taskBegin; t < pf.taskBegin + pf.taskCount; ++t) {
-						const gsb::PlanTask& pt = plan.tasks[static_cast<size_t>(t)];
-						gsb::XTaskDesc td;
-						td.atom = static_cast<int>(std::lower_bound(atomBlocks.begin(), atomBlocks.end(), pt.block) - atomBlocks.begin());
-						td.kind = pt.kind;
-						td.dest = pt.dest;
-						td.pad = 0;
-						if (!((xf.exclMask >> td.atom) & 1u)) ok = false; // a predicted block must be held out of the fit
-						xtasks.push_back(td);
-					}
-					xfits.push_back(xf);
+			rd.nslots = 0;
+			std::vector<int> atomRowCount(static_cast<size_t>(natoms), 0);
+			std::vector<uint32_t>& perm = permRows[static_cast<size_t>(r)];
+			for (int a = 0; a < natoms && ok; ++a) {
+				std::vector<uint32_t> rowsA;
+				for (int i = 0; i < n; ++i) if (owner[static_cast<size_t>(i)] == a) rowsA.push_back(static_cast<uint32_t>(i));
+				atomRowCount[static_cast<size_t>(a)] = static_cast<int>(rowsA.size());
+				for (size_t at = 0; at < rowsA.size(); at += 32) {
+					if (rd.nslots >= gsb::kScoreMaxSlots) { ok = false; break; }
+					const int live = static_cast<int>(std::min<size_t>(32, rowsA.size() - at));
+					rd.slotAtom[rd.nslots] = a;
+					rd.slotRows[rd.nslots] = live;
+					++rd.nslots;
+					for (int j = 0; j < 32; ++j) perm.push_back(j < live ? rowsA[at + static_cast<size_t>(j)] : 0xffffffffu);
 				}
-				groups.push_back(g);
+			}
+			if (!ok) break;
+			for (int u = rd.nslots; u < gsb::kScoreMaxSlots; ++u) { rd.slotAtom[u] = -1; rd.slotRows[u] = 0; }
+			maxSlots = std::max(maxSlots, rd.nslots);
+			// fits of the replication: one group of <= 16, or groups of <= 8 (balanced chunks)
+			const int fitBase = static_cast<int>(xfits.size());
+			for (size_t x = 0; x < fitsHere.size(); ++x) {
+				const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(fitsHere[x])];
+				gsb::XFitDesc xf;
+				xf.exclMask = 0u;
+				xf.taskBegin = static_cast<int>(xtasks.size());
+				xf.ntasks = pf.taskCount;
+				xf.pad = 0;
+				size_t exclRows = 0;
+				for (size_t q = 0; q < pf.exclBlocks.size(); ++q) {
+					const int a = static_cast<int>(std::lower_bound(atomBlocks.begin(), atomBlocks.end(), pf.exclBlocks[q]) - atomBlocks.begin());
+					xf.exclMask |= 1u << a;
+					exclRows += plan.blocks[static_cast<size_t>(pf.exclBlocks[q])].rows.size();
+				}
+				if (exclRows + pf.rows.size() != static_cast<size_t>(n)) ok = false;
+				for (int t = pf.taskBegin; t < pf.taskBegin + pf.taskCount; ++t) {
+					const gsb::PlanTask& pt = plan.tasks[static_cast<size_t>(t)];
+					gsb::XTaskDesc td;
+					td.atom = static_cast<int>(std::lower_bound(atomBlocks.begin(), atomBlocks.end(), pt.block) - atomBlocks.begin());
+					td.kind = pt.kind;
+					td.dest = pt.dest;
+					td.rows = atomRowCount[static_cast<size_t>(td.atom)];
+					if (!((xf.exclMask >> td.atom) & 1u)) ok = false; // a predicted block must be held out of the fit
+					xtasks.push_back(td);
+				}
+				xfits.push_back(xf);
+			}
+			for (int width = 8; width <= 16; width += 8) {
+				std::vector<gsb::XGroupDesc>& groups = width == 8 ? groups8 : groups16;
+				const size_t count = fitsHere.size(), chunks = (count + width - 1) / width, per = (count + chunks - 1) / chunks;
+				for (size_t c0 = 0; c0 < count; c0 += per) {
+					gsb::XGroupDesc g;
+					g.rep = r;
+					g.nfits = static_cast<int>(std::min(count, c0 + per) - c0);
+					g.fitBegin = fitBase + static_cast<int>(c0);
+					g.pad = 0;
+					groups.push_back(g);
+				}
 			}
 		}
 		if (ok) {
+			const int nr = 32 * maxSlots;
+			for (int r = 0; r < R; ++r) {
+				permRows[static_cast<size_t>(r)].resize(static_cast<size_t>(nr), 0xffffffffu);
+				reps[static_cast<size_t>(r)].zOff = static_cast<unsigned long long>(r) * nr * P2;
+			}
+			std::vector<uint32_t> permAll;
+			for (int r = 0; r < R; ++r) permAll.insert(permAll.end(), permRows[static_cast<size_t>(r)].begin(), permRows[static_cast<size_t>(r)].end());
 			e->xz.reserve(static_cast<size_t>(R) * nr * P2);
 			DeviceArray<uint32_t> dPerm;
-			dPerm.upload(permRows, e->stream);
+			dPerm.upload(permAll, e->stream);
 			for (int r = 0; r < R; ++r) {
-				gsb::launchBlockGather(e->zpool.ptr, ldz, P2, nullptr, dPerm.ptr + static_cast<size_t>(r) * n, n,
+				gsb::launchBlockGather(e->zpool.ptr, ldz, P2, nullptr, dPerm.ptr + static_cast<size_t>(r) * nr, nr,
 				                       e->xz.ptr + static_cast<size_t>(r) * nr * P2, nr, e->stream);
 			}
 			GSB_CUDA(cudaGetLastError());
 			e->xReps.upload(reps, e->stream);
-			e->xAtomRows.upload(atomRows, e->stream);
-			e->xGroups.upload(groups, e->stream);
+			e->xGroups8.upload(groups8, e->stream);
+			e->xGroups16.upload(groups16, e->stream);
 			e->xFits.upload(xfits, e->stream);
 			e->xTasks.upload(xtasks, e->stream);
 			GSB_CUDA(cudaStreamSynchronize(e->stream));
-			e->scoreGroups = static_cast<int>(groups.size());
+			e->scoreGroups8 = static_cast<int>(groups8.size());
+			e->scoreGroups16 = static_cast<int>(groups16.size());
 			e->scoreNr = nr;
-			e->scoreMaxK = std::max(gsb::scoreKernelMaxK(n, 1, e->smemLimit), gsb::scoreKernelMaxK(n, 2, e->smemLimit));
 		}
 	}
 
@@ -1080,10 +1099,38 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			std::vector<char> useBatch(e->buckets.size(), 0);
 			std::vector<long long> scratchPerCta(e->buckets.size(), 0), scratchOffset(e->buckets.size(), 0);
 			long long scratchTotal = 0;
-			const bool scoresOn = e->scoreGroups > 0 && e->tableA <= gsb::kScoreComponents && !std::getenv("GSB_NO_SCORES");
+			// K1x configurations in order of preference (measured, profiles/kb_cfg.sh): the cost is dominated by a per-CTA,
+			// per-component overhead, so the fewest CTAs win: 16 fits per CTA, the stored loadings in the global scratch
+			// (vGlobal) as soon as that keeps the subset in one CTA, then clusters of 2 and 3 CTAs splitting the columns
+			const bool scoresOn = e->scoreGroups8 > 0 && e->tableA <= gsb::kScoreComponents && !std::getenv("GSB_NO_SCORES");
+			static const int kScoreCfg[8][3] = {{16, 1, 0}, {8, 1, 0}, {8, 1, 1}, {8, 2, 0}, {16, 2, 1}, {8, 2, 1}, {16, 3, 1}, {8, 3, 1}};
 			std::vector<char> useScores(e->buckets.size(), 0);
+			std::vector<int> scoreNf(e->buckets.size(), 0), scoreCs(e->buckets.size(), 0), scoreVg(e->buckets.size(), 0);
+			std::vector<long long> vPerCta(e->buckets.size(), 0), vOffset(e->buckets.size(), 0);
+			long long vTotal = 0;
+			int forcedNf = 0, forcedCs = 0, forcedVg = 0; // GSB_SCORE_CFG=nf,cs,vg: profiling aid
+			if (const char* fc = std::getenv("GSB_SCORE_CFG")) std::sscanf(fc, "%d,%d,%d", &forcedNf, &forcedCs, &forcedVg);
 			for (size_t b = 0; b < e->buckets.size(); ++b) {
-				useScores[b] = scoresOn && e->buckets[b].kMax <= e->scoreMaxK;
+				if (scoresOn && forcedNf > 0 && e->buckets[b].kMax <= gsb::scoreKernelMaxK(e->scoreNr, forcedNf, forcedCs, forcedVg, e->smemLimit)) {
+					useScores[b] = 1;
+					scoreNf[b] = forcedNf;
+					scoreCs[b] = forcedCs;
+					scoreVg[b] = forcedVg;
+				}
+				for (int c = 0; scoresOn && forcedNf == 0 && c < 8 && !useScores[b]; ++c) {
+					if (e->buckets[b].kMax <= gsb::scoreKernelMaxK(e->scoreNr, kScoreCfg[c][0], kScoreCfg[c][1], kScoreCfg[c][2], e->smemLimit)) {
+						useScores[b] = 1;
+						scoreNf[b] = kScoreCfg[c][0];
+						scoreCs[b] = kScoreCfg[c][1];
+						scoreVg[b] = kScoreCfg[c][2];
+					}
+				}
+				if (useScores[b] && scoreVg[b]) {
+					const long long groupsHere = scoreNf[b] == 16 ? e->scoreGroups16 : e->scoreGroups8;
+					vPerCta[b] = gsb::scoreKernelScratchDoubles(e->buckets[b].kMax, scoreNf[b], scoreCs[b]);
+					vOffset[b] = vTotal;
+					vTotal += vPerCta[b] * groupsHere * e->buckets[b].count * scoreCs[b];
+				}
 				useBatch[b] = !useScores[b] && batchOn && e->buckets[b].kMax <= e->batchMaxK;
 				if (!useBatch[b]) continue;
 				scratchPerCta[b] = gsb::batchKernelScratchDoubles(e->buckets[b].kMax, e->batchNfMax, e->batchUDoubles);
@@ -1097,6 +1144,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				spillTotal += spillPerCta[b] * static_cast<long long>(e->buckets[b].count) * static_cast<long long>(e->plan.fits.size());
 			}
 			if (scratchTotal > 0) e->batchScratch.reserve(static_cast<size_t>(scratchTotal));
+			if (vTotal > 0) e->scoreScratch.reserve(static_cast<size_t>(vTotal));
 			if (spillTotal > 0) e->spill.reserve(static_cast<size_t>(spillTotal));
 			int slot = 0;
 			for (size_t bi = e->buckets.size(); bi-- > 0; ++slot) {
@@ -1106,24 +1154,26 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 					gsb::XParams xp;
 					xp.zpool = e->xz.ptr;
 					xp.reps = e->xReps.ptr;
-					xp.atomRows = e->xAtomRows.ptr;
-					xp.groups = e->xGroups.ptr;
+					xp.groups = scoreNf[b] == 16 ? e->xGroups16.ptr : e->xGroups8.ptr;
 					xp.xfits = e->xFits.ptr;
 					xp.xtasks = e->xTasks.ptr;
 					xp.idx = e->dIdx.ptr;
 					xp.offsets = e->dOffsets.ptr;
 					xp.bucket = e->dBucket.ptr + e->buckets[b].begin;
 					xp.bucketCount = e->buckets[b].count;
-					xp.ngroups = e->scoreGroups;
-					xp.n = e->n;
+					xp.ngroups = scoreNf[b] == 16 ? e->scoreGroups16 : e->scoreGroups8;
 					xp.nr = e->scoreNr;
+					xp.nf = scoreNf[b];
+					xp.trace = e->traceBuf.ptr;
+					xp.vscratch = scoreVg[b] ? e->scoreScratch.ptr + vOffset[b] : nullptr;
+					xp.vstride = vPerCta[b];
 					xp.p = e->p;
 					xp.maxNComp = e->tableA;
 					xp.innerDests = innerDests;
 					xp.outerDests = e->plan.groups;
 					xp.mse = e->dMse.ptr;
 					xp.ostat = e->dOstat.ptr;
-					GSB_CUDA(gsb::launchScoreKernel(xp, e->buckets[b].kMax, e->tableA, e->smemLimit, launchStream, &ctas));
+					GSB_CUDA(gsb::launchScoreKernel(xp, e->buckets[b].kMax, e->tableA, scoreCs[b], scoreVg[b], e->smemLimit, launchStream, &ctas));
 					++launches;
 					continue;
 				}

@@ -202,7 +202,8 @@ __global__ void blockGatherKernel(const double* __restrict__ z, int ldz, const u
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= ld) return;
 	const size_t src = cols ? cols[c] : static_cast<uint32_t>(c);
-	dst[static_cast<size_t>(c) * ld + r] = (r < nrows) ? z[src * ldz + rows[r]] : 0.0;
+	// a row index of 0xffffffff asks for a zero row (padding inside a row-permuted copy)
+	dst[static_cast<size_t>(c) * ld + r] = (r < nrows && rows[r] != 0xffffffffu) ? z[src * ldz + rows[r]] : 0.0;
 }
 
 } // namespace

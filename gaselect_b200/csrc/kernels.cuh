@@ -178,9 +178,11 @@ struct BatchParams {
 // segments of a nested CV whose inner segments coincide with them, plus the never-held-out rest).  Rows are kept in
 // atom order (one row-permuted copy of Z per replication); a fit is a bit mask of excluded atoms.
 struct XRepDesc {
-	unsigned long long zOff; // row-permuted copy of Z for this replication: ldg x (p + 2), column-major
-	int atomBegin;           // into atomRows: natoms + 1 row offsets
+	unsigned long long zOff; // row-permuted copy of Z for this replication: nr x (p + 2), column-major
+	int nslots;              // 32-row slots; every atom starts a new slot (padding rows are zero rows)
 	int natoms;
+	int slotAtom[6];         // atom of each slot
+	int slotRows[6];         // live rows of each slot (<= 32)
 };
 
 struct XFitDesc {
@@ -194,12 +196,12 @@ struct XTaskDesc {
 	int atom;
 	int kind; // 0 inner (MSEP table), 1 outer (pooled residual statistics)
 	int dest;
-	int pad;
+	int rows; // rows of the atom
 };
 
 struct XGroupDesc {
 	int rep;
-	int nfits;    // <= 8
+	int nfits;    // <= 16
 	int fitBegin; // into xfits
 	int pad;
 };
@@ -207,7 +209,6 @@ struct XGroupDesc {
 struct XParams {
 	const double* zpool;
 	const XRepDesc* reps;
-	const int* atomRows;
 	const XGroupDesc* groups;
 	const XFitDesc* xfits;
 	const XTaskDesc* xtasks;
@@ -216,8 +217,11 @@ struct XParams {
 	const int* bucket;
 	int bucketCount;
 	int ngroups;
-	int n;        // rows
-	int nr;       // rows padded to a multiple of 8 (= leading dimension of the permuted copies)
+	int nr;       // rows of the permuted copies: 32 x slots (the same for every replication)
+	int nf;       // fits per group: 8 or 16 (= warps per CTA)
+	long long* trace; // optional (profiling): clock64() stamps of one CTA per launch
+	double* vscratch;    // stored loadings of the vGlobal configurations: one region per CTA
+	long long vstride;   // doubles per CTA
 	int p;
 	int maxNComp;
 	int innerDests;
@@ -244,11 +248,12 @@ int batchKernelMaxK(int nfMax, int uDoubles, int smemLimit);
 long long batchKernelScratchDoubles(int kMax, int nfMax, int uDoubles);
 cudaError_t launchBatchKernel(const BatchParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
 constexpr int kBatchComponents = 10;
-int scoreKernelMaxK(int n, int clusterSize, int smemLimit);
-cudaError_t launchScoreKernel(const XParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
+int scoreKernelMaxK(int nr, int nf, int clusterSize, int vGlobal, int smemLimit);
+long long scoreKernelScratchDoubles(int kMax, int nf, int clusterSize);
+cudaError_t launchScoreKernel(const XParams& prm, int kMax, int A, int clusterSize, int vGlobal, int smemLimit, cudaStream_t stream,
+                              long long* ctas);
 constexpr int kScoreComponents = 10;
-constexpr int kScoreMaxRows = 192;
-constexpr int kScoreMaxAtoms = 32;
+constexpr int kScoreMaxSlots = 6; // 32-row slots: at most 192 rows including the padding of every atom to 32
 void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream);
 cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream);
 int olsKernelMaxK(int smemLimit);

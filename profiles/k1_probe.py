@@ -16,7 +16,12 @@ for _ in range(steps):
     ev.evaluate_resident(); ts.append(ev.timing()["fit_kernel_ms"])
 fits = pop * 150
 print("k=%d pop=%d K1 ms=%s  us/fit-slot(148 SMs)=%.2f ctas=%d" % (k, pop, ["%.3f" % t for t in ts], min(ts) * 1e3 * 148 / fits, ev.timing()["fit_ctas"]))
-tr = ev.debug_trace(40)
+tr = ev.debug_trace(64)
+if tr[32:].any():
+    t0 = tr[0]
+    print('tile0:', (tr[:32][tr[:32] > 0] - t0).tolist())
+    print('tile1:', (tr[32:][tr[32:] > 0] - t0).tolist())
+    tr = tr[:32]
 if tr.any():
     d = np.diff(tr[tr > 0])
     print("phase clocks:", d.tolist(), "total", int(tr[tr > 0][-1] - tr[0]))

@@ -279,7 +279,7 @@ def test_resident_population_api_and_call_order(engine):
         assert fp and sp and n == 50
         t = ev.timing()
         # one CTA per (chromosome, fit) on the per-fit kernel, per (chromosome, group of <= 8 fits) on the score-space kernel
-        assert t["fit_ctas"] > 0 and t["fit_ctas"] % 50 == 0 and t["fit_ctas"] <= 50 * ev.info()["distinct_fits"] and t["fit_kernel_ms"] > 0
+        assert t["fit_ctas"] > 0 and t["fit_ctas"] % 50 == 0 and t["fit_ctas"] <= 4 * 50 * ev.info()["distinct_fits"] and t["fit_kernel_ms"] > 0
 
 
 def test_two_engines_and_a_caller_stream(engine):
