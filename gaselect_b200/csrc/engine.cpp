@@ -1103,10 +1103,12 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			// per-component overhead, so the fewest CTAs win: 16 fits per CTA, the stored loadings in the global scratch
 			// (vGlobal) as soon as that keeps the subset in one CTA, then clusters of 2 and 3 CTAs splitting the columns
 			const bool scoresOn = e->scoreGroups8 > 0 && e->tableA <= gsb::kScoreComponents && !std::getenv("GSB_NO_SCORES");
+			static const int kScoreMinK = 40;
 			static const int kScoreCfg[8][3] = {{16, 1, 0}, {8, 1, 0}, {8, 1, 1}, {8, 2, 0}, {16, 2, 1}, {8, 2, 1}, {16, 3, 1}, {8, 3, 1}};
 			std::vector<char> useScores(e->buckets.size(), 0);
 			std::vector<int> scoreNf(e->buckets.size(), 0), scoreCs(e->buckets.size(), 0), scoreVg(e->buckets.size(), 0);
 			std::vector<long long> vPerCta(e->buckets.size(), 0), vOffset(e->buckets.size(), 0);
+			std::vector<int> vSlots(e->buckets.size(), 0);
 			long long vTotal = 0;
 			int forcedNf = 0, forcedCs = 0, forcedVg = 0; // GSB_SCORE_CFG=nf,cs,vg: profiling aid
 			if (const char* fc = std::getenv("GSB_SCORE_CFG")) std::sscanf(fc, "%d,%d,%d", &forcedNf, &forcedCs, &forcedVg);
@@ -1117,7 +1119,9 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 					scoreCs[b] = forcedCs;
 					scoreVg[b] = forcedVg;
 				}
-				for (int c = 0; scoresOn && forcedNf == 0 && c < 8 && !useScores[b]; ++c) {
+				// small subsets: the per-fit kernel (one CTA per fit, many CTAs per SM) is faster below ~40 columns
+				const bool small = e->buckets[b].kMax <= kScoreMinK;
+				for (int c = 0; scoresOn && forcedNf == 0 && !small && c < 8 && !useScores[b]; ++c) {
 					if (e->buckets[b].kMax <= gsb::scoreKernelMaxK(e->scoreNr, kScoreCfg[c][0], kScoreCfg[c][1], kScoreCfg[c][2], e->smemLimit)) {
 						useScores[b] = 1;
 						scoreNf[b] = kScoreCfg[c][0];
@@ -1129,7 +1133,9 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 					const long long groupsHere = scoreNf[b] == 16 ? e->scoreGroups16 : e->scoreGroups8;
 					vPerCta[b] = gsb::scoreKernelScratchDoubles(e->buckets[b].kMax, scoreNf[b], scoreCs[b]);
 					vOffset[b] = vTotal;
-					vTotal += vPerCta[b] * groupsHere * e->buckets[b].count * scoreCs[b];
+					const long long ctasHere = groupsHere * e->buckets[b].count * scoreCs[b];
+					vSlots[b] = gsb::scoreKernelScratchSlots(e->buckets[b].kMax, scoreNf[b], scoreCs[b], e->scoreNr, ctasHere);
+					vTotal += vPerCta[b] * (vSlots[b] < 0 ? -vSlots[b] : vSlots[b]);
 				}
 				useBatch[b] = !useScores[b] && batchOn && e->buckets[b].kMax <= e->batchMaxK;
 				if (!useBatch[b]) continue;
@@ -1167,6 +1173,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 					xp.trace = e->traceBuf.ptr;
 					xp.vscratch = scoreVg[b] ? e->scoreScratch.ptr + vOffset[b] : nullptr;
 					xp.vstride = vPerCta[b];
+					xp.vslots = (scoreVg[b] && vSlots[b] < 0) ? -vSlots[b] : 0;
 					xp.p = e->p;
 					xp.maxNComp = e->tableA;
 					xp.innerDests = innerDests;

@@ -221,7 +221,8 @@ struct XParams {
 	int nf;       // fits per group: 8 or 16 (= warps per CTA)
 	long long* trace; // optional (profiling): clock64() stamps of one CTA per launch
 	double* vscratch;    // stored loadings of the vGlobal configurations: one region per CTA
-	long long vstride;   // doubles per CTA
+	long long vstride;   // doubles per region
+	int vslots;          // > 0: regions are indexed by %smid (at most one CTA of the launch per SM), else by CTA
 	int p;
 	int maxNComp;
 	int innerDests;
@@ -250,6 +251,8 @@ cudaError_t launchBatchKernel(const BatchParams& prm, int kMax, int A, int smemL
 constexpr int kBatchComponents = 10;
 int scoreKernelMaxK(int nr, int nf, int clusterSize, int vGlobal, int smemLimit);
 long long scoreKernelScratchDoubles(int kMax, int nf, int clusterSize);
+int scoreKernelScratchSlots(int kMax, int nf, int clusterSize, int nr, long long ctas);
+constexpr int kScoreSmSlots = 256; // >= the largest %smid + 1
 cudaError_t launchScoreKernel(const XParams& prm, int kMax, int A, int clusterSize, int vGlobal, int smemLimit, cudaStream_t stream,
                               long long* ctas);
 constexpr int kScoreComponents = 10;

@@ -272,7 +272,10 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsScoreKernel(const XParams pr
 	double* __restrict__ Zs = smem + cv.Z;
 	double* __restrict__ Sx = smem + cv.S;
 	double* __restrict__ Wv = smem + cv.Wv;
-	double* __restrict__ V = VG ? prm.vscratch + static_cast<size_t>(blockIdx.x) * prm.vstride : smem + cv.V;
+	// vGlobal: one scratch region per CTA, or -- when at most one CTA of this launch fits an SM (vslots > 0) -- per SM
+	unsigned vslot = blockIdx.x;
+	if (VG && prm.vslots > 0) asm volatile("mov.u32 %0, %%smid;" : "=r"(vslot));
+	double* __restrict__ V = VG ? prm.vscratch + static_cast<size_t>(vslot) * prm.vstride : smem + cv.V;
 	double* __restrict__ TA = smem + cv.TA;
 	double* __restrict__ TB = smem + cv.TB;
 	double* __restrict__ xch = smem + cv.xch;
@@ -614,6 +617,28 @@ int scoreKernelMaxK(int nr, int nf, int clusterSize, int vGlobal, int smemLimit)
 		++k;
 	}
 	return k;
+}
+
+template <int NF, int CS>
+int scoreOccupancy(int kMax, int nr) {
+	const XCarve cv = xCarve(xLocalColumns(kMax, CS), nr, NF, false);
+	int nb = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, simplsScoreKernel<NF, CS, true>, 32 * NF, static_cast<size_t>(cv.total) * sizeof(double)) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return nb;
+}
+
+// Scratch regions a vGlobal launch of `ctas` CTAs needs: one per CTA, or kScoreSmSlots (indexed by %smid) when the
+// launch is large and at most one of its CTAs fits an SM at a time (returned negative: index by %smid).
+int scoreKernelScratchSlots(int kMax, int nf, int clusterSize, int nr, long long ctas) {
+	if (ctas <= kScoreSmSlots) return static_cast<int>(ctas);
+	int nb = 0;
+	if (nf == 16) nb = clusterSize == 1 ? scoreOccupancy<16, 1>(kMax, nr) : clusterSize == 2 ? scoreOccupancy<16, 2>(kMax, nr) : scoreOccupancy<16, 3>(kMax, nr);
+	else nb = clusterSize == 1 ? scoreOccupancy<8, 1>(kMax, nr) : clusterSize == 2 ? scoreOccupancy<8, 2>(kMax, nr) : scoreOccupancy<8, 3>(kMax, nr);
+	if (nb == 1) return -kScoreSmSlots; // negative: indexed by %smid
+	return ctas > 2147483647LL ? 0 : static_cast<int>(ctas);
 }
 
 // doubles of global scratch one CTA needs for its stored loadings (vGlobal configurations)

@@ -2,7 +2,7 @@
 
 usage: python profiles/summarize.py r01
   gpurun_out/<round>_launches.csv      (ncu --metrics gpu__time_duration.sum ... python bench.py ...)
-  gpurun_out/<round>_k1_full.ncu-rep   (ncu --set full ... -k regex:simplsFit ... python bench.py ...)
+  gpurun_out/<round>_k1_full.ncu-rep   (ncu --set full ... -k regex:simpls ... python bench.py ...)
 """
 import collections, csv, io, os, subprocess, sys
 
@@ -39,6 +39,7 @@ if os.path.exists(rep):
             "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
             "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
             "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
             "lts__t_sectors_op_read.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum"]
     idx = [(w, hdr.index(w)) for w in want if w in hdr]
@@ -48,8 +49,8 @@ if os.path.exists(rep):
         for r in rows[2:]:
             w.writerow([r[i].replace("void gsb::<unnamed>::", "") for _, i in idx])
     out.append("")
-    out.append("== K1 (simplsFitFast) per size class, ncu --set full --clock-control none (one generation, 14 launches) ==")
-    out.append("%-10s %-8s %9s %10s %10s %6s %7s %7s %7s %7s %7s" % ("block", "grid", "time ms", "dram rd MB", "dram wr MB", "regs", "smem KB", "warps%", "issue%", "fp64%", "lds%"))
+    out.append("== K1 (simplsScoreKernel / simplsFitFast) per size class, ncu --set full --clock-control none (one generation) ==")
+    out.append("%-34s %-10s %-8s %9s %10s %10s %6s %7s %7s %7s %7s %7s %7s" % ("kernel", "block", "grid", "time ms", "dram rd MB", "dram wr MB", "regs", "smem KB", "warps%", "issue%", "fp64%", "lds%", "dmma%"))
     g = dict(idx)
     tot_t = tot_rd = tot_wr = 0.0
     for r in rows[2:]:
@@ -59,12 +60,13 @@ if os.path.exists(rep):
             except (KeyError, ValueError):
                 return d
         tot_t += f("gpu__time_duration.sum"); tot_rd += f("dram__bytes_read.sum"); tot_wr += f("dram__bytes_write.sum")
-        out.append("%-10s %-8s %9.3f %10.1f %10.1f %6.0f %7.1f %7.1f %7.1f %7.1f %7.1f" % (
-            r[g["Block Size"]].replace(" ", ""), r[g["Grid Size"]].split(",")[0].strip("("), f("gpu__time_duration.sum"),
+        out.append("%-34s %-10s %-8s %9.3f %10.1f %10.1f %6.0f %7.1f %7.1f %7.1f %7.1f %7.1f %7.1f" % (
+            r[g["Kernel Name"]].replace("void gsb::<unnamed>::", "").split("(")[0][:34], r[g["Block Size"]].replace(" ", ""), r[g["Grid Size"]].split(",")[0].strip("("), f("gpu__time_duration.sum"),
             f("dram__bytes_read.sum"), f("dram__bytes_write.sum"), f("launch__registers_per_thread"),
             f("launch__shared_mem_per_block_dynamic"), f("sm__warps_active.avg.pct_of_peak_sustained_active"),
             f("smsp__issue_active.avg.pct_of_peak_sustained_active"), f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
-            f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")))
+            f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+            f("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")))
     units = {n: rows[1][i] for n, i in idx}
     out.append("sum over the generation: time %.3f %s (serialised under ncu), dram read %.1f %s, dram write %.1f %s" % (
         tot_t, units.get("gpu__time_duration.sum", ""), tot_rd, units.get("dram__bytes_read.sum", ""), tot_wr, units.get("dram__bytes_write.sum", "")))
