@@ -167,6 +167,10 @@ struct gsb_engine {
 	DeviceArray<gsb::XFitDesc> xFits;
 	DeviceArray<gsb::XTaskDesc> xTasks;
 	int scoreGroups8 = 0, scoreGroups16 = 0, scoreNr = 0;
+	// K1k (kernel-space tensor-core kernel): training-row masks of the fits, held-out-row masks of the tasks
+	DeviceArray<gsb::KFitDesc> kFits;
+	DeviceArray<gsb::KTaskDesc> kTasks;
+	int kspaceFits = 0; // 0: not available for this plan
 	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
 
@@ -725,6 +729,36 @@ void prepareDevice(gsb_engine* e) {
 		}
 	}
 
+	// ---- K1k: per-lane row masks (lane = row mod 32) of every distinct fit and prediction task
+	e->kspaceFits = 0;
+	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && gsb::kspaceKernelFits(n, 1, e->smemLimit) && !std::getenv("GSB_NO_KSPACE")) {
+		std::vector<gsb::KFitDesc> kf(static_cast<size_t>(nfits));
+		std::vector<gsb::KTaskDesc> kt(plan.tasks.size());
+		for (int f = 0; f < nfits; ++f) {
+			const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
+			gsb::KFitDesc& d = kf[static_cast<size_t>(f)];
+			for (int u = 0; u < gsb::kKspaceSlots; ++u) d.train[u] = 0u;
+			for (size_t i = 0; i < pf.rows.size(); ++i) d.train[pf.rows[i] >> 5] |= 1u << (pf.rows[i] & 31u);
+			d.taskBegin = pf.taskBegin;
+			d.ntasks = pf.taskCount;
+			d.ntr = static_cast<int>(pf.rows.size());
+		}
+		for (size_t t = 0; t < plan.tasks.size(); ++t) {
+			const gsb::PlanTask& pt = plan.tasks[t];
+			const gsb::PlanBlock& pb = plan.blocks[static_cast<size_t>(pt.block)];
+			gsb::KTaskDesc& d = kt[t];
+			for (int u = 0; u < gsb::kKspaceSlots; ++u) d.rows[u] = 0u;
+			for (size_t i = 0; i < pb.rows.size(); ++i) d.rows[pb.rows[i] >> 5] |= 1u << (pb.rows[i] & 31u);
+			d.kind = pt.kind;
+			d.dest = pt.dest;
+			d.nrows = static_cast<int>(pb.rows.size());
+		}
+		e->kFits.upload(kf, e->stream);
+		e->kTasks.upload(kt, e->stream);
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		e->kspaceFits = nfits;
+	}
+
 	mPool.release(); // give the SYRK scratch back before the population tables are allocated
 
 	gsb_info& inf = e->info;
@@ -1111,8 +1145,24 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			std::vector<int> vSlots(e->buckets.size(), 0);
 			long long vTotal = 0;
 			int forcedNf = 0, forcedCs = 0, forcedVg = 0; // GSB_SCORE_CFG=nf,cs,vg: profiling aid
+			int desyncMode = 0;
+			if (const char* ds = std::getenv("GSB_DESYNC")) desyncMode = std::atoi(ds);
 			if (const char* fc = std::getenv("GSB_SCORE_CFG")) std::sscanf(fc, "%d,%d,%d", &forcedNf, &forcedCs, &forcedVg);
+			// K1k takes every size class above kspaceMinK in ONE launch (its cost per fit does not depend on the subset
+			// size; below, the per-fit and score-space kernels are cheaper): the classes are contiguous in dBucket
+			const bool kspaceOn = e->kspaceFits > 0 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit) && !std::getenv("GSB_NO_KSPACE");
+			int kspaceMinK = 56, kspaceSplit = 0;
+			if (const char* mk = std::getenv("GSB_KSPACE_MINK")) kspaceMinK = std::atoi(mk);
+			if (const char* sp = std::getenv("GSB_KSPACE_SPLIT")) kspaceSplit = std::atoi(sp);
+			std::vector<char> useKspace(e->buckets.size(), 0);
+			size_t kspaceFirst = e->buckets.size();
+			for (size_t b = e->buckets.size(); kspaceOn && b-- > 0;) {
+				if (e->buckets[b].kMax <= kspaceMinK) break;
+				useKspace[b] = 1;
+				kspaceFirst = b;
+			}
 			for (size_t b = 0; b < e->buckets.size(); ++b) {
+				if (useKspace[b]) continue;
 				if (scoresOn && forcedNf > 0 && e->buckets[b].kMax <= gsb::scoreKernelMaxK(e->scoreNr, forcedNf, forcedCs, forcedVg, e->smemLimit)) {
 					useScores[b] = 1;
 					scoreNf[b] = forcedNf;
@@ -1144,7 +1194,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				scratchTotal += scratchPerCta[b] * static_cast<long long>(e->buckets[b].count) * e->batchGroups;
 			}
 			for (size_t b = 0; b < e->buckets.size(); ++b) {
-				if (useBatch[b] || useScores[b]) continue;
+				if (useBatch[b] || useScores[b] || useKspace[b]) continue;
 				spillPerCta[b] = gsb::fitKernelSpillDoubles(e->buckets[b].kMax, e->tableA, e->smemLimit, e->maxTasks, e->maxBlockLd);
 				spillOffset[b] = spillTotal;
 				spillTotal += spillPerCta[b] * static_cast<long long>(e->buckets[b].count) * static_cast<long long>(e->plan.fits.size());
@@ -1153,8 +1203,43 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			if (vTotal > 0) e->scoreScratch.reserve(static_cast<size_t>(vTotal));
 			if (spillTotal > 0) e->spill.reserve(static_cast<size_t>(spillTotal));
 			int slot = 0;
+			if (kspaceFirst < e->buckets.size()) {
+				cudaStream_t launchStream = nside ? e->side[slot % nside] : e->stream;
+				++slot;
+				gsb::KParams kp;
+				kp.zpool = e->zpool.ptr;
+				kp.kfits = e->kFits.ptr;
+				kp.ktasks = e->kTasks.ptr;
+				kp.idx = e->dIdx.ptr;
+				kp.offsets = e->dOffsets.ptr;
+				kp.bucket = e->dBucket.ptr + e->buckets[kspaceFirst].begin;
+				kp.bucketCount = 0;
+				for (size_t b = kspaceFirst; b < e->buckets.size(); ++b) kp.bucketCount += e->buckets[b].count;
+				kp.nfits = e->kspaceFits;
+				// CTAs per chromosome: enough CTAs for ~6 waves over the SMs, each still amortising its own K over >= 3 passes
+				const int passes = (e->kspaceFits + 7) / 8;
+				int split = kspaceSplit;
+				if (split <= 0) {
+					split = 1;
+					while (split < 8 && static_cast<long long>(kp.bucketCount) * split < 6LL * e->smCount && (passes + split) / (split + 1) >= 3) ++split;
+				}
+				kp.split = std::max(1, std::min(split, passes));
+				kp.n = e->n;
+				kp.n8 = roundUp(e->n, 8);
+				kp.ldz = e->ldz;
+				kp.p = e->p;
+				kp.maxNComp = e->tableA;
+				kp.innerDests = innerDests;
+				kp.outerDests = e->plan.groups;
+				kp.mse = e->dMse.ptr;
+				kp.ostat = e->dOstat.ptr;
+				kp.trace = e->traceBuf.ptr;
+				GSB_CUDA(gsb::launchKspaceKernel(kp, launchStream, &ctas));
+				++launches;
+			}
 			for (size_t bi = e->buckets.size(); bi-- > 0; ++slot) {
 				const size_t b = bi;
+				if (useKspace[b]) { --slot; continue; }
 				cudaStream_t launchStream = nside ? e->side[slot % nside] : e->stream;
 				if (useScores[b]) {
 					gsb::XParams xp;
@@ -1174,6 +1259,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 					xp.vscratch = scoreVg[b] ? e->scoreScratch.ptr + vOffset[b] : nullptr;
 					xp.vstride = vPerCta[b];
 					xp.vslots = (scoreVg[b] && vSlots[b] < 0) ? -vSlots[b] : 0;
+					xp.desync = desyncMode;
 					xp.p = e->p;
 					xp.maxNComp = e->tableA;
 					xp.innerDests = innerDests;

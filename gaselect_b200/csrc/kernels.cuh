@@ -223,6 +223,7 @@ struct XParams {
 	double* vscratch;    // stored loadings of the vGlobal configurations: one region per CTA
 	long long vstride;   // doubles per region
 	int vslots;          // > 0: regions are indexed by %smid (at most one CTA of the launch per SM), else by CTA
+	int desync;          // 16-fit single-CTA launches: 0 CTA-wide barriers, 1 the two 8-fit tiles run on named barriers, 2/3 and start out of phase
 	int p;
 	int maxNComp;
 	int innerDests;
@@ -230,6 +231,44 @@ struct XParams {
 	double* mse;
 	double* ostat;
 };
+
+// ---- K1k (simpls_kspace.cu): SIMPLS in the space of the rows; one K = Z Z' per chromosome, any training sets --------
+constexpr int kKspaceComponents = 10;
+constexpr int kKspaceSlots = 5; // 32-row slots per lane: n <= 160
+
+struct KFitDesc {
+	uint32_t train[kKspaceSlots]; // bit r % 32 of word r / 32: row r is a training row
+	int taskBegin;                // into ktasks
+	int ntasks;
+	int ntr;                      // number of training rows
+};
+
+struct KTaskDesc {
+	uint32_t rows[kKspaceSlots]; // the held-out rows this task predicts
+	int kind;                    // 0 inner (MSEP table), 1 outer (pooled residual statistics)
+	int dest;
+	int nrows;
+};
+
+struct KParams {
+	const double* zpool; // globally centred Z = [X y 1], column-major, leading dimension ldz, rows n..ldz-1 zero
+	const KFitDesc* kfits;
+	const KTaskDesc* ktasks;
+	const uint32_t* idx;
+	const uint32_t* offsets;
+	const int* bucket;
+	int bucketCount;
+	int nfits;
+	int split;  // CTAs per chromosome (each builds K and takes a share of the passes of 8 fits)
+	int n, n8, ldz, p;
+	int maxNComp;
+	int innerDests;
+	int outerDests;
+	double* mse;
+	double* ostat;
+	long long* trace; // optional (profiling): clock64() stamps of one CTA
+};
+
 
 __host__ __device__ inline unsigned long long tri(unsigned long long i) { return i * (i + 1ull) / 2ull; }
 
@@ -257,6 +296,9 @@ cudaError_t launchScoreKernel(const XParams& prm, int kMax, int A, int clusterSi
                               long long* ctas);
 constexpr int kScoreComponents = 10;
 constexpr int kScoreMaxSlots = 6; // 32-row slots: at most 192 rows including the padding of every atom to 32
+int kspaceKernelSharedBytes(int n);
+int kspaceKernelFits(int n, int A, int smemLimit);
+cudaError_t launchKspaceKernel(const KParams& prm, cudaStream_t stream, long long* ctas);
 void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream);
 cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream);
 int olsKernelMaxK(int smemLimit);

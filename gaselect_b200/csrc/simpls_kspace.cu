@@ -1,0 +1,516 @@
+// simpls_kspace.cu -- K1k: SIMPLS in the space of the rows ("kernel space") on the FP64 tensor cores.
+//
+// What it replaces per CTA (same as simpls_fit.cu / simpls_scores.cu): PLS::viewSelectColumns / viewSelectRows
+// (src/PLS.cpp:13-23), PLSSimpls::fit (src/PLSSimpls.cpp:106-166), PLS::predict (src/PLS.cpp:34-47) and the MSEP /
+// residual sums of PLSEvaluator::estSEP (src/PLSEvaluator.cpp:263-268, 323-325).
+//
+// Every vector the reference's recurrences touch lies in the range of X' (S_0 = X_c'y_c, the loadings v = X_c't), so
+// the whole fit can be carried by vectors over the ROWS.  With Z = the selected columns of the globally centred data
+// (all rows), K = Z Z' (n x n, ONE matrix per chromosome, shared by every fit of every replication), a fit given by
+// its training-row mask m, and n-vectors g, h with S = Z'g, v = Z'h:
+//
+//   scores of every row      t = Z S            = K g        kept by recurrence: t <- t - (K h) (v'S)/(v'v)   (:135,:160)
+//   centring                 mean over the training rows of t  (= column-centring of X applied to t, :28-49)
+//   tc = m.(t - mu)/|.|      normalised training scores (:138-145);   q = y_c'tc (:148)
+//   predictions              yhat += (t - mu) q / |t|   on the held-out rows (cumulative coefficients, :152-156)
+//   loading                  v = Z'tc,  K tc = w  is THE tensor-core product of the component  (152 x 152) . (152 x 8)
+//   projections              V_j'v = (K h_j)'tc = U_j'tc   with U_j = K h_j / |v_j| stored per fit (:57-63)
+//   orthogonalised           K h = w - sum_j (U_j'tc) U_j = u,  v'v = tc'w - sum_j (U_j'tc)^2,  v'S = tc't   (:70-88)
+//
+// One product per component instead of the two of score space (Z S and Z't), its size independent of the subset size,
+// no stored loadings, no size classes, no clusters: the subset size only enters the one-off K = Z Z' (a DMMA SYRK over
+// column chunks streamed through shared memory with cp.async).  One warp per fit: lane = row (mod 32), the fit's
+// vectors (t, y_c, yhat, tc, the nine U_j) live in registers; masks are per-lane bits, so ANY training sets and
+// held-out blocks work (no atom structure needed).  Two CTA barriers per component (around the product).
+//
+// Numerics: mathematically the reference's SIMPLS; K squares the conditioning like the Gram-space kernel does.
+// tests/test_kspace_model.py holds the numpy model of exactly these recurrences (<= 6e-12 against the reference on
+// the parity data set, the same band as the oracle restatement itself).
+#include "kernels.cuh"
+
+namespace gsb {
+
+namespace {
+
+constexpr int kKA = kKspaceComponents;
+constexpr int kKNS = kKspaceSlots;   // 32-row slots per lane
+constexpr int kKNF = 8;              // fits per pass = warps per CTA (one tensor-core column tile)
+constexpr int kKThreads = 32 * kKNF;
+constexpr int kKBlocks = 7;          // 2x2-tile blocks of the lower triangle of K per warp: ceil(55 / 8) for 20 tiles
+
+__host__ __device__ inline int roundUpK(int v, int m) { return (v + m - 1) / m * m; }
+
+__device__ __forceinline__ void dmma884k(double& d0, double& d1, double a, double b) {
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cpAsync16k(double* dst, const double* src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src));
+}
+__device__ __forceinline__ void cpAsyncWaitAllK() {
+	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ double shflXorK(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// Sum NV (a power of two <= 16) values per lane over the warp with NV - 1 + log2(32 / NV) shuffles: the lanes halve
+// the value set at every butterfly step.  Afterwards lane L holds the total of value L / (32 / NV).
+template <int NV>
+__device__ __forceinline__ double warpSumNK(double (&v)[NV], int lane) {
+	int m = 16;
+#pragma unroll
+	for (int h = NV / 2; h >= 1; h >>= 1, m >>= 1) {
+		const bool up = (lane & m) != 0;
+#pragma unroll
+		for (int i = 0; i < h; ++i) {
+			const double send = up ? v[i] : v[i + h];
+			const double keep = up ? v[i + h] : v[i];
+			v[i] = keep + shflXorK(send, m);
+		}
+	}
+	double r = v[0];
+#pragma unroll
+	for (; m >= 1; m >>= 1) r += shflXorK(r, m);
+	return r;
+}
+
+struct KCarve {
+	int ldk;
+	int K, TA, TB, ys, total; // in doubles; the column ids of a chunk alias TA, the staged chunk aliases K
+};
+
+__host__ __device__ inline KCarve kCarve(int n8) {
+	KCarve c;
+	c.ldk = n8 + 4; // = 4 or 12 (mod 16): the 8x4 / 4x8 fragment loads are bank-conflict free
+	int o = 0;
+	c.K = o; o += n8 * c.ldk;
+	c.TA = o; o += kKNF * c.ldk; // [fit][row]: B operand of the product
+	c.TB = o; o += kKNF * c.ldk; // [fit][row]: its result
+	c.ys = o; o += n8;
+	c.total = o;
+	return c;
+}
+
+// dst[fit][row] = sum_r K[row][r] src[fit][r]: 8 warps share the row tiles (tiles ws, ws + 8, ...), NT per warp
+template <int NT>
+__device__ __forceinline__ void productTiles(const double* __restrict__ kp, const double* __restrict__ bp, int nsteps, int tileStride,
+                                             double* __restrict__ dst, int ldk) {
+	double c0[NT], c1[NT];
+#pragma unroll
+	for (int j = 0; j < NT; ++j) { c0[j] = 0.0; c1[j] = 0.0; }
+#pragma unroll 2
+	for (int s = 0; s < nsteps; ++s) {
+		const double b = *bp;
+#pragma unroll
+		for (int j = 0; j < NT; ++j) dmma884k(c0[j], c1[j], kp[j * tileStride], b);
+		kp += 4;
+		bp += 4;
+	}
+#pragma unroll
+	for (int j = 0; j < NT; ++j) {
+		dst[j * 64] = c0[j];
+		dst[j * 64 + ldk] = c1[j];
+	}
+}
+
+__device__ __forceinline__ void kernelProduct(const double* __restrict__ Km, const double* __restrict__ src, double* __restrict__ dst,
+                                              int n8, int ldk, int warp, int lane) {
+	const int g = lane >> 2, t = lane & 3;
+	const int nt = n8 >> 3, nsteps = n8 >> 2;
+	const int ntiles = (nt - warp + kKNF - 1) / kKNF;
+	const double* __restrict__ kp = Km + (8 * warp + g) * ldk + t;
+	const double* __restrict__ bp = src + g * ldk + t;
+	double* __restrict__ dp = dst + (2 * t) * ldk + 8 * warp + g;
+	switch (ntiles) {
+	case 1: productTiles<1>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+	case 2: productTiles<2>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+	case 3: productTiles<3>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+	default: break;
+	}
+}
+
+// what a component step needs besides the fit's own vectors
+struct KCtx {
+	const KParams* prm;
+	const double* Km;
+	double* TA;
+	double* TB;
+	double* taW;       // this warp's row of TA
+	const double* tbW; // this warp's row of TB
+	int n8, ldk, warp, lane, A, chrom;
+	const KFitDesc* fd;
+	const KTaskDesc* tdA;
+	const KTaskDesc* tdB;
+	double rrowsA, rrowsB;
+	bool tracing;
+};
+
+// the vectors of one fit, one warp per fit, lane = row (mod 32): all in registers
+struct KFitState {
+	double yc[kKNS], tt[kKNS], pred[kKNS];
+	double U[kKA - 1][kKNS];
+	uint32_t trainBits, rowBits;
+	double rntr, syc;
+	bool under;
+};
+
+#define GSB_KSTAMP() do { if (cx.tracing && stamp < 64) cx.prm->trace[stamp++] = clock64(); } while (0)
+
+// component COMP (0-based) of the 8 fits of a pass; the barriers are uniform (A is a property of the chromosome)
+template <int COMP>
+__device__ __forceinline__ void kspaceComponent(KFitState& fs, const KCtx& cx, int& stamp) {
+	if (COMP >= cx.A) return;
+	const KParams& prm = *cx.prm;
+	const int lane = cx.lane;
+	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+	// ---- centre, normalise, predict the held-out rows ----------------------------------------------------------
+	double tc[kKNS];
+	{
+		double sv[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) {
+			if ((fs.trainBits >> u) & 1u) {
+				sv[0] += fs.tt[u];
+				sv[1] = fma(fs.tt[u], fs.tt[u], sv[1]);
+				sv[2] = fma(fs.yc[u], fs.tt[u], sv[2]);
+			}
+		}
+		const double tot = warpSumNK<4>(sv, lane); // lane L: value L / 8
+		const double s1 = __shfl_sync(0xffffffffu, tot, 0), s2 = __shfl_sync(0xffffffffu, tot, 8), s3 = __shfl_sync(0xffffffffu, tot, 16);
+		if (COMP == 1) GSB_KSTAMP();
+		// centring of the scores = column-centring of X (:28-49): |t - mu|^2 = sum t^2 - n mu^2, y_c'(t - mu)
+		const double mu = s1 * fs.rntr;
+		const double a2 = fma(-s1, mu, s2);
+		fs.under = fs.under || !(a2 >= 1e-50); // ||t|| < 1e-25 (NORM_TOL, :16,:141-143); also NaN
+		const double b2 = fma(-mu, fs.syc, s3);
+		const double rtn = rsqrt(a2);
+		const double q = b2 * rtn;
+		const double fac = fs.under ? nanv : q * rtn; // coefficient increment is S q / tn (:152-156)
+		const double scale = fs.under ? nanv : rtn;
+		if (COMP == 1 && cx.tracing && stamp < 64 && scale != 0.0) cx.prm->trace[stamp++] = clock64();
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) {
+			const double d = fs.tt[u] - mu;
+			tc[u] = ((fs.trainBits >> u) & 1u) ? d * scale : 0.0;
+			fs.pred[u] = fma(d, fac, fs.pred[u]); // only the held-out rows are read
+		}
+	}
+	const bool more = COMP + 1 < cx.A;
+	if (more) {
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) {
+			if ((fs.rowBits >> u) & 1u) cx.taW[32 * u + lane] = tc[u];
+		}
+	}
+	if (COMP == 1) GSB_KSTAMP();
+	// residual sums of the prediction tasks, two tasks per reduction
+	const KFitDesc& fd = *cx.fd;
+	for (int tk = 0; tk < fd.ntasks; tk += 2) {
+		KTaskDesc td0 = *cx.tdA, td1 = *cx.tdB;
+		if (tk > 0) { // more than two tasks on one fit: not in a nested CV, but legal
+			td0 = prm.ktasks[fd.taskBegin + tk];
+			if (tk + 1 < fd.ntasks) td1 = prm.ktasks[fd.taskBegin + tk + 1];
+		}
+		const bool two = tk + 1 < fd.ntasks;
+		double st[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) {
+			const double e = fs.yc[u] - fs.pred[u];
+			if ((td0.rows[u] >> lane) & 1u) { st[0] += e; st[1] = fma(e, e, st[1]); }
+			if (two && ((td1.rows[u] >> lane) & 1u)) { st[2] += e; st[3] = fma(e, e, st[3]); }
+		}
+		const double tot = warpSumNK<4>(st, lane); // lane L: value L / 8
+		if ((lane & 7) == 0) {
+			const int vi = lane >> 3;
+			const bool second = vi >= 2;
+			if (!second || two) {
+				const int kind = second ? td1.kind : td0.kind, dest = second ? td1.dest : td0.dest;
+				if (kind == 0) {
+					// mean squared error of prediction for this fold (src/PLSEvaluator.cpp:266-268)
+					const double rr = (tk > 0) ? 1.0 / static_cast<double>(second ? td1.nrows : td0.nrows) : (second ? cx.rrowsB : cx.rrowsA);
+					if (vi & 1) prm.mse[(static_cast<size_t>(cx.chrom) * prm.innerDests + dest) * prm.maxNComp + COMP] = tot * rr;
+				} else {
+					prm.ostat[((static_cast<size_t>(cx.chrom) * prm.outerDests + dest) * prm.maxNComp + COMP) * 2 + (vi & 1)] = tot;
+				}
+			}
+		}
+	}
+	if (!more) return;
+	if (COMP == 1) GSB_KSTAMP();
+	// ---- w = K tc: the loading v = X't seen from the rows (:145-147) -------------------------------------------
+	__syncthreads();
+	GSB_KSTAMP();
+	kernelProduct(cx.Km, cx.TA, cx.TB, cx.n8, cx.ldk, cx.warp, lane);
+	__syncthreads();
+	GSB_KSTAMP();
+	// ---- orthogonalise against the stored loadings, deflate (:57-63, :70-88, :160) -----------------------------
+	double w[kKNS];
+#pragma unroll
+	for (int u = 0; u < kKNS; ++u) w[u] = ((fs.rowBits >> u) & 1u) ? cx.tbW[32 * u + lane] : 0.0;
+	constexpr int NV = (COMP + 2 <= 2) ? 2 : (COMP + 2 <= 4) ? 4 : (COMP + 2 <= 8) ? 8 : 16;
+	double sv[NV];
+#pragma unroll
+	for (int j = 0; j < NV; ++j) sv[j] = 0.0;
+#pragma unroll
+	for (int u = 0; u < kKNS; ++u) {
+#pragma unroll
+		for (int j = 0; j < COMP; ++j) sv[j] = fma(fs.U[j][u], tc[u], sv[j]); // V_j'v = U_j'tc
+		sv[COMP] = fma(tc[u], fs.tt[u], sv[COMP]);                             // v'S = tc't
+		sv[COMP + 1] = fma(tc[u], w[u], sv[COMP + 1]);                         // |X'tc|^2 = tc'K tc
+	}
+	const double tot = warpSumNK<NV>(sv, lane);
+	constexpr int LP = 32 / NV; // lanes per value
+	double cj[kKA];
+	double vv = __shfl_sync(0xffffffffu, tot, (COMP + 1) * LP);
+	const double vs = __shfl_sync(0xffffffffu, tot, COMP * LP);
+#pragma unroll
+	for (int j = 0; j < COMP; ++j) {
+		cj[j] = __shfl_sync(0xffffffffu, tot, j * LP);
+		vv = fma(-cj[j], cj[j], vv); // |v - sum_j (V_j'v) V_j|^2 for orthonormal V_j
+	}
+	const double dd = vs / vv;
+	const double rvn = rsqrt(vv);
+#pragma unroll
+	for (int u = 0; u < kKNS; ++u) {
+		// two partial sums: half the dependent chain
+		double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+		for (int j = 0; j < COMP; j += 2) {
+			d0 = fma(fs.U[j][u], cj[j], d0);
+			if (j + 1 < COMP) d1 = fma(fs.U[j + 1][u], cj[j + 1], d1);
+		}
+		const double uu = w[u] - (d0 + d1); // K h for the orthogonalised loading v = Z'h
+		double tn = fma(-uu, dd, fs.tt[u]);  // Z (S - v v'S / v'v)
+		if (fs.under) tn = nanv;             // the reference throws: poison this and every later component
+		fs.tt[u] = tn;
+		if (COMP < kKA - 1) fs.U[COMP < kKA - 1 ? COMP : 0][u] = uu * rvn;
+	}
+	GSB_KSTAMP();
+}
+
+template <int COMP>
+struct KSteps {
+	static __device__ __forceinline__ void run(KFitState& fs, const KCtx& cx, int& stamp) {
+		kspaceComponent<COMP>(fs, cx, stamp);
+		KSteps<COMP + 1>::run(fs, cx, stamp);
+	}
+};
+template <>
+struct KSteps<kKA> {
+	static __device__ __forceinline__ void run(KFitState&, const KCtx&, int&) {}
+};
+#undef GSB_KSTAMP
+
+__global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams prm) {
+	extern __shared__ __align__(16) double smem[];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int g = lane >> 2, t4 = lane & 3;
+	const int n = prm.n, n8 = prm.n8, ldz = prm.ldz;
+	const KCarve cv = kCarve(n8);
+	const int ldk = cv.ldk;
+	double* __restrict__ Km = smem + cv.K;
+	double* __restrict__ TA = smem + cv.TA;
+	double* __restrict__ TB = smem + cv.TB;
+	double* __restrict__ ys = smem + cv.ys;
+	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(TA);
+
+	// largest subsets first (the bucket list is ascending): their K costs the most
+	const int ci = prm.bucketCount - 1 - static_cast<int>(blockIdx.x % static_cast<unsigned>(prm.bucketCount));
+	const int part = static_cast<int>(blockIdx.x / static_cast<unsigned>(prm.bucketCount));
+	const int chrom = prm.bucket[ci];
+	const uint32_t selBegin = prm.offsets[chrom];
+	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
+	const int A = min(prm.maxNComp, k);
+	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+
+	const bool tracing = prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
+	int stamp = 0;
+#define GSB_KSTAMP() do { if (tracing && stamp < 64) prm.trace[stamp++] = clock64(); } while (0)
+	GSB_KSTAMP();
+
+	// globally centred response of every row (column p of Z)
+	for (int r = tid; r < n8; r += kKThreads) ys[r] = (r < n) ? __ldg(prm.zpool + static_cast<size_t>(prm.p) * ldz + r) : 0.0;
+
+	// ---- K = Z Z' over column chunks (PLS::viewSelectColumns + the implicit X X' of the recurrences) -------------
+	{
+		const int nt = n8 >> 3, nb = (nt + 1) >> 1, nblocks = nb * (nb + 1) / 2;
+		double acc[kKBlocks][8];
+		int rowA[kKBlocks], rowB[kKBlocks]; // first row of the block's tile pairs; -1: no block
+#pragma unroll
+		for (int b = 0; b < kKBlocks; ++b) {
+#pragma unroll
+			for (int i = 0; i < 8; ++i) acc[b][i] = 0.0;
+			const int id = warp + kKNF * b;
+			rowA[b] = -1;
+			rowB[b] = 0;
+			if (id < nblocks) {
+				int bi = 0;
+				while ((bi + 1) * (bi + 2) / 2 <= id) ++bi;
+				rowA[b] = 16 * bi;
+				rowB[b] = 16 * (id - bi * (bi + 1) / 2);
+			}
+		}
+		const int chunk = n8; // columns per chunk: the staged chunk [column][ldk] fills exactly the area of K
+		for (int c0 = 0; c0 < k; c0 += chunk) {
+			const int kc = min(chunk, k - c0), kc4 = roundUpK(kc, 4);
+			__syncthreads(); // the previous chunk has been consumed
+			for (int j = tid; j < kc; j += kKThreads) sel[j] = prm.idx[selBegin + c0 + j];
+			__syncthreads();
+			const int pieces = ldz >> 1; // 16-byte pieces per column (ldz is a multiple of 4)
+			for (int j = warp; j < kc4; j += kKNF) {
+				double* __restrict__ dcol = Km + j * ldk;
+				if (j < kc) {
+					const double* __restrict__ scol = prm.zpool + static_cast<size_t>(sel[j]) * ldz;
+					for (int piece = lane; piece < pieces; piece += 32) cpAsync16k(dcol + 2 * piece, scol + 2 * piece);
+					for (int r = ldz + lane; r < ldk; r += 32) dcol[r] = 0.0;
+				} else {
+					for (int r = lane; r < ldk; r += 32) dcol[r] = 0.0;
+				}
+			}
+			cpAsyncWaitAllK();
+			__syncthreads();
+			const int nsteps = kc4 >> 2;
+#pragma unroll
+			for (int b = 0; b < kKBlocks; ++b) {
+				if (rowA[b] >= 0) {
+					// tile rows beyond n8 (odd tile count) read the padding / the next column: results discarded
+					const double* __restrict__ pa = Km + t4 * ldk + rowA[b] + g;
+					const double* __restrict__ pb = Km + t4 * ldk + rowB[b] + g;
+#pragma unroll 2
+					for (int s = 0; s < nsteps; ++s) {
+						const double a0 = pa[0], a1 = pa[8], b0 = pb[0], b1 = pb[8];
+						dmma884k(acc[b][0], acc[b][1], a0, b0);
+						dmma884k(acc[b][2], acc[b][3], a0, b1);
+						dmma884k(acc[b][4], acc[b][5], a1, b0);
+						dmma884k(acc[b][6], acc[b][7], a1, b1);
+						pa += 4 * ldk;
+						pb += 4 * ldk;
+					}
+				}
+			}
+		}
+		__syncthreads(); // every warp is done with the staged columns: K takes their place
+#pragma unroll
+		for (int b = 0; b < kKBlocks; ++b) {
+			if (rowA[b] >= 0) {
+#pragma unroll
+				for (int i = 0; i < 2; ++i) {
+#pragma unroll
+					for (int j = 0; j < 2; ++j) {
+						const int r0 = rowA[b] + 8 * i, c0 = rowB[b] + 8 * j;
+						if (r0 < n8 && c0 < n8 && r0 >= c0) {
+							const double v0 = acc[b][(i * 2 + j) * 2], v1 = acc[b][(i * 2 + j) * 2 + 1];
+							Km[(r0 + g) * ldk + c0 + 2 * t4] = v0;
+							Km[(r0 + g) * ldk + c0 + 2 * t4 + 1] = v1;
+							if (r0 != c0) {
+								Km[(c0 + 2 * t4) * ldk + r0 + g] = v0;
+								Km[(c0 + 2 * t4 + 1) * ldk + r0 + g] = v1;
+							}
+						}
+					}
+				}
+			}
+		}
+	}
+	__syncthreads();
+	GSB_KSTAMP(); // 1: K done
+
+	// ---- passes of 8 fits: one warp per fit ----------------------------------------------------------------------
+	const int passes = (prm.nfits + kKNF - 1) / kKNF;
+	const int perPart = (passes + prm.split - 1) / prm.split;
+	const int passEnd = min(passes, (part + 1) * perPart);
+	double* __restrict__ taW = TA + warp * ldk;
+	const double* __restrict__ tbW = TB + warp * ldk;
+#pragma unroll 1
+	for (int pass = part * perPart; pass < passEnd; ++pass) {
+		const int fi = pass * kKNF + warp;
+		const bool fitActive = fi < prm.nfits;
+		KFitDesc fd;
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) fd.train[u] = 0u;
+		fd.taskBegin = 0; fd.ntasks = 0; fd.ntr = 1;
+		if (fitActive) fd = prm.kfits[fi];
+		KTaskDesc tdA, tdB;
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) { tdA.rows[u] = 0u; tdB.rows[u] = 0u; }
+		tdA.kind = -1; tdA.dest = 0; tdA.nrows = 1;
+		tdB.kind = -1; tdB.dest = 0; tdB.nrows = 1;
+		if (fd.ntasks > 0) tdA = prm.ktasks[fd.taskBegin];
+		if (fd.ntasks > 1) tdB = prm.ktasks[fd.taskBegin + 1];
+		const double rrowsA = 1.0 / static_cast<double>(tdA.nrows), rrowsB = 1.0 / static_cast<double>(tdB.nrows);
+
+		KFitState fs;
+		fs.trainBits = 0u; // bit u: the lane's row of slot u is a training row of the fit
+		fs.rowBits = 0u;   // bit u: the lane's row of slot u exists in shared memory
+		fs.under = false;
+		{
+			double sy = 0.0;
+#pragma unroll
+			for (int u = 0; u < kKNS; ++u) {
+				const int r = 32 * u + lane;
+				if (r < n8) fs.rowBits |= 1u << u;
+				if ((fd.train[u] >> lane) & 1u) fs.trainBits |= 1u << u;
+				fs.yc[u] = (r < n8) ? ys[r] : 0.0;
+				fs.pred[u] = 0.0;
+				if ((fs.trainBits >> u) & 1u) sy += fs.yc[u];
+			}
+#pragma unroll
+			for (int m = 16; m >= 1; m >>= 1) sy += shflXorK(sy, m);
+			fs.rntr = 1.0 / static_cast<double>(fd.ntr);
+			const double ym = sy * fs.rntr;
+			double s2 = 0.0;
+#pragma unroll
+			for (int u = 0; u < kKNS; ++u) {
+				fs.yc[u] = (32 * u + lane < n) ? fs.yc[u] - ym : 0.0;
+				if ((fs.trainBits >> u) & 1u) s2 += fs.yc[u];
+			}
+#pragma unroll
+			for (int m = 16; m >= 1; m >>= 1) s2 += shflXorK(s2, m);
+			fs.syc = s2; // rounding residue of the centring, ~ 1e-16
+		}
+		// t_0 = Z S_0 = K (m . y_c)   (S_0 = X_c'y_c, :126)
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) {
+			if ((fs.rowBits >> u) & 1u) taW[32 * u + lane] = ((fs.trainBits >> u) & 1u) ? fs.yc[u] : 0.0;
+		}
+		__syncthreads();
+		kernelProduct(Km, TA, TB, n8, ldk, warp, lane);
+		__syncthreads();
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) fs.tt[u] = ((fs.rowBits >> u) & 1u) ? tbW[32 * u + lane] : 0.0;
+		KCtx cx;
+		cx.prm = &prm; cx.Km = Km; cx.TA = TA; cx.TB = TB; cx.taW = taW; cx.tbW = tbW;
+		cx.n8 = n8; cx.ldk = ldk; cx.warp = warp; cx.lane = lane; cx.A = A; cx.chrom = chrom;
+		cx.fd = &fd; cx.tdA = &tdA; cx.tdB = &tdB; cx.rrowsA = rrowsA; cx.rrowsB = rrowsB;
+		cx.tracing = tracing && pass == part * perPart;
+		if (cx.tracing) GSB_KSTAMP(); // 2: first scores
+		KSteps<0>::run(fs, cx, stamp);
+	}
+#undef GSB_KSTAMP
+}
+
+} // namespace
+
+int kspaceKernelSharedBytes(int n) {
+	return kCarve(roundUpK(n, 8)).total * static_cast<int>(sizeof(double));
+}
+
+// 1 when the kernel-space kernel can take a plan with n rows and A components under the shared-memory limit
+int kspaceKernelFits(int n, int A, int smemLimit) {
+	const int n8 = roundUpK(n, 8);
+	if (n < 8 || n8 > 32 * kKNS || A > kKA || A < 1) return 0;
+	if ((n8 >> 3) > 20) return 0; // 2x2 blocks of the lower triangle: kKBlocks * 8 >= blocks
+	return kspaceKernelSharedBytes(n) <= smemLimit ? 1 : 0;
+}
+
+cudaError_t launchKspaceKernel(const KParams& prm, cudaStream_t stream, long long* ctas) {
+	const int bytes = kspaceKernelSharedBytes(prm.n);
+	const long long grid = static_cast<long long>(prm.bucketCount) * prm.split;
+	if (grid <= 0) return cudaSuccess;
+	if (grid > 2147483647LL || prm.split < 1) return cudaErrorInvalidConfiguration;
+	cudaError_t err = cudaFuncSetAttribute(simplsKspaceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (err != cudaSuccess) return err;
+	simplsKspaceKernel<<<static_cast<unsigned>(grid), kKThreads, static_cast<size_t>(bytes), stream>>>(prm);
+	if (ctas) *ctas += grid;
+	return cudaGetLastError();
+}
+
+} // namespace gsb

@@ -195,6 +195,9 @@ __device__ __forceinline__ void gemmLoadings(const double* __restrict__ Zs, cons
 	}
 }
 
+// barrier of one 8-fit tile (256 threads) of a decoupled 16-fit CTA; id 1 or 2
+__device__ __forceinline__ void tileSync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
 template <int CS>
 __device__ __forceinline__ void ctaOrClusterSync() {
 	if (CS == 1) __syncthreads();
@@ -378,22 +381,28 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsScoreKernel(const XParams pr
 	cpAsyncWaitAllX();
 	ctaOrClusterSync<CS>(); // also: the partner CTAs run before any distributed-shared-memory access
 	GSB_XSTAMP(); // 1: gather done
+	// a 16-fit single CTA may run its two 8-fit tiles independently from here on (they share only the read-only Zs):
+	// one tile's warp-local FP64 phases then overlap the other's tensor-core products
+	const bool decoupled = (NF == 16 && CS == 1) && prm.desync > 0;
+#define GSB_PHASE_SYNC() do { if (decoupled) tileSync(1 + half16); else __syncthreads(); } while (0)
+	if (decoupled && prm.desync >= 2 && half16 == 1) asm volatile("bar.sync 3, 512;" ::: "memory"); // start half a component late
 	gemmLoadings<KS>(Zs, tcH, WvH, TBwH, klp, nr, ldz, lds, ldt, w8, lane);
-	__syncthreads();
+	GSB_PHASE_SYNC();
 #pragma unroll
 	for (int u = 0; u < CU; ++u) {
 		const int i = lane + 32 * u;
 		if (i < klp) Sx[f * lds + i] = Wv[f * lds + i] + (KS == 2 ? TBwH[fl * lds + i] : 0.0);
 	}
-	__syncthreads();
+	GSB_PHASE_SYNC();
 	GSB_XSTAMP(); // 2: S_0 done
 
 #pragma unroll 1
 	for (int comp = 0; comp < A; ++comp) {
 		// ---- P1: scores of every row --------------------------------------------------------------------------
 		gemmScores<KS>(Zs, SxH, TAH, TBsH, klp, nr, ldz, lds, ldt, w8, lane);
-		ctaOrClusterSync<CS>();
+		if (CS == 1) { GSB_PHASE_SYNC(); } else ctaOrClusterSync<CS>();
 		GSB_XSTAMP();
+		if (decoupled && prm.desync == 2 && comp == 0 && half16 == 0) asm volatile("bar.arrive 3, 512;" ::: "memory");
 
 		// ---- P2: centre, normalise, predict the held-out rows -------------------------------------------------
 		bool under = false;
@@ -487,12 +496,13 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsScoreKernel(const XParams pr
 			}
 		}
 
-		__syncthreads();
+		GSB_PHASE_SYNC();
 		GSB_XSTAMP();
+		if (decoupled && prm.desync == 3 && comp == 0 && half16 == 0) asm volatile("bar.arrive 3, 512;" ::: "memory");
 
 		// ---- P3: loadings v = X't --------------------------------------------------------------------------------
 		gemmLoadings<KS>(Zs, tcH, WvH, TBwH, klp, nr, ldz, lds, ldt, w8, lane);
-		__syncthreads();
+		GSB_PHASE_SYNC();
 		GSB_XSTAMP();
 
 		// ---- P4: orthogonalise against the stored loadings, deflate S ------------------------------------------
@@ -568,10 +578,12 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsScoreKernel(const XParams pr
 				}
 			}
 		}
-		__syncthreads();
+		GSB_PHASE_SYNC();
 		GSB_XSTAMP();
 	}
+	if (decoupled && prm.desync >= 2 && half16 == 0 && A == 0) asm volatile("bar.arrive 3, 512;" ::: "memory");
 #undef GSB_XSTAMP
+#undef GSB_PHASE_SYNC
 	if (CS > 1) cg::this_cluster().sync(); // no CTA exits while a partner may still read its shared memory
 }
 

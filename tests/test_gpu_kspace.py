@@ -1,0 +1,129 @@
+"""K1k, the kernel-space tensor-core kernel (gaselect_b200/csrc/simpls_kspace.cu): SIMPLS carried by vectors over the
+rows with one K = Z Z' per chromosome.  Checked against the CPU oracle for every subset size (1 column to several
+chunks of columns), every split of a chromosome's fits over CTAs, nested and single CV, segments that do not tile,
+underflow; and against the per-fit kernel.  Reference semantics: PLSEvaluator::evaluate (src/PLSEvaluator.cpp:71-91,
+228-343) over PLSSimpls::fit (src/PLSSimpls.cpp:106-166)."""
+import numpy as np
+import pytest
+
+from gaselect_b200 import synth
+from helpers import rel_err
+from test_gpu_scores import forced
+
+REL_TOL = 1e-8  # north_star: "within relative 1e-8 in FP64"
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(numReplications=2, maxNComp=6, innerSegments=3, outerSegments=4)  # 60 rows, 20 distinct fits: 3 passes of 8
+
+
+@pytest.fixture(scope="module")
+def case(oracle_lib):
+    X, y = synth.nir_spectra(60, 260, seed=41)
+    sv = oracle_lib.make_seedvec(77)
+    subsets = synth.random_subsets(260, 40, 1, 230, seed=3) + [np.arange(200, dtype=np.uint32), np.array([7], dtype=np.uint32)]
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **KW).evaluate(subsets, threads=4)
+    return X, y, sv, subsets, want, wstatus
+
+
+@pytest.mark.parametrize("split", [1, 2, 3])
+def test_every_subset_size_and_split_against_the_oracle(engine, case, split):
+    """GSB_KSPACE_MINK=0 sends every subset (1..230 columns: up to four column chunks of K) through K1k."""
+    from gaselect_b200 import evaluators as E
+    X, y, sv, subsets, want, wstatus = case
+    with forced(GSB_KSPACE_MINK="0", GSB_KSPACE_SPLIT=str(split), GSB_NO_KSPACE=None):
+        with E.PLSEvaluator(X, y, sv, **KW) as ev:
+            fit, status = ev.evaluate_population(subsets)
+            assert ev.timing()["fit_ctas"] == len(subsets) * split  # one launch, `split` CTAs per chromosome
+            assert (status == wstatus).all()
+            assert rel_err(fit[wstatus == 0], want[wstatus == 0]).max() <= REL_TOL
+            again, _ = ev.evaluate_population(subsets)
+            assert (again == fit).all()  # fixed summation order: bitwise reproducible
+
+
+def test_default_policy_matches_the_per_fit_kernel(engine, case):
+    from gaselect_b200 import evaluators as E
+    X, y, sv, subsets, want, wstatus = case
+    with forced(GSB_KSPACE_MINK=None, GSB_KSPACE_SPLIT=None, GSB_NO_KSPACE=None, GSB_SCORE_CFG=None, GSB_NO_SCORES=None):
+        with E.PLSEvaluator(X, y, sv, **KW) as ev:
+            f1, s1 = ev.evaluate_population(subsets)
+            ctas1 = ev.timing()["fit_ctas"]
+    with forced(GSB_NO_KSPACE="1", GSB_NO_SCORES="1"):
+        with E.PLSEvaluator(X, y, sv, **KW) as ev:
+            f0, s0 = ev.evaluate_population(subsets)
+            ctas0 = ev.timing()["fit_ctas"]
+            nfits = ev.info()["distinct_fits"]
+    assert ctas0 == len(subsets) * nfits and ctas1 < ctas0      # different kernels ran
+    assert (s0 == s1).all() and rel_err(f1, f0).max() <= 1e-9  # same arithmetic up to rounding
+
+
+def test_any_segmentation(engine, oracle_lib):
+    """K1k needs no structure in the segments: 62 rows in 4 ragged outer segments, 150 rows in 3 (50-row blocks),
+    single CV (outerSegments=1: a test set drawn once per replication), 160 rows (the largest K).  190 rows do not
+    fit: the engine stays on the other kernels."""
+    from gaselect_b200 import evaluators as E
+    for n, kw, kspace in [(62, dict(numReplications=2, maxNComp=4, innerSegments=3, outerSegments=4), True),
+                          (150, dict(numReplications=2, maxNComp=5, innerSegments=2, outerSegments=3), True),
+                          (100, dict(numReplications=3, maxNComp=10, innerSegments=5, outerSegments=1, testSetSize=0.25), True),
+                          (160, dict(numReplications=1, maxNComp=10, innerSegments=4, outerSegments=5), True),
+                          (157, dict(numReplications=1, maxNComp=7, innerSegments=3, outerSegments=2), True),
+                          (190, dict(numReplications=1, maxNComp=4, innerSegments=4, outerSegments=5), False)]:
+        X, y = synth.nir_spectra(n, 90, seed=n)
+        sv = oracle_lib.make_seedvec(n)
+        subsets = synth.random_subsets(90, 24, 1, 80, seed=n + 1)
+        want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=4)
+        with forced(GSB_KSPACE_MINK="0", GSB_KSPACE_SPLIT="1", GSB_NO_KSPACE=None):
+            with E.PLSEvaluator(X, y, sv, **kw) as ev:
+                fit, status = ev.evaluate_population(subsets)
+                ran = ev.timing()["fit_ctas"] == len(subsets)
+        assert (status == wstatus).all() and rel_err(fit[wstatus == 0], want[wstatus == 0]).max() <= REL_TOL, (n, kw)
+        assert ran == kspace, (n, kw)
+
+
+def test_more_components_than_the_kernel_holds_fall_back(engine, oracle_lib):
+    """maxNComp > 10: the nine stored vectors per fit live in registers, so K1k declines."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(60, 90, seed=5)
+    sv = oracle_lib.make_seedvec(5)
+    kw = dict(numReplications=1, maxNComp=14, innerSegments=3, outerSegments=4)
+    subsets = synth.random_subsets(90, 12, 20, 80, seed=6)
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=4)
+    with forced(GSB_KSPACE_MINK="0", GSB_KSPACE_SPLIT="1", GSB_NO_KSPACE=None):
+        with E.PLSEvaluator(X, y, sv, **kw) as ev:
+            fit, status = ev.evaluate_population(subsets)
+            assert ev.timing()["fit_ctas"] > len(subsets)
+    assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL
+
+
+def test_underflow_and_tiny_subsets(engine, oracle_lib):
+    """Constant response: X'y vanishes and the reference throws (src/PLSSimpls.cpp:141-143) -> status 2 for every
+    chromosome; single-column subsets run one component."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(60, 50, seed=8)
+    sv = oracle_lib.make_seedvec(9)
+    subsets = [[1, 2, 3], [5], list(range(0, 50, 2)), list(range(50))]
+    with forced(GSB_KSPACE_MINK="0", GSB_KSPACE_SPLIT="1", GSB_NO_KSPACE=None):
+        with E.PLSEvaluator(X, np.full(60, 1.5), sv, **KW) as ev:
+            _, status = ev.evaluate_population(subsets)
+            assert ev.timing()["fit_ctas"] == len(subsets)
+        assert status.tolist() == [2, 2, 2, 2]
+        want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **KW).evaluate(subsets)
+        with E.PLSEvaluator(X, y, sv, **KW) as ev:
+            fit, status = ev.evaluate_population(subsets)
+        assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL
+
+
+def test_config3_shape_with_wide_subsets(engine, oracle_lib):
+    """BASELINE config 3 (n=150, p=1000, 10 x 5/4 CV, <= 10 components): 150 distinct fits = 19 passes; subsets up to
+    400 columns (three chunks of 152 columns in the K build)."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(150, 1000, seed=777)
+    sv = oracle_lib.make_seedvec(123)
+    kw = dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)
+    subsets = synth.random_subsets(1000, 10, 57, 400, seed=12) + synth.random_subsets(1000, 4, 2, 12, seed=13)
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=8)
+    for env in (dict(GSB_KSPACE_MINK="0", GSB_KSPACE_SPLIT=None), dict(GSB_KSPACE_MINK=None, GSB_KSPACE_SPLIT="5")):
+        with forced(GSB_NO_KSPACE=None, **env):
+            with E.PLSEvaluator(X, y, sv, **kw) as ev:
+                fit, status = ev.evaluate_population(subsets)
+        assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL

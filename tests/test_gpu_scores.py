@@ -37,6 +37,13 @@ class forced:
                 os.environ[k] = v
 
 
+@pytest.fixture(autouse=True)
+def _no_kspace():
+    """These tests are about K1x: keep K1k (tests/test_gpu_kspace.py), which would otherwise take the larger subsets."""
+    with forced(GSB_NO_KSPACE="1"):
+        yield
+
+
 KW = dict(numReplications=2, maxNComp=6, innerSegments=3, outerSegments=4)  # 60 rows: 4 atoms of 15, 10 fits / replication
 
 
