@@ -1151,7 +1151,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			// K1k takes every size class above kspaceMinK in ONE launch (its cost per fit does not depend on the subset
 			// size; below, the per-fit and score-space kernels are cheaper): the classes are contiguous in dBucket
 			const bool kspaceOn = e->kspaceFits > 0 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit) && !std::getenv("GSB_NO_KSPACE");
-			int kspaceMinK = 56, kspaceSplit = 0;
+			int kspaceMinK = 40, kspaceSplit = 0;
 			if (const char* mk = std::getenv("GSB_KSPACE_MINK")) kspaceMinK = std::atoi(mk);
 			if (const char* sp = std::getenv("GSB_KSPACE_SPLIT")) kspaceSplit = std::atoi(sp);
 			std::vector<char> useKspace(e->buckets.size(), 0);

@@ -137,9 +137,6 @@ struct KCtx {
 	const double* tbW; // this warp's row of TB
 	int n8, ldk, warp, lane, A, chrom;
 	const KFitDesc* fd;
-	const KTaskDesc* tdA;
-	const KTaskDesc* tdB;
-	double rrowsA, rrowsB;
 	bool tracing;
 };
 
@@ -147,22 +144,33 @@ struct KCtx {
 struct KFitState {
 	double yc[kKNS], tt[kKNS], pred[kKNS];
 	double U[kKA - 1][kKNS];
-	uint32_t trainBits, rowBits;
+	uint32_t trainBits, rowBits;  // bit u: the lane's row of slot u is a training row / exists in shared memory
+	uint32_t taskBitsA, taskBitsB; // bit u: the lane's row of slot u belongs to the fit's first / second prediction task
+	double* outA;                 // where the task's statistic of component 0 goes (kind 0: mse, kind 1: sum e, sum e^2)
+	double* outB;
+	int kindA, kindB;             // -1: no such task
+	double rrA, rrB;              // 1 / rows of the task
 	double rntr, syc;
 	bool under;
 };
 
-#define GSB_KSTAMP() do { if (cx.tracing && stamp < 64) cx.prm->trace[stamp++] = clock64(); } while (0)
+// statistic of one prediction task for component COMP from its residual sums (src/PLSEvaluator.cpp:266-268, 323-325)
+__device__ __forceinline__ void storeTaskSum(int kind, double* out, double rr, int which, double tot, int comp) {
+	if (kind == 0) {
+		if (which) out[comp] = tot * rr; // mean squared error of prediction for this fold
+	} else if (kind == 1) {
+		out[2 * comp + which] = tot;     // sum e, sum e^2 of the pooled outer residuals
+	}
+}
 
-// component COMP (0-based) of the 8 fits of a pass; the barriers are uniform (A is a property of the chromosome)
-template <int COMP>
-__device__ __forceinline__ void kspaceComponent(KFitState& fs, const KCtx& cx, int& stamp) {
-	if (COMP >= cx.A) return;
+// First half of component `comp` (0-based), the same code for every component: centre and normalise the scores,
+// predict the held-out rows, hand tc to the product, residual sums of the fit's first two tasks (left in st[] for the
+// second half's reduction when one follows, else reduced and stored here).
+__device__ __forceinline__ void kspaceScores(KFitState& fs, const KCtx& cx, int comp, bool more, double (&tc)[kKNS], double (&st)[4]) {
 	const KParams& prm = *cx.prm;
 	const int lane = cx.lane;
 	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 	// ---- centre, normalise, predict the held-out rows ----------------------------------------------------------
-	double tc[kKNS];
 	{
 		double sv[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -175,7 +183,6 @@ __device__ __forceinline__ void kspaceComponent(KFitState& fs, const KCtx& cx, i
 		}
 		const double tot = warpSumNK<4>(sv, lane); // lane L: value L / 8
 		const double s1 = __shfl_sync(0xffffffffu, tot, 0), s2 = __shfl_sync(0xffffffffu, tot, 8), s3 = __shfl_sync(0xffffffffu, tot, 16);
-		if (COMP == 1) GSB_KSTAMP();
 		// centring of the scores = column-centring of X (:28-49): |t - mu|^2 = sum t^2 - n mu^2, y_c'(t - mu)
 		const double mu = s1 * fs.rntr;
 		const double a2 = fma(-s1, mu, s2);
@@ -185,7 +192,6 @@ __device__ __forceinline__ void kspaceComponent(KFitState& fs, const KCtx& cx, i
 		const double q = b2 * rtn;
 		const double fac = fs.under ? nanv : q * rtn; // coefficient increment is S q / tn (:152-156)
 		const double scale = fs.under ? nanv : rtn;
-		if (COMP == 1 && cx.tracing && stamp < 64 && scale != 0.0) cx.prm->trace[stamp++] = clock64();
 #pragma unroll
 		for (int u = 0; u < kKNS; ++u) {
 			const double d = fs.tt[u] - mu;
@@ -193,111 +199,121 @@ __device__ __forceinline__ void kspaceComponent(KFitState& fs, const KCtx& cx, i
 			fs.pred[u] = fma(d, fac, fs.pred[u]); // only the held-out rows are read
 		}
 	}
-	const bool more = COMP + 1 < cx.A;
 	if (more) {
 #pragma unroll
 		for (int u = 0; u < kKNS; ++u) {
 			if ((fs.rowBits >> u) & 1u) cx.taW[32 * u + lane] = tc[u];
 		}
 	}
-	if (COMP == 1) GSB_KSTAMP();
-	// residual sums of the prediction tasks, two tasks per reduction
+	// residual sums of the fit's (first two) prediction tasks: reduced together with the dot products below
+#pragma unroll
+	for (int i = 0; i < 4; ++i) st[i] = 0.0;
+#pragma unroll
+	for (int u = 0; u < kKNS; ++u) {
+		const double e = fs.yc[u] - fs.pred[u];
+		const double eA = ((fs.taskBitsA >> u) & 1u) ? e : 0.0;
+		const double eB = ((fs.taskBitsB >> u) & 1u) ? e : 0.0;
+		st[0] += eA;
+		st[1] = fma(eA, eA, st[1]);
+		st[2] += eB;
+		st[3] = fma(eB, eB, st[3]);
+	}
+	// more than two tasks on one fit: not in a nested CV, but legal
 	const KFitDesc& fd = *cx.fd;
-	for (int tk = 0; tk < fd.ntasks; tk += 2) {
-		KTaskDesc td0 = *cx.tdA, td1 = *cx.tdB;
-		if (tk > 0) { // more than two tasks on one fit: not in a nested CV, but legal
-			td0 = prm.ktasks[fd.taskBegin + tk];
-			if (tk + 1 < fd.ntasks) td1 = prm.ktasks[fd.taskBegin + tk + 1];
-		}
-		const bool two = tk + 1 < fd.ntasks;
-		double st[4] = {0.0, 0.0, 0.0, 0.0};
+	for (int tk = 2; tk < fd.ntasks; ++tk) {
+		const KTaskDesc td = prm.ktasks[fd.taskBegin + tk];
+		double sx[2] = {0.0, 0.0};
 #pragma unroll
 		for (int u = 0; u < kKNS; ++u) {
-			const double e = fs.yc[u] - fs.pred[u];
-			if ((td0.rows[u] >> lane) & 1u) { st[0] += e; st[1] = fma(e, e, st[1]); }
-			if (two && ((td1.rows[u] >> lane) & 1u)) { st[2] += e; st[3] = fma(e, e, st[3]); }
+			const double e = ((td.rows[u] >> lane) & 1u) ? fs.yc[u] - fs.pred[u] : 0.0;
+			sx[0] += e;
+			sx[1] = fma(e, e, sx[1]);
 		}
+		const double tot = warpSumNK<2>(sx, lane); // lane L: value L / 16
+		if ((lane & 15) == 0) {
+			double* out = td.kind == 0 ? prm.mse + (static_cast<size_t>(cx.chrom) * prm.innerDests + td.dest) * prm.maxNComp
+			                           : prm.ostat + (static_cast<size_t>(cx.chrom) * prm.outerDests + td.dest) * prm.maxNComp * 2;
+			storeTaskSum(td.kind, out, 1.0 / static_cast<double>(td.nrows), lane >> 4, tot, comp);
+		}
+	}
+	if (!more) {
 		const double tot = warpSumNK<4>(st, lane); // lane L: value L / 8
 		if ((lane & 7) == 0) {
 			const int vi = lane >> 3;
-			const bool second = vi >= 2;
-			if (!second || two) {
-				const int kind = second ? td1.kind : td0.kind, dest = second ? td1.dest : td0.dest;
-				if (kind == 0) {
-					// mean squared error of prediction for this fold (src/PLSEvaluator.cpp:266-268)
-					const double rr = (tk > 0) ? 1.0 / static_cast<double>(second ? td1.nrows : td0.nrows) : (second ? cx.rrowsB : cx.rrowsA);
-					if (vi & 1) prm.mse[(static_cast<size_t>(cx.chrom) * prm.innerDests + dest) * prm.maxNComp + COMP] = tot * rr;
-				} else {
-					prm.ostat[((static_cast<size_t>(cx.chrom) * prm.outerDests + dest) * prm.maxNComp + COMP) * 2 + (vi & 1)] = tot;
-				}
-			}
+			storeTaskSum(vi < 2 ? fs.kindA : fs.kindB, vi < 2 ? fs.outA : fs.outB, vi < 2 ? fs.rrA : fs.rrB, vi & 1, tot, comp);
 		}
 	}
-	if (!more) return;
-	if (COMP == 1) GSB_KSTAMP();
-	// ---- w = K tc: the loading v = X't seen from the rows (:145-147) -------------------------------------------
-	__syncthreads();
-	GSB_KSTAMP();
-	kernelProduct(cx.Km, cx.TA, cx.TB, cx.n8, cx.ldk, cx.warp, lane);
-	__syncthreads();
-	GSB_KSTAMP();
-	// ---- orthogonalise against the stored loadings, deflate (:57-63, :70-88, :160) -----------------------------
+}
+
+// Second half of component `comp` in [JLO, JHI], after w = K tc: orthogonalise against the `comp` stored vectors,
+// deflate the scores, store the new vector (:57-63, :70-88, :160).  The stored vectors live in registers, so their
+// index must be a compile-time constant: an instance covers the components JLO..JHI with the terms j >= comp
+// predicated off.  The first half of a component is deliberately NOT part of these instances: unrolling whole
+// components made 230 KB of code, an instruction-cache hit rate of 63 % and "no instruction" the second largest stall.
+template <int JLO, int JHI>
+__device__ __forceinline__ void kspaceDeflate(KFitState& fs, const KCtx& cx, int comp, const double (&tc)[kKNS], const double (&st)[4]) {
+	const int lane = cx.lane;
+	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 	double w[kKNS];
 #pragma unroll
 	for (int u = 0; u < kKNS; ++u) w[u] = ((fs.rowBits >> u) & 1u) ? cx.tbW[32 * u + lane] : 0.0;
-	constexpr int NV = (COMP + 2 <= 2) ? 2 : (COMP + 2 <= 4) ? 4 : (COMP + 2 <= 8) ? 8 : 16;
+	// one reduction for: V_j'v (JHI slots), v'S, |X'tc|^2, and the four residual sums
+	constexpr int NV = (JHI + 6 <= 8) ? 8 : 16;
 	double sv[NV];
 #pragma unroll
 	for (int j = 0; j < NV; ++j) sv[j] = 0.0;
 #pragma unroll
 	for (int u = 0; u < kKNS; ++u) {
 #pragma unroll
-		for (int j = 0; j < COMP; ++j) sv[j] = fma(fs.U[j][u], tc[u], sv[j]); // V_j'v = U_j'tc
-		sv[COMP] = fma(tc[u], fs.tt[u], sv[COMP]);                             // v'S = tc't
-		sv[COMP + 1] = fma(tc[u], w[u], sv[COMP + 1]);                         // |X'tc|^2 = tc'K tc
+		for (int j = 0; j < JHI; ++j) {
+			if (j < JLO || j < comp) sv[j] = fma(fs.U[j][u], tc[u], sv[j]); // V_j'v = U_j'tc
+		}
+		sv[JHI] = fma(tc[u], fs.tt[u], sv[JHI]);     // v'S = tc't
+		sv[JHI + 1] = fma(tc[u], w[u], sv[JHI + 1]); // |X'tc|^2 = tc'K tc
 	}
+#pragma unroll
+	for (int i = 0; i < 4; ++i) sv[JHI + 2 + i] = st[i];
 	const double tot = warpSumNK<NV>(sv, lane);
 	constexpr int LP = 32 / NV; // lanes per value
-	double cj[kKA];
-	double vv = __shfl_sync(0xffffffffu, tot, (COMP + 1) * LP);
-	const double vs = __shfl_sync(0xffffffffu, tot, COMP * LP);
-#pragma unroll
-	for (int j = 0; j < COMP; ++j) {
-		cj[j] = __shfl_sync(0xffffffffu, tot, j * LP);
-		vv = fma(-cj[j], cj[j], vv); // |v - sum_j (V_j'v) V_j|^2 for orthonormal V_j
+	{
+		const int vi = lane / LP - (JHI + 2);
+		if ((lane % LP) == 0 && vi >= 0 && vi < 4) {
+			storeTaskSum(vi < 2 ? fs.kindA : fs.kindB, vi < 2 ? fs.outA : fs.outB, vi < 2 ? fs.rrA : fs.rrB, vi & 1, tot, comp);
+		}
 	}
-	const double dd = vs / vv;
+	double cj[kKA];
+	double vv = __shfl_sync(0xffffffffu, tot, (JHI + 1) * LP), vv2 = 0.0;
+	const double vs = __shfl_sync(0xffffffffu, tot, JHI * LP);
+#pragma unroll
+	for (int j = 0; j < JHI; ++j) {
+		cj[j] = __shfl_sync(0xffffffffu, tot, j * LP); // exactly 0 for j >= comp
+		// |v - sum_j (V_j'v) V_j|^2 for orthonormal V_j (two chains)
+		if (j & 1) vv2 = fma(cj[j], cj[j], vv2);
+		else vv = fma(-cj[j], cj[j], vv);
+	}
+	vv -= vv2;
 	const double rvn = rsqrt(vv);
+	const double dd = vs * rvn * rvn; // v'S / v'v
 #pragma unroll
 	for (int u = 0; u < kKNS; ++u) {
 		// two partial sums: half the dependent chain
 		double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-		for (int j = 0; j < COMP; j += 2) {
-			d0 = fma(fs.U[j][u], cj[j], d0);
-			if (j + 1 < COMP) d1 = fma(fs.U[j + 1][u], cj[j + 1], d1);
+		for (int j = 0; j < JHI; j += 2) {
+			if (j < JLO || j < comp) d0 = fma(fs.U[j][u], cj[j], d0);
+			if (j + 1 < JHI && (j + 1 < JLO || j + 1 < comp)) d1 = fma(fs.U[j + 1][u], cj[j + 1], d1);
 		}
 		const double uu = w[u] - (d0 + d1); // K h for the orthogonalised loading v = Z'h
 		double tn = fma(-uu, dd, fs.tt[u]);  // Z (S - v v'S / v'v)
 		if (fs.under) tn = nanv;             // the reference throws: poison this and every later component
 		fs.tt[u] = tn;
-		if (COMP < kKA - 1) fs.U[COMP < kKA - 1 ? COMP : 0][u] = uu * rvn;
+		const double un = uu * rvn;
+#pragma unroll
+		for (int j = JLO; j <= JHI; ++j) {
+			if (j == comp) fs.U[j][u] = un;
+		}
 	}
-	GSB_KSTAMP();
 }
-
-template <int COMP>
-struct KSteps {
-	static __device__ __forceinline__ void run(KFitState& fs, const KCtx& cx, int& stamp) {
-		kspaceComponent<COMP>(fs, cx, stamp);
-		KSteps<COMP + 1>::run(fs, cx, stamp);
-	}
-};
-template <>
-struct KSteps<kKA> {
-	static __device__ __forceinline__ void run(KFitState&, const KCtx&, int&) {}
-};
-#undef GSB_KSTAMP
 
 __global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams prm) {
 	extern __shared__ __align__(16) double smem[];
@@ -428,19 +444,32 @@ __global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams
 		for (int u = 0; u < kKNS; ++u) fd.train[u] = 0u;
 		fd.taskBegin = 0; fd.ntasks = 0; fd.ntr = 1;
 		if (fitActive) fd = prm.kfits[fi];
-		KTaskDesc tdA, tdB;
-#pragma unroll
-		for (int u = 0; u < kKNS; ++u) { tdA.rows[u] = 0u; tdB.rows[u] = 0u; }
-		tdA.kind = -1; tdA.dest = 0; tdA.nrows = 1;
-		tdB.kind = -1; tdB.dest = 0; tdB.nrows = 1;
-		if (fd.ntasks > 0) tdA = prm.ktasks[fd.taskBegin];
-		if (fd.ntasks > 1) tdB = prm.ktasks[fd.taskBegin + 1];
-		const double rrowsA = 1.0 / static_cast<double>(tdA.nrows), rrowsB = 1.0 / static_cast<double>(tdB.nrows);
-
 		KFitState fs;
 		fs.trainBits = 0u; // bit u: the lane's row of slot u is a training row of the fit
 		fs.rowBits = 0u;   // bit u: the lane's row of slot u exists in shared memory
 		fs.under = false;
+		fs.taskBitsA = 0u; fs.taskBitsB = 0u;
+		fs.kindA = -1; fs.kindB = -1;
+		fs.outA = nullptr; fs.outB = nullptr;
+		fs.rrA = 1.0; fs.rrB = 1.0;
+		if (fd.ntasks > 0) {
+			const KTaskDesc td = prm.ktasks[fd.taskBegin];
+#pragma unroll
+			for (int u = 0; u < kKNS; ++u) if ((td.rows[u] >> lane) & 1u) fs.taskBitsA |= 1u << u;
+			fs.kindA = td.kind;
+			fs.rrA = 1.0 / static_cast<double>(td.nrows);
+			fs.outA = td.kind == 0 ? prm.mse + (static_cast<size_t>(chrom) * prm.innerDests + td.dest) * prm.maxNComp
+			                       : prm.ostat + (static_cast<size_t>(chrom) * prm.outerDests + td.dest) * prm.maxNComp * 2;
+		}
+		if (fd.ntasks > 1) {
+			const KTaskDesc td = prm.ktasks[fd.taskBegin + 1];
+#pragma unroll
+			for (int u = 0; u < kKNS; ++u) if ((td.rows[u] >> lane) & 1u) fs.taskBitsB |= 1u << u;
+			fs.kindB = td.kind;
+			fs.rrB = 1.0 / static_cast<double>(td.nrows);
+			fs.outB = td.kind == 0 ? prm.mse + (static_cast<size_t>(chrom) * prm.innerDests + td.dest) * prm.maxNComp
+			                       : prm.ostat + (static_cast<size_t>(chrom) * prm.outerDests + td.dest) * prm.maxNComp * 2;
+		}
 		{
 			double sy = 0.0;
 #pragma unroll
@@ -479,10 +508,37 @@ __global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams
 		KCtx cx;
 		cx.prm = &prm; cx.Km = Km; cx.TA = TA; cx.TB = TB; cx.taW = taW; cx.tbW = tbW;
 		cx.n8 = n8; cx.ldk = ldk; cx.warp = warp; cx.lane = lane; cx.A = A; cx.chrom = chrom;
-		cx.fd = &fd; cx.tdA = &tdA; cx.tdB = &tdB; cx.rrowsA = rrowsA; cx.rrowsB = rrowsB;
+		cx.fd = &fd;
 		cx.tracing = tracing && pass == part * perPart;
 		if (cx.tracing) GSB_KSTAMP(); // 2: first scores
-		KSteps<0>::run(fs, cx, stamp);
+		// the barriers below are uniform: A is a property of the chromosome
+#pragma unroll 1
+		for (int comp = 0; comp < A; ++comp) {
+			const bool more = comp + 1 < A;
+			double tc[kKNS], st[4];
+			kspaceScores(fs, cx, comp, more, tc, st);
+			if (!more) break;
+			// ---- w = K tc: the loading v = X't seen from the rows (:145-147) ---------------------------------------
+			__syncthreads();
+			if (cx.tracing) GSB_KSTAMP();
+			kernelProduct(Km, TA, TB, n8, ldk, warp, lane);
+			__syncthreads();
+			if (cx.tracing) GSB_KSTAMP();
+			// one instance per component (measured: faster than three instances covering 0-2, 3-5, 6-8 with
+			// predicated terms, although each then runs once per pass out of a cold instruction cache)
+			switch (comp) {
+			case 0: kspaceDeflate<0, 0>(fs, cx, comp, tc, st); break;
+			case 1: kspaceDeflate<1, 1>(fs, cx, comp, tc, st); break;
+			case 2: kspaceDeflate<2, 2>(fs, cx, comp, tc, st); break;
+			case 3: kspaceDeflate<3, 3>(fs, cx, comp, tc, st); break;
+			case 4: kspaceDeflate<4, 4>(fs, cx, comp, tc, st); break;
+			case 5: kspaceDeflate<5, 5>(fs, cx, comp, tc, st); break;
+			case 6: kspaceDeflate<6, 6>(fs, cx, comp, tc, st); break;
+			case 7: kspaceDeflate<7, 7>(fs, cx, comp, tc, st); break;
+			default: kspaceDeflate<8, 8>(fs, cx, comp, tc, st); break;
+			}
+			if (cx.tracing) GSB_KSTAMP();
+		}
 	}
 #undef GSB_KSTAMP
 }
