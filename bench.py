@@ -146,7 +146,9 @@ def cpu_leg(w, X, y, subsets, budget_s):
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the K1 launches of ONE step from the committed
 # ncu --set full capture (profiles/r01_summary.txt); only valid for the default workload
-MEASURED_TRAFFIC = {("cfg3", 500): 2.025e8}
+MEASURED_TRAFFIC = {("cfg3", 500): 4.499e8}
+# FP64 tensor-core peak: 148 SMs x 4 sub-partitions x 256 FMA per DMMA.8x8x4 / 16 cycles x 1.965 GHz x 2
+DMMA_PEAK_TFLOPS = 37.2
 
 
 def main():
@@ -272,12 +274,14 @@ def main():
     launches = ev.timing()["kernel_launches"] * args.steps
     # K1 timed live with the engine's CUDA events on the same stream, per step
     k1_ms, k2_ms = [], []
+    tensor_gflop = 0.0
     for _ in range(args.steps):
         flush_buf.zero_()
         ev.evaluate_resident()
         t = ev.timing()
         k1_ms.append(t["fit_kernel_ms"])
         k2_ms.append(t["reduce_kernel_ms"])
+        tensor_gflop = t.get("fit_tensor_gflop", 0.0)
     clocks = sampler.stop() if rank == 0 else None
     ev.download_results(fitness, status)
     assert (status == 0).all() and np.isfinite(fitness).all() and (fitness < 0).all()
@@ -319,7 +323,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, l2="explicit flush: a 256 MB buffer (2 x L2) is overwritten before every step, inside the "
-                                      "timed region (the path's own inputs, 12 MB of row-permuted copies of Z, would stay in L2)",
+                                      "timed region (the path's own inputs, the 1.2 MB of centred data, would stay in L2)",
                            fits_per_evaluation=info["fits_per_evaluation"], distinct_fits=info["distinct_fits"],
                            setup_ms=info["setup_ms"], gram_dmma_ms=info["gram_dmma_ms"],
                            gram_tflops=info["gram_flops"] / max(info["gram_dmma_ms"], 1e-9) / 1e9),
@@ -327,15 +331,23 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "K1 = simplsScoreKernel (score-space FP64 DMMA; simplsFitFast beyond its capacity), all subset-size classes of a step",
+            "roofline": {"bound": "hbm", "kernel": "K1 = simplsKspaceKernel (kernel-space SIMPLS on the FP64 tensor cores; subsets of more than 40 "
+                                                   "columns) + simplsFitFast (per-fit Gram-space kernel; the rest), all launches of a step",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "algorithmic_bytes_per_step": algo_bytes, "k1_ms_per_step": k1,
                          "k2_ms_per_step": float(np.mean(k2_ms)),
                          "traffic": MEASURED_TRAFFIC.get((args.workload, w["pop"])),
                          "traffic_source": "profiles/r01_summary.txt (ncu --set full, sum over the K1 launches of one step)",
-                         "note": "K1 works out of shared memory and L2 (DRAM traffic far below the algorithmic bytes of the Gram "
-                                 "formulation); its binding resource is the FP64 tensor pipe, see profiles/README.md"},
+                         "note": "achieved = SURVEY 8(d)'s algorithmic bytes (the logical inputs of every fit in the Gram formulation) / K1 "
+                                 "time; the kernel-space kernel does not move those bytes: it builds one K = Z Z' per chromosome in shared "
+                                 "memory (DRAM traffic: see traffic) and is bound by the FP64 tensor pipe, see fp64_tensor",
+                         "fp64_tensor": {"bound": "tensor", "achieved": tensor_gflop / max(k1, 1e-9), "peak": DMMA_PEAK_TFLOPS,
+                                         "unit": "TFLOP/s", "frac": tensor_gflop / max(k1, 1e-9) / DMMA_PEAK_TFLOPS,
+                                         "gflop_per_step": tensor_gflop,
+                                         "peak_source": "measured on B200 with profiles/micro/dmma_probe.cu: one DMMA.8x8x4 per 16 cycles "
+                                                        "per SM sub-partition at 1965 MHz (MEASURED_PEAKS.json has no FP64 figure)",
+                                         "note": "DMMA.8x8x4 issued by the kernel-space kernel x 512 FLOP over the time of ALL K1 launches"}},
         }
         if not args.no_cpu and world == 1:
             cb, _, _ = cpu_leg(w, X, y, subsets, args.cpu_seconds)

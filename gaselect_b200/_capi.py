@@ -46,6 +46,7 @@ class Timing(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_double), ("fit_kernel_ms", C.c_double), ("reduce_kernel_ms", C.c_double),
         ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("fit_ctas", C.c_int64), ("kernel_launches", C.c_int32),
+        ("reserved", C.c_int32), ("fit_tensor_gflop", C.c_double),
     ]
 
     def as_dict(self):

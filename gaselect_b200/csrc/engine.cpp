@@ -1089,6 +1089,7 @@ namespace {
 
 // K1 per subset-size class, then K2 (or K3 for the LM evaluator); events ev[2..4] bracket them
 void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
+		e->timing.fit_tensor_gflop = 0.0;
 		GSB_CUDA(cudaEventRecord(e->ev[2], e->stream));
 		if (e->cfg.evaluator == GSB_EVAL_LM) {
 			gsb::launchMarkEmpty(e->dOffsets.ptr, e->npop, e->dFitness.ptr, e->dStatus.ptr, e->stream);
@@ -1216,12 +1217,13 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				kp.bucketCount = 0;
 				for (size_t b = kspaceFirst; b < e->buckets.size(); ++b) kp.bucketCount += e->buckets[b].count;
 				kp.nfits = e->kspaceFits;
-				// CTAs per chromosome: enough CTAs for ~6 waves over the SMs, each still amortising its own K over >= 3 passes
+				// CTAs per chromosome: every CTA builds its own K (about one pass worth of time), so split only until there
+				// are two CTAs per SM (measured at 500 chromosomes: 1 CTA per chromosome 2.17 ms, 3 per chromosome 2.23 ms)
 				const int passes = (e->kspaceFits + 7) / 8;
 				int split = kspaceSplit;
 				if (split <= 0) {
 					split = 1;
-					while (split < 8 && static_cast<long long>(kp.bucketCount) * split < 6LL * e->smCount && (passes + split) / (split + 1) >= 3) ++split;
+					while (split < 8 && static_cast<long long>(kp.bucketCount) * split < 2LL * e->smCount && (passes + split) / (split + 1) >= 3) ++split;
 				}
 				kp.split = std::max(1, std::min(split, passes));
 				kp.n = e->n;
@@ -1236,6 +1238,17 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				kp.trace = e->traceBuf.ptr;
 				GSB_CUDA(gsb::launchKspaceKernel(kp, launchStream, &ctas));
 				++launches;
+				{ // tensor-core work of this launch: DMMA.8x8x4 = 512 FLOP
+					const double nt = kp.n8 / 8, steps = kp.n8 / 4, nb = (kp.n8 / 8 + 1) / 2;
+					double dmma = 0.0;
+					for (int i = 0; i < kp.bucketCount; ++i) {
+						const int c = e->hBucket.ptr[e->buckets[kspaceFirst].begin + i];
+						const int k = static_cast<int>(e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c]);
+						dmma += static_cast<double>(passes) * std::min(e->tableA, k) * nt * steps;               // products
+						dmma += static_cast<double>(kp.split) * (nb * (nb + 1) / 2) * 4.0 * ((k + 3) / 4);        // K = Z Z'
+					}
+					e->timing.fit_tensor_gflop = dmma * 512.0 * 1e-9;
+				}
 			}
 			for (size_t bi = e->buckets.size(); bi-- > 0; ++slot) {
 				const size_t b = bi;

@@ -25,7 +25,7 @@
 //
 // Numerics: mathematically the reference's SIMPLS; K squares the conditioning like the Gram-space kernel does.
 // tests/test_kspace_model.py holds the numpy model of exactly these recurrences (<= 6e-12 against the reference on
-// the parity data set, the same band as the oracle restatement itself).
+// the parity data set, the same band as two CPU builds of the reference's algorithm that differ in summation order).
 #include "kernels.cuh"
 
 namespace gsb {

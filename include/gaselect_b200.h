@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define GSB_ABI_VERSION 1
+#define GSB_ABI_VERSION 2
 #define GSB_SEED_WORDS 624 /* RNG::SEED_SIZE, src/RNG.h:64 */
 
 typedef struct gsb_engine gsb_engine;
@@ -113,6 +113,9 @@ typedef struct gsb_timing {
 	double total_ms;
 	int64_t fit_ctas;         /* CTAs launched by K1 */
 	int32_t kernel_launches;  /* kernels launched by the call */
+	int32_t reserved;
+	double fit_tensor_gflop;  /* FP64 tensor-core work of K1 (kernel-space kernel): DMMA.8x8x4 issued x 512 FLOP, from
+	                             the launch geometry (passes x products x tiles, plus the K = Z Z' builds) */
 } gsb_timing;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */

@@ -49,7 +49,7 @@ if os.path.exists(rep):
         for r in rows[2:]:
             w.writerow([r[i].replace("void gsb::<unnamed>::", "") for _, i in idx])
     out.append("")
-    out.append("== K1 (simplsScoreKernel / simplsFitFast) per size class, ncu --set full --clock-control none (one generation) ==")
+    out.append("== K1 (simplsKspaceKernel + simplsFitFast per size class), ncu --set full --clock-control none (one generation) ==")
     out.append("%-34s %-10s %-8s %9s %10s %10s %6s %7s %7s %7s %7s %7s %7s" % ("kernel", "block", "grid", "time ms", "dram rd MB", "dram wr MB", "regs", "smem KB", "warps%", "issue%", "fp64%", "lds%", "dmma%"))
     g = dict(idx)
     tot_t = tot_rd = tot_wr = 0.0
