@@ -731,7 +731,7 @@ void prepareDevice(gsb_engine* e) {
 
 	// ---- K1k: per-lane row masks (lane = row mod 32) of every distinct fit and prediction task
 	e->kspaceFits = 0;
-	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && gsb::kspaceKernelFits(n, 1, e->smemLimit) && !std::getenv("GSB_NO_KSPACE")) {
+	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && gsb::kspaceKernelFits(n, 1, e->smemLimit, 8) && !std::getenv("GSB_NO_KSPACE")) {
 		std::vector<gsb::KFitDesc> kf(static_cast<size_t>(nfits));
 		std::vector<gsb::KTaskDesc> kt(plan.tasks.size());
 		for (int f = 0; f < nfits; ++f) {
@@ -1151,7 +1151,15 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			if (const char* fc = std::getenv("GSB_SCORE_CFG")) std::sscanf(fc, "%d,%d,%d", &forcedNf, &forcedCs, &forcedVg);
 			// K1k takes every size class above kspaceMinK in ONE launch (its cost per fit does not depend on the subset
 			// size; below, the per-fit and score-space kernels are cheaper): the classes are contiguous in dBucket
-			const bool kspaceOn = e->kspaceFits > 0 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit) && !std::getenv("GSB_NO_KSPACE");
+			const bool kspaceOn = e->kspaceFits > 0 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit, 8) && !std::getenv("GSB_NO_KSPACE");
+			// 8 fits per pass.  GSB_KSPACE_NF=16: 16 fits per pass (two tensor-core column tiles on every fragment of K, the
+			// fits' stored vectors in tensor memory; needs n <= 152) -- measured no faster (1.28 vs 1.26 ms per 296
+			// chromosomes): the warp-local phases are bound by FP64 / shuffle issue, not by latency, so twice the warps
+			// take twice the time; kept as a tested option
+			int kspaceNf = 8;
+			if (const char* nfv = std::getenv("GSB_KSPACE_NF")) {
+				if (std::atoi(nfv) == 16 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit, 16)) kspaceNf = 16;
+			}
 			int kspaceMinK = 40, kspaceSplit = 0;
 			if (const char* mk = std::getenv("GSB_KSPACE_MINK")) kspaceMinK = std::atoi(mk);
 			if (const char* sp = std::getenv("GSB_KSPACE_SPLIT")) kspaceSplit = std::atoi(sp);
@@ -1219,7 +1227,8 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				kp.nfits = e->kspaceFits;
 				// CTAs per chromosome: every CTA builds its own K (about one pass worth of time), so split only until there
 				// are two CTAs per SM (measured at 500 chromosomes: 1 CTA per chromosome 2.17 ms, 3 per chromosome 2.23 ms)
-				const int passes = (e->kspaceFits + 7) / 8;
+				const int passes = (e->kspaceFits + kspaceNf - 1) / kspaceNf;
+				kp.nf = kspaceNf;
 				int split = kspaceSplit;
 				if (split <= 0) {
 					split = 1;
@@ -1244,7 +1253,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 					for (int i = 0; i < kp.bucketCount; ++i) {
 						const int c = e->hBucket.ptr[e->buckets[kspaceFirst].begin + i];
 						const int k = static_cast<int>(e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c]);
-						dmma += static_cast<double>(passes) * std::min(e->tableA, k) * nt * steps;               // products
+						dmma += static_cast<double>((e->kspaceFits + 7) / 8) * std::min(e->tableA, k) * nt * steps;  // products: column tiles of 8 fits
 						dmma += static_cast<double>(kp.split) * (nb * (nb + 1) / 2) * 4.0 * ((k + 3) / 4);        // K = Z Z'
 					}
 					e->timing.fit_tensor_gflop = dmma * 512.0 * 1e-9;

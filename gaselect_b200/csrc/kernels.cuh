@@ -259,7 +259,8 @@ struct KParams {
 	const int* bucket;
 	int bucketCount;
 	int nfits;
-	int split;  // CTAs per chromosome (each builds K and takes a share of the passes of 8 fits)
+	int split;  // CTAs per chromosome (each builds K and takes a share of the passes of nf fits)
+	int nf;     // fits per pass = warps per CTA: 8, or 16 (stored vectors in tensor memory)
 	int n, n8, ldz, p;
 	int maxNComp;
 	int innerDests;
@@ -296,8 +297,8 @@ cudaError_t launchScoreKernel(const XParams& prm, int kMax, int A, int clusterSi
                               long long* ctas);
 constexpr int kScoreComponents = 10;
 constexpr int kScoreMaxSlots = 6; // 32-row slots: at most 192 rows including the padding of every atom to 32
-int kspaceKernelSharedBytes(int n);
-int kspaceKernelFits(int n, int A, int smemLimit);
+int kspaceKernelSharedBytes(int n, int nf);
+int kspaceKernelFits(int n, int A, int smemLimit, int nf);
 cudaError_t launchKspaceKernel(const KParams& prm, cudaStream_t stream, long long* ctas);
 void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream);
 cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream);

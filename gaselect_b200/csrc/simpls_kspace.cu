@@ -34,9 +34,10 @@ namespace {
 
 constexpr int kKA = kKspaceComponents;
 constexpr int kKNS = kKspaceSlots;   // 32-row slots per lane
-constexpr int kKNF = 8;              // fits per pass = warps per CTA (one tensor-core column tile)
-constexpr int kKThreads = 32 * kKNF;
-constexpr int kKBlocks = 7;          // 2x2-tile blocks of the lower triangle of K per warp: ceil(55 / 8) for 20 tiles
+// NF = fits per pass = warps per CTA: 8 (one tensor-core column tile; the stored vectors of a fit in registers) or 16
+// (two column tiles sharing every fragment of K; 128 registers per thread, the stored vectors in tensor memory)
+constexpr int kKProductWarps = 8;    // warps that issue the products (enough to saturate the FP64 tensor pipe)
+constexpr int kKUStride = 12;        // TMEM columns per stored vector: 5 doubles as .x8 + .x4
 
 __host__ __device__ inline int roundUpK(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -50,6 +51,24 @@ __device__ __forceinline__ void cpAsyncWaitAllK() {
 	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 __device__ __forceinline__ double shflXorK(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// Tensor memory as per-thread scratch (32x32b: thread i of the warp <-> lane 32 (warp % 4) + i, consecutive columns).
+// Measured (profiles/micro/tmem_probe.cu): 415-640 B/clk/SM for loads, 3-5 x shared memory; ~65 cycles ld + wait.
+__device__ __forceinline__ void tmemLd8(uint32_t (&r)[12], uint32_t addr) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+	             : "r"(addr));
+}
+__device__ __forceinline__ void tmemLd4(uint32_t (&r)[12], uint32_t addr) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]) : "r"(addr));
+}
+__device__ __forceinline__ void tmemSt12(uint32_t addr, const uint32_t (&r)[12]) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+	             "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr + 8), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]));
+}
+__device__ __forceinline__ void tmemWaitLd() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmemWaitSt() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 // Sum NV (a power of two <= 16) values per lane over the warp with NV - 1 + log2(32 / NV) shuffles: the lanes halve
 // the value set at every butterfly step.  Afterwards lane L holds the total of value L / (32 / NV).
@@ -77,53 +96,77 @@ struct KCarve {
 	int K, TA, TB, ys, total; // in doubles; the column ids of a chunk alias TA, the staged chunk aliases K
 };
 
-__host__ __device__ inline KCarve kCarve(int n8) {
+__host__ __device__ inline KCarve kCarve(int n8, int nf) {
 	KCarve c;
 	c.ldk = n8 + 4; // = 4 or 12 (mod 16): the 8x4 / 4x8 fragment loads are bank-conflict free
 	int o = 0;
 	c.K = o; o += n8 * c.ldk;
-	c.TA = o; o += kKNF * c.ldk; // [fit][row]: B operand of the product
-	c.TB = o; o += kKNF * c.ldk; // [fit][row]: its result
+	c.TA = o; o += nf * c.ldk; // [fit][row]: B operand of the product
+	c.TB = o; o += nf * c.ldk; // [fit][row]: its result
 	c.ys = o; o += n8;
 	c.total = o;
 	return c;
 }
 
-// dst[fit][row] = sum_r K[row][r] src[fit][r]: 8 warps share the row tiles (tiles ws, ws + 8, ...), NT per warp
-template <int NT>
+// dst[fit][row] = sum_r K[row][r] src[fit][r]: 8 warps share the row tiles (tiles ws, ws + 8, ...), NT per warp; CT
+// column tiles of 8 fits each reuse every fragment of K
+template <int NT, int CT>
 __device__ __forceinline__ void productTiles(const double* __restrict__ kp, const double* __restrict__ bp, int nsteps, int tileStride,
                                              double* __restrict__ dst, int ldk) {
-	double c0[NT], c1[NT];
+	double c0[CT][NT], c1[CT][NT];
 #pragma unroll
-	for (int j = 0; j < NT; ++j) { c0[j] = 0.0; c1[j] = 0.0; }
+	for (int c = 0; c < CT; ++c) {
+#pragma unroll
+		for (int j = 0; j < NT; ++j) { c0[c][j] = 0.0; c1[c][j] = 0.0; }
+	}
 #pragma unroll 2
 	for (int s = 0; s < nsteps; ++s) {
-		const double b = *bp;
+		double b[CT];
 #pragma unroll
-		for (int j = 0; j < NT; ++j) dmma884k(c0[j], c1[j], kp[j * tileStride], b);
+		for (int c = 0; c < CT; ++c) b[c] = bp[c * 8 * ldk];
+#pragma unroll
+		for (int j = 0; j < NT; ++j) {
+			const double a = kp[j * tileStride];
+#pragma unroll
+			for (int c = 0; c < CT; ++c) dmma884k(c0[c][j], c1[c][j], a, b[c]);
+		}
 		kp += 4;
 		bp += 4;
 	}
 #pragma unroll
-	for (int j = 0; j < NT; ++j) {
-		dst[j * 64] = c0[j];
-		dst[j * 64 + ldk] = c1[j];
+	for (int c = 0; c < CT; ++c) {
+#pragma unroll
+		for (int j = 0; j < NT; ++j) {
+			dst[c * 8 * ldk + j * 64] = c0[c][j];
+			dst[c * 8 * ldk + j * 64 + ldk] = c1[c][j];
+		}
 	}
 }
 
+// executed by the first 8 warps of the CTA; ct = column tiles in use (1 or 2)
 __device__ __forceinline__ void kernelProduct(const double* __restrict__ Km, const double* __restrict__ src, double* __restrict__ dst,
-                                              int n8, int ldk, int warp, int lane) {
+                                              int n8, int ldk, int warp, int lane, int ct) {
+	if (warp >= kKProductWarps) return;
 	const int g = lane >> 2, t = lane & 3;
 	const int nt = n8 >> 3, nsteps = n8 >> 2;
-	const int ntiles = (nt - warp + kKNF - 1) / kKNF;
+	const int ntiles = (nt - warp + kKProductWarps - 1) / kKProductWarps;
 	const double* __restrict__ kp = Km + (8 * warp + g) * ldk + t;
 	const double* __restrict__ bp = src + g * ldk + t;
 	double* __restrict__ dp = dst + (2 * t) * ldk + 8 * warp + g;
-	switch (ntiles) {
-	case 1: productTiles<1>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
-	case 2: productTiles<2>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
-	case 3: productTiles<3>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
-	default: break;
+	if (ct == 1) {
+		switch (ntiles) {
+		case 1: productTiles<1, 1>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+		case 2: productTiles<2, 1>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+		case 3: productTiles<3, 1>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+		default: break;
+		}
+	} else {
+		switch (ntiles) {
+		case 1: productTiles<1, 2>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+		case 2: productTiles<2, 2>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+		case 3: productTiles<3, 2>(kp, bp, nsteps, 64 * ldk, dp, ldk); break;
+		default: break;
+		}
 	}
 }
 
@@ -140,10 +183,13 @@ struct KCtx {
 	bool tracing;
 };
 
-// the vectors of one fit, one warp per fit, lane = row (mod 32): all in registers
+// the vectors of one fit, one warp per fit, lane = row (mod 32): all in registers -- but for the nine stored
+// vectors U of the 16-fit configuration, which live in tensor memory (12 columns per vector at tmemU)
+template <int NF>
 struct KFitState {
 	double yc[kKNS], tt[kKNS], pred[kKNS];
-	double U[kKA - 1][kKNS];
+	double U[NF == 8 ? kKA - 1 : 1][kKNS];
+	uint32_t tmemU;
 	uint32_t trainBits, rowBits;  // bit u: the lane's row of slot u is a training row / exists in shared memory
 	uint32_t taskBitsA, taskBitsB; // bit u: the lane's row of slot u belongs to the fit's first / second prediction task
 	double* outA;                 // where the task's statistic of component 0 goes (kind 0: mse, kind 1: sum e, sum e^2)
@@ -166,7 +212,8 @@ __device__ __forceinline__ void storeTaskSum(int kind, double* out, double rr, i
 // First half of component `comp` (0-based), the same code for every component: centre and normalise the scores,
 // predict the held-out rows, hand tc to the product, residual sums of the fit's first two tasks (left in st[] for the
 // second half's reduction when one follows, else reduced and stored here).
-__device__ __forceinline__ void kspaceScores(KFitState& fs, const KCtx& cx, int comp, bool more, double (&tc)[kKNS], double (&st)[4]) {
+template <int NF>
+__device__ __forceinline__ void kspaceScores(KFitState<NF>& fs, const KCtx& cx, int comp, bool more, double (&tc)[kKNS], double (&st)[4]) {
 	const KParams& prm = *cx.prm;
 	const int lane = cx.lane;
 	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
@@ -250,8 +297,8 @@ __device__ __forceinline__ void kspaceScores(KFitState& fs, const KCtx& cx, int 
 // index must be a compile-time constant: an instance covers the components JLO..JHI with the terms j >= comp
 // predicated off.  The first half of a component is deliberately NOT part of these instances: unrolling whole
 // components made 230 KB of code, an instruction-cache hit rate of 63 % and "no instruction" the second largest stall.
-template <int JLO, int JHI>
-__device__ __forceinline__ void kspaceDeflate(KFitState& fs, const KCtx& cx, int comp, const double (&tc)[kKNS], const double (&st)[4]) {
+template <int NF, int JLO, int JHI>
+__device__ __forceinline__ void kspaceDeflate(KFitState<NF>& fs, const KCtx& cx, int comp, const double (&tc)[kKNS], const double (&st)[4]) {
 	const int lane = cx.lane;
 	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 	double w[kKNS];
@@ -262,12 +309,37 @@ __device__ __forceinline__ void kspaceDeflate(KFitState& fs, const KCtx& cx, int
 	double sv[NV];
 #pragma unroll
 	for (int j = 0; j < NV; ++j) sv[j] = 0.0;
+	if (NF == 8) {
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) {
+#pragma unroll
+			for (int j = 0; j < JHI; ++j) {
+				if (j < JLO || j < comp) sv[j] = fma(fs.U[j][u], tc[u], sv[j]); // V_j'v = U_j'tc
+			}
+		}
+	} else {
+#pragma unroll
+		for (int j0 = 0; j0 < JHI; j0 += 2) { // two stored vectors per round trip to tensor memory
+			uint32_t r[2][12];
+#pragma unroll
+			for (int jj = 0; jj < 2; ++jj) {
+				if (j0 + jj < JHI) {
+					tmemLd8(r[jj], fs.tmemU + kKUStride * (j0 + jj));
+					tmemLd4(r[jj], fs.tmemU + kKUStride * (j0 + jj) + 8);
+				}
+			}
+			tmemWaitLd();
+#pragma unroll
+			for (int jj = 0; jj < 2; ++jj) {
+				if (j0 + jj < JHI && (j0 + jj < JLO || j0 + jj < comp)) {
+#pragma unroll
+					for (int u = 0; u < kKNS; ++u) sv[j0 + jj] = fma(__hiloint2double(r[jj][2 * u + 1], r[jj][2 * u]), tc[u], sv[j0 + jj]);
+				}
+			}
+		}
+	}
 #pragma unroll
 	for (int u = 0; u < kKNS; ++u) {
-#pragma unroll
-		for (int j = 0; j < JHI; ++j) {
-			if (j < JLO || j < comp) sv[j] = fma(fs.U[j][u], tc[u], sv[j]); // V_j'v = U_j'tc
-		}
 		sv[JHI] = fma(tc[u], fs.tt[u], sv[JHI]);     // v'S = tc't
 		sv[JHI + 1] = fma(tc[u], w[u], sv[JHI + 1]); // |X'tc|^2 = tc'K tc
 	}
@@ -294,33 +366,77 @@ __device__ __forceinline__ void kspaceDeflate(KFitState& fs, const KCtx& cx, int
 	vv -= vv2;
 	const double rvn = rsqrt(vv);
 	const double dd = vs * rvn * rvn; // v'S / v'v
+	double dsum[kKNS]; // sum_j (V_j'v) U_j
+#pragma unroll
+	for (int u = 0; u < kKNS; ++u) dsum[u] = 0.0;
+	if (NF == 8) {
+#pragma unroll
+		for (int u = 0; u < kKNS; ++u) {
+			// two partial sums: half the dependent chain
+			double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+			for (int j = 0; j < JHI; j += 2) {
+				if (j < JLO || j < comp) d0 = fma(fs.U[j][u], cj[j], d0);
+				if (j + 1 < JHI && (j + 1 < JLO || j + 1 < comp)) d1 = fma(fs.U[j + 1][u], cj[j + 1], d1);
+			}
+			dsum[u] = d0 + d1;
+		}
+	} else {
+#pragma unroll
+		for (int j0 = 0; j0 < JHI; j0 += 2) {
+			uint32_t r[2][12];
+#pragma unroll
+			for (int jj = 0; jj < 2; ++jj) {
+				if (j0 + jj < JHI) {
+					tmemLd8(r[jj], fs.tmemU + kKUStride * (j0 + jj));
+					tmemLd4(r[jj], fs.tmemU + kKUStride * (j0 + jj) + 8);
+				}
+			}
+			tmemWaitLd();
+#pragma unroll
+			for (int jj = 0; jj < 2; ++jj) {
+				if (j0 + jj < JHI && (j0 + jj < JLO || j0 + jj < comp)) {
+#pragma unroll
+					for (int u = 0; u < kKNS; ++u) dsum[u] = fma(__hiloint2double(r[jj][2 * u + 1], r[jj][2 * u]), cj[j0 + jj], dsum[u]);
+				}
+			}
+		}
+	}
+	uint32_t packed[12];
 #pragma unroll
 	for (int u = 0; u < kKNS; ++u) {
-		// two partial sums: half the dependent chain
-		double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-		for (int j = 0; j < JHI; j += 2) {
-			if (j < JLO || j < comp) d0 = fma(fs.U[j][u], cj[j], d0);
-			if (j + 1 < JHI && (j + 1 < JLO || j + 1 < comp)) d1 = fma(fs.U[j + 1][u], cj[j + 1], d1);
-		}
-		const double uu = w[u] - (d0 + d1); // K h for the orthogonalised loading v = Z'h
-		double tn = fma(-uu, dd, fs.tt[u]);  // Z (S - v v'S / v'v)
-		if (fs.under) tn = nanv;             // the reference throws: poison this and every later component
+		const double uu = w[u] - dsum[u];   // K h for the orthogonalised loading v = Z'h
+		double tn = fma(-uu, dd, fs.tt[u]); // Z (S - v v'S / v'v)
+		if (fs.under) tn = nanv;            // the reference throws: poison this and every later component
 		fs.tt[u] = tn;
 		const double un = uu * rvn;
+		if (NF == 8) {
 #pragma unroll
-		for (int j = JLO; j <= JHI; ++j) {
-			if (j == comp) fs.U[j][u] = un;
+			for (int j = JLO; j <= JHI; ++j) {
+				if (j == comp) fs.U[NF == 8 ? j : 0][u] = un;
+			}
+		} else {
+			packed[2 * u] = static_cast<uint32_t>(__double2loint(un));
+			packed[2 * u + 1] = static_cast<uint32_t>(__double2hiint(un));
 		}
+	}
+	if (NF != 8) {
+		packed[10] = 0u;
+		packed[11] = 0u;
+		tmemSt12(fs.tmemU + kKUStride * comp, packed);
+		tmemWaitSt();
 	}
 }
 
-__global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams prm) {
+template <int NF>
+__global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams prm) {
+	constexpr int kKNF = NF, kKThreads = 32 * NF;
+	constexpr int kKBlocks = (55 + NF - 1) / NF; // 2x2-tile blocks of the lower triangle of K per warp (20 tiles: 55 blocks)
 	extern __shared__ __align__(16) double smem[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, t4 = lane & 3;
 	const int n = prm.n, n8 = prm.n8, ldz = prm.ldz;
-	const KCarve cv = kCarve(n8);
+	const KCarve cv = kCarve(n8, NF);
 	const int ldk = cv.ldk;
 	double* __restrict__ Km = smem + cv.K;
 	double* __restrict__ TA = smem + cv.TA;
@@ -344,6 +460,21 @@ __global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams
 
 	// globally centred response of every row (column p of Z)
 	for (int r = tid; r < n8; r += kKThreads) ys[r] = (r < n) ? __ldg(prm.zpool + static_cast<size_t>(prm.p) * ldz + r) : 0.0;
+
+	// the 16-fit configuration keeps the stored vectors of its fits in tensor memory: 4 warps per 32-lane quadrant,
+	// 128 columns each (9 vectors x 12 columns used).  Allocated here, released at the single exit below.
+	uint32_t tmemBase = 0u;
+	if (NF != 8) {
+		uint32_t* slot = reinterpret_cast<uint32_t*>(TB); // TB is idle until the first product
+		if (warp == 0) {
+			asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(slot))));
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+		}
+		asm volatile("tcgen05.fence::before_thread_sync;\n");
+		__syncthreads();
+		asm volatile("tcgen05.fence::after_thread_sync;\n");
+		tmemBase = *slot;
+	}
 
 	// ---- K = Z Z' over column chunks (PLS::viewSelectColumns + the implicit X X' of the recurrences) -------------
 	{
@@ -444,7 +575,8 @@ __global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams
 		for (int u = 0; u < kKNS; ++u) fd.train[u] = 0u;
 		fd.taskBegin = 0; fd.ntasks = 0; fd.ntr = 1;
 		if (fitActive) fd = prm.kfits[fi];
-		KFitState fs;
+		KFitState<NF> fs;
+		fs.tmemU = tmemBase + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(128 * (warp >> 2));
 		fs.trainBits = 0u; // bit u: the lane's row of slot u is a training row of the fit
 		fs.rowBits = 0u;   // bit u: the lane's row of slot u exists in shared memory
 		fs.under = false;
@@ -500,8 +632,9 @@ __global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams
 		for (int u = 0; u < kKNS; ++u) {
 			if ((fs.rowBits >> u) & 1u) taW[32 * u + lane] = ((fs.trainBits >> u) & 1u) ? fs.yc[u] : 0.0;
 		}
+		const int ct = (min(prm.nfits - pass * kKNF, kKNF) + 7) >> 3; // column tiles of 8 fits in use
 		__syncthreads();
-		kernelProduct(Km, TA, TB, n8, ldk, warp, lane);
+		kernelProduct(Km, TA, TB, n8, ldk, warp, lane, ct);
 		__syncthreads();
 #pragma unroll
 		for (int u = 0; u < kKNS; ++u) fs.tt[u] = ((fs.rowBits >> u) & 1u) ? tbW[32 * u + lane] : 0.0;
@@ -516,57 +649,70 @@ __global__ void __launch_bounds__(kKThreads, 1) simplsKspaceKernel(const KParams
 		for (int comp = 0; comp < A; ++comp) {
 			const bool more = comp + 1 < A;
 			double tc[kKNS], st[4];
-			kspaceScores(fs, cx, comp, more, tc, st);
+			kspaceScores<NF>(fs, cx, comp, more, tc, st);
 			if (!more) break;
 			// ---- w = K tc: the loading v = X't seen from the rows (:145-147) ---------------------------------------
 			__syncthreads();
 			if (cx.tracing) GSB_KSTAMP();
-			kernelProduct(Km, TA, TB, n8, ldk, warp, lane);
+			kernelProduct(Km, TA, TB, n8, ldk, warp, lane, ct);
 			__syncthreads();
 			if (cx.tracing) GSB_KSTAMP();
 			// one instance per component (measured: faster than three instances covering 0-2, 3-5, 6-8 with
 			// predicated terms, although each then runs once per pass out of a cold instruction cache)
 			switch (comp) {
-			case 0: kspaceDeflate<0, 0>(fs, cx, comp, tc, st); break;
-			case 1: kspaceDeflate<1, 1>(fs, cx, comp, tc, st); break;
-			case 2: kspaceDeflate<2, 2>(fs, cx, comp, tc, st); break;
-			case 3: kspaceDeflate<3, 3>(fs, cx, comp, tc, st); break;
-			case 4: kspaceDeflate<4, 4>(fs, cx, comp, tc, st); break;
-			case 5: kspaceDeflate<5, 5>(fs, cx, comp, tc, st); break;
-			case 6: kspaceDeflate<6, 6>(fs, cx, comp, tc, st); break;
-			case 7: kspaceDeflate<7, 7>(fs, cx, comp, tc, st); break;
-			default: kspaceDeflate<8, 8>(fs, cx, comp, tc, st); break;
+			case 0: kspaceDeflate<NF, 0, 0>(fs, cx, comp, tc, st); break;
+			case 1: kspaceDeflate<NF, 1, 1>(fs, cx, comp, tc, st); break;
+			case 2: kspaceDeflate<NF, 2, 2>(fs, cx, comp, tc, st); break;
+			case 3: kspaceDeflate<NF, 3, 3>(fs, cx, comp, tc, st); break;
+			case 4: kspaceDeflate<NF, 4, 4>(fs, cx, comp, tc, st); break;
+			case 5: kspaceDeflate<NF, 5, 5>(fs, cx, comp, tc, st); break;
+			case 6: kspaceDeflate<NF, 6, 6>(fs, cx, comp, tc, st); break;
+			case 7: kspaceDeflate<NF, 7, 7>(fs, cx, comp, tc, st); break;
+			default: kspaceDeflate<NF, 8, 8>(fs, cx, comp, tc, st); break;
 			}
 			if (cx.tracing) GSB_KSTAMP();
 		}
 	}
 #undef GSB_KSTAMP
+	if (NF != 8) {
+		__syncthreads();
+		if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmemBase));
+	}
 }
 
 } // namespace
 
-int kspaceKernelSharedBytes(int n) {
-	return kCarve(roundUpK(n, 8)).total * static_cast<int>(sizeof(double));
+int kspaceKernelSharedBytes(int n, int nf) {
+	return kCarve(roundUpK(n, 8), nf).total * static_cast<int>(sizeof(double));
 }
 
-// 1 when the kernel-space kernel can take a plan with n rows and A components under the shared-memory limit
-int kspaceKernelFits(int n, int A, int smemLimit) {
+// 1 when the kernel-space kernel with nf (8 or 16) fits per pass can take a plan with n rows and A components under
+// the shared-memory limit
+int kspaceKernelFits(int n, int A, int smemLimit, int nf) {
 	const int n8 = roundUpK(n, 8);
+	if (nf != 8 && nf != 16) return 0;
 	if (n < 8 || n8 > 32 * kKNS || A > kKA || A < 1) return 0;
-	if ((n8 >> 3) > 20) return 0; // 2x2 blocks of the lower triangle: kKBlocks * 8 >= blocks
-	return kspaceKernelSharedBytes(n) <= smemLimit ? 1 : 0;
+	if ((n8 >> 3) > 20) return 0; // 2x2 blocks of the lower triangle of K: at most 55
+	return kspaceKernelSharedBytes(n, nf) <= smemLimit ? 1 : 0;
+}
+
+template <int NF>
+static cudaError_t launchKspaceOne(const KParams& prm, int bytes, long long grid, cudaStream_t stream) {
+	cudaError_t err = cudaFuncSetAttribute(simplsKspaceKernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (err != cudaSuccess) return err;
+	simplsKspaceKernel<NF><<<static_cast<unsigned>(grid), 32 * NF, static_cast<size_t>(bytes), stream>>>(prm);
+	return cudaGetLastError();
 }
 
 cudaError_t launchKspaceKernel(const KParams& prm, cudaStream_t stream, long long* ctas) {
-	const int bytes = kspaceKernelSharedBytes(prm.n);
+	const int bytes = kspaceKernelSharedBytes(prm.n, prm.nf);
 	const long long grid = static_cast<long long>(prm.bucketCount) * prm.split;
 	if (grid <= 0) return cudaSuccess;
-	if (grid > 2147483647LL || prm.split < 1) return cudaErrorInvalidConfiguration;
-	cudaError_t err = cudaFuncSetAttribute(simplsKspaceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (grid > 2147483647LL || prm.split < 1 || (prm.nf != 8 && prm.nf != 16)) return cudaErrorInvalidConfiguration;
+	const cudaError_t err = prm.nf == 8 ? launchKspaceOne<8>(prm, bytes, grid, stream) : launchKspaceOne<16>(prm, bytes, grid, stream);
 	if (err != cudaSuccess) return err;
-	simplsKspaceKernel<<<static_cast<unsigned>(grid), kKThreads, static_cast<size_t>(bytes), stream>>>(prm);
 	if (ctas) *ctas += grid;
-	return cudaGetLastError();
+	return cudaSuccess;
 }
 
 } // namespace gsb

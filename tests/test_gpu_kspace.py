@@ -26,15 +26,18 @@ def case(oracle_lib):
     return X, y, sv, subsets, want, wstatus
 
 
+@pytest.mark.parametrize("nf", [8, 16])
 @pytest.mark.parametrize("split", [1, 2, 3])
-def test_every_subset_size_and_split_against_the_oracle(engine, case, split):
-    """GSB_KSPACE_MINK=0 sends every subset (1..230 columns: up to four column chunks of K) through K1k."""
+def test_every_subset_size_and_split_against_the_oracle(engine, case, split, nf):
+    """GSB_KSPACE_MINK=0 sends every subset (1..230 columns: up to four column chunks of K) through K1k, with 16 fits
+    per pass (the fits' stored vectors in tensor memory: GSB_KSPACE_NF=16) and with the default 8."""
     from gaselect_b200 import evaluators as E
     X, y, sv, subsets, want, wstatus = case
-    with forced(GSB_KSPACE_MINK="0", GSB_KSPACE_SPLIT=str(split), GSB_NO_KSPACE=None):
+    with forced(GSB_KSPACE_MINK="0", GSB_KSPACE_SPLIT=str(split), GSB_NO_KSPACE=None, GSB_KSPACE_NF=str(nf)):
         with E.PLSEvaluator(X, y, sv, **KW) as ev:
             fit, status = ev.evaluate_population(subsets)
-            assert ev.timing()["fit_ctas"] == len(subsets) * split  # one launch, `split` CTAs per chromosome
+            passes = -(-ev.info()["distinct_fits"] // nf)
+            assert ev.timing()["fit_ctas"] == len(subsets) * min(split, passes)  # one launch, <= `split` CTAs per chromosome
             assert (status == wstatus).all()
             assert rel_err(fit[wstatus == 0], want[wstatus == 0]).max() <= REL_TOL
             again, _ = ev.evaluate_population(subsets)
