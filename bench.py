@@ -68,7 +68,7 @@ class ClockSampler:
     """SM clock and throttle reasons sampled through NVML while the timed region runs (the
     nvidia-smi clocks line of B200_PROFILING.md, without spawning a process next to the GPU work)."""
 
-    def __init__(self, device, period=0.05):
+    def __init__(self, device, period=0.01):
         self.device, self.period, self.rows, self.thread, self.h = device, period, [], None, None
         self._stop = threading.Event()
         try:
@@ -154,7 +154,7 @@ DMMA_PEAK_TFLOPS = 37.2
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
