@@ -175,7 +175,8 @@ def main():
                           (args.workload, w["kw"]["numReplications"], w["kw"]["outerSegments"], w["kw"]["innerSegments"],
                            w["kw"]["maxNComp"], w["n"], w["p"], w["pop"], w["kmin"], w["kmax"]),
               "population_per_gpu": w["pop"], "global_population": w["pop"] * world, "ga_seed": GA_SEED,
-              "parallelism": "population sharded over %d GPU(s); fitness all-gather over NCCL" % world}
+              "parallelism": "generation of %d chromosomes dealt to %d GPU(s) (equal counts, longest-processing-time-first on "
+                              "the kernels' measured cost); fitness all-gather over NCCL" % (w["pop"] * world, world)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -216,8 +217,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # every rank scores its own shard of the (500 * N)-chromosome generation
-    subsets = synth.random_subsets(w["p"], w["pop"], w["kmin"], w["kmax"], seed=42 + rank)
+    # the (500 * N)-chromosome generation is dealt to the ranks (equal counts, balanced on the kernels' measured cost)
+    from gaselect_b200 import multigpu
+    generation = synth.random_subsets(w["p"], w["pop"] * world, w["kmin"], w["kmax"], seed=42)
+    sizes = [len(s) for s in generation]
+    cost = multigpu.kspace_cost(sizes) if w["n"] <= 160 else multigpu.gram_cost(sizes)
+    subsets = [generation[i] for i in multigpu.deal(sizes, world, cost=cost, equal_counts=True)[rank]]
     idx, offsets = _capi.to_csr(subsets)
     ks = np.diff(offsets.astype(np.int64))
 

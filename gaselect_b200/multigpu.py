@@ -11,20 +11,39 @@ data-path collective.
 import numpy as np
 
 
-def deal(sizes, world_size):
+def gram_cost(sizes):
+    """Cost proxy of one evaluation on the per-fit Gram-space kernel: k^2 (the matrix-vector products dominate)."""
+    sizes = np.asarray(sizes, dtype=np.float64)
+    return sizes * sizes + 1.0
+
+
+def kspace_cost(sizes, min_k=40):
+    """Cost proxy where the kernel-space kernel K1k takes the subsets of more than `min_k` columns (PLS_CV plans with
+    n <= 160 rows and <= 10 components): its cost does not depend on the subset size but for the K = Z Z' build;
+    below, the per-fit kernel.  Measured at BASELINE config 3 (profiles/README.md, ms per 296 chromosomes):
+    0.59 at k = 16, 0.80 at k = 32, 1.25 ... 1.31 for K1k at k = 48 ... 300."""
+    sizes = np.asarray(sizes, dtype=np.float64)
+    return np.where(sizes > min_k, 1.24 + 0.00023 * sizes, 0.38 + 0.0131 * sizes)
+
+
+def deal(sizes, world_size, cost=None, equal_counts=False):
     """Longest-processing-time-first deal of chromosomes to ranks.
 
-    Cost proxy of one evaluation: k^2 (the Gram-space SIMPLS matrix-vector products dominate).
+    `cost`: per-chromosome cost proxy (default gram_cost: k^2).  `equal_counts`: no rank takes more than
+    ceil(n / world_size) chromosomes (equal-sized result buffers for the all-gather).
     Deterministic (stable sort, ties to the lower rank); returns a list of index arrays, one per
     rank, each ascending."""
     sizes = np.asarray(sizes, dtype=np.int64)
-    order = np.argsort(-(sizes * sizes), kind="stable")
-    load = np.zeros(world_size, dtype=np.int64)
+    c = gram_cost(sizes) if cost is None else np.asarray(cost, dtype=np.float64)
+    order = np.argsort(-c, kind="stable")
+    cap = -(-len(sizes) // world_size) if equal_counts else len(sizes)
+    load = np.zeros(world_size, dtype=np.float64)
     shares = [[] for _ in range(world_size)]
     for i in order:
-        r = int(np.argmin(load))  # first minimum
+        open_ranks = [r for r in range(world_size) if len(shares[r]) < cap]
+        r = min(open_ranks, key=lambda q: (load[q], q))  # first minimum among the ranks with room
         shares[r].append(int(i))
-        load[r] += int(sizes[i]) ** 2 + 1
+        load[r] += c[i]
     return [np.asarray(sorted(s), dtype=np.int64) for s in shares]
 
 

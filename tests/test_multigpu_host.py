@@ -22,6 +22,20 @@ def test_deal_is_a_balanced_partition():
         assert all((a == b).all() for a, b in zip(shares, multigpu.deal(sizes, world)))  # deterministic
 
 
+def test_deal_with_the_kernel_space_cost_and_equal_counts():
+    """The kernel-space kernel's cost is flat above 40 columns: the deal balances counts, and with equal_counts every
+    rank holds exactly ceil(n / world) chromosomes or one less (equal-sized all-gather buffers)."""
+    from gaselect_b200 import multigpu, synth
+    sizes = [len(s) for s in synth.random_subsets(1000, 4000, 10, 200, seed=42)]
+    cost = multigpu.kspace_cost(sizes)
+    for world in (2, 8):
+        shares = multigpu.deal(sizes, world, cost=cost, equal_counts=True)
+        assert np.sort(np.concatenate(shares)).tolist() == list(range(len(sizes)))
+        assert {len(s) for s in shares} == {len(sizes) // world}
+        loads = [float(cost[s].sum()) for s in shares]
+        assert max(loads) - min(loads) <= 1.5 * float(cost.max())
+
+
 class _FakeEvaluator:
     """Stands in for the engine in the plumbing test: a deterministic function of the subset."""
 
