@@ -1225,14 +1225,27 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				kp.bucketCount = 0;
 				for (size_t b = kspaceFirst; b < e->buckets.size(); ++b) kp.bucketCount += e->buckets[b].count;
 				kp.nfits = e->kspaceFits;
-				// CTAs per chromosome: every CTA builds its own K (about one pass worth of time), so split only until there
-				// are two CTAs per SM (measured at 500 chromosomes: 1 CTA per chromosome 2.17 ms, 3 per chromosome 2.23 ms)
+				// CTAs per chromosome: every CTA builds its own K, and CTAs run in waves of one per SM.  Pick the split
+				// that minimises waves x (passes per CTA x pass time + K build time); measured (k-cycles, B200): a
+				// component of a pass ~6, its first scores ~6, K = Z Z' ~0.37 per column
 				const int passes = (e->kspaceFits + kspaceNf - 1) / kspaceNf;
 				kp.nf = kspaceNf;
 				int split = kspaceSplit;
 				if (split <= 0) {
+					double kbar = 0.0;
+					for (int i = 0; i < kp.bucketCount; ++i) {
+						const int c = e->hBucket.ptr[e->buckets[kspaceFirst].begin + i];
+						kbar += static_cast<double>(e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c]);
+					}
+					kbar /= std::max(1, kp.bucketCount);
+					const double passTime = (6.0 * e->tableA + 6.0) * (kspaceNf / 8), buildTime = 0.37 * kbar;
+					double best = 0.0;
 					split = 1;
-					while (split < 8 && static_cast<long long>(kp.bucketCount) * split < 2LL * e->smCount && (passes + split) / (split + 1) >= 3) ++split;
+					for (int sp = 1; sp <= std::min(8, passes); ++sp) {
+						const long long waves = (static_cast<long long>(kp.bucketCount) * sp + e->smCount - 1) / std::max(1, e->smCount);
+						const double t = static_cast<double>(waves) * (((passes + sp - 1) / sp) * passTime + buildTime);
+						if (sp == 1 || t < best * 0.98) { best = t; split = sp; }
+					}
 				}
 				kp.split = std::max(1, std::min(split, passes));
 				kp.n = e->n;
