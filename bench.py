@@ -215,7 +215,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # no device_id: the NCCL communicator is then created by the first collective, i.e. in the warm-up steps, AFTER
+        # the engine and the flush buffer have allocated their device memory.  Measured (profiles/ag_probe.py,
+        # profiles/ag_env.sh): with the communicator created first every step takes 2.28 instead of 2.20 ms, K1 itself
+        # unchanged -- the all-gather costs 12 us, the rest of the 1 -> N GPU gap was this allocation order
+        dist.init_process_group("nccl")
 
     # the (500 * N)-chromosome generation is dealt to the ranks (equal counts, balanced on the kernels' measured cost)
     from gaselect_b200 import multigpu
