@@ -52,9 +52,11 @@ class ShardedEvaluator:
     gaselect_b200.evaluators.Evaluator, every rank passes the SAME population and receives the
     complete (fitness, status) vectors."""
 
-    def __init__(self, evaluator, group=None, device=None):
+    def __init__(self, evaluator, group=None, device=None, cost=None):
+        """cost: callable sizes -> per-chromosome cost proxy (gram_cost by default; kspace_cost for PLS_CV plans the
+        kernel-space kernel takes)."""
         import torch.distributed as dist
-        self.ev, self.group, self.device = evaluator, group, device
+        self.ev, self.group, self.device, self.cost = evaluator, group, device, cost
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
@@ -62,7 +64,8 @@ class ShardedEvaluator:
         import torch
         import torch.distributed as dist
         n = len(subsets)
-        shares = deal([len(s) for s in subsets], self.world)
+        sizes = [len(s) for s in subsets]
+        shares = deal(sizes, self.world, cost=None if self.cost is None else self.cost(sizes))
         mine = shares[self.rank]
         fit_l, st_l = self.ev.evaluate_population([subsets[i] for i in mine])
         cap = max(len(s) for s in shares) if n else 0
