@@ -734,15 +734,6 @@ void prepareDevice(gsb_engine* e) {
 	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && gsb::kspaceKernelFits(n, 1, e->smemLimit, 8) && !std::getenv("GSB_NO_KSPACE")) {
 		std::vector<gsb::KFitDesc> kf(static_cast<size_t>(nfits));
 		std::vector<gsb::KTaskDesc> kt(plan.tasks.size());
-		for (int f = 0; f < nfits; ++f) {
-			const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
-			gsb::KFitDesc& d = kf[static_cast<size_t>(f)];
-			for (int u = 0; u < gsb::kKspaceSlots; ++u) d.train[u] = 0u;
-			for (size_t i = 0; i < pf.rows.size(); ++i) d.train[pf.rows[i] >> 5] |= 1u << (pf.rows[i] & 31u);
-			d.taskBegin = pf.taskBegin;
-			d.ntasks = pf.taskCount;
-			d.ntr = static_cast<int>(pf.rows.size());
-		}
 		for (size_t t = 0; t < plan.tasks.size(); ++t) {
 			const gsb::PlanTask& pt = plan.tasks[t];
 			const gsb::PlanBlock& pb = plan.blocks[static_cast<size_t>(pt.block)];
@@ -752,6 +743,35 @@ void prepareDevice(gsb_engine* e) {
 			d.kind = pt.kind;
 			d.dest = pt.dest;
 			d.nrows = static_cast<int>(pb.rows.size());
+			d.rr = 1.0 / static_cast<double>(std::max<size_t>(1, pb.rows.size()));
+		}
+		for (int f = 0; f < nfits; ++f) {
+			const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
+			gsb::KFitDesc& d = kf[static_cast<size_t>(f)];
+			for (int u = 0; u < gsb::kKspaceSlots; ++u) d.train[u] = 0u;
+			for (size_t i = 0; i < pf.rows.size(); ++i) d.train[pf.rows[i] >> 5] |= 1u << (pf.rows[i] & 31u);
+			d.taskBegin = pf.taskBegin;
+			d.ntasks = pf.taskCount;
+			d.ntr = static_cast<int>(pf.rows.size());
+			// centring of the response on the training rows, in the arithmetic of the device data (y - global mean)
+			double sy = 0.0;
+			for (size_t i = 0; i < pf.rows.size(); ++i) sy += e->y[pf.rows[i]] - e->yMean;
+			d.rntr = 1.0 / static_cast<double>(std::max<size_t>(1, pf.rows.size()));
+			d.ym = sy * d.rntr;
+			double res = 0.0;
+			for (size_t i = 0; i < pf.rows.size(); ++i) res += (e->y[pf.rows[i]] - e->yMean) - d.ym;
+			d.syc = res;
+			for (int j = 0; j < 2; ++j) {
+				if (j < pf.taskCount) {
+					d.first[j] = kt[static_cast<size_t>(pf.taskBegin + j)];
+				} else {
+					for (int u = 0; u < gsb::kKspaceSlots; ++u) d.first[j].rows[u] = 0u;
+					d.first[j].kind = -1;
+					d.first[j].dest = 0;
+					d.first[j].nrows = 1;
+					d.first[j].rr = 1.0;
+				}
+			}
 		}
 		e->kFits.upload(kf, e->stream);
 		e->kTasks.upload(kt, e->stream);

@@ -236,18 +236,24 @@ struct XParams {
 constexpr int kKspaceComponents = 10;
 constexpr int kKspaceSlots = 5; // 32-row slots per lane: n <= 160
 
+struct KTaskDesc {
+	uint32_t rows[kKspaceSlots]; // the held-out rows this task predicts
+	int kind;                    // 0 inner (MSEP table), 1 outer (pooled residual statistics); -1: none
+	int dest;
+	int nrows;
+	double rr;                   // 1 / nrows
+};
+
+// everything a warp needs to start a fit, in one 128-byte record: no dependent loads, no divisions, no reductions
 struct KFitDesc {
 	uint32_t train[kKspaceSlots]; // bit r % 32 of word r / 32: row r is a training row
 	int taskBegin;                // into ktasks
 	int ntasks;
 	int ntr;                      // number of training rows
-};
-
-struct KTaskDesc {
-	uint32_t rows[kKspaceSlots]; // the held-out rows this task predicts
-	int kind;                    // 0 inner (MSEP table), 1 outer (pooled residual statistics)
-	int dest;
-	int nrows;
+	double ym;                    // mean of the (globally centred) response over the training rows (src/PLSSimpls.cpp:28-49)
+	double syc;                   // sum over the training rows of (y - ym): the rounding residue of that centring
+	double rntr;                  // 1 / ntr
+	KTaskDesc first[2];           // copies of the fit's first two tasks (kind -1 when absent)
 };
 
 struct KParams {

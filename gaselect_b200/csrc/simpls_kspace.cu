@@ -180,6 +180,7 @@ struct KCtx {
 	const double* tbW; // this warp's row of TB
 	int n8, ldk, warp, lane, A, chrom;
 	const KFitDesc* fd;
+	bool fitActive;
 	bool tracing;
 };
 
@@ -267,7 +268,7 @@ __device__ __forceinline__ void kspaceScores(KFitState<NF>& fs, const KCtx& cx, 
 	}
 	// more than two tasks on one fit: not in a nested CV, but legal
 	const KFitDesc& fd = *cx.fd;
-	for (int tk = 2; tk < fd.ntasks; ++tk) {
+	for (int tk = 2; cx.fitActive && tk < fd.ntasks; ++tk) {
 		const KTaskDesc td = prm.ktasks[fd.taskBegin + tk];
 		double sx[2] = {0.0, 0.0};
 #pragma unroll
@@ -570,62 +571,35 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	for (int pass = part * perPart; pass < passEnd; ++pass) {
 		const int fi = pass * kKNF + warp;
 		const bool fitActive = fi < prm.nfits;
-		KFitDesc fd;
-#pragma unroll
-		for (int u = 0; u < kKNS; ++u) fd.train[u] = 0u;
-		fd.taskBegin = 0; fd.ntasks = 0; fd.ntr = 1;
-		if (fitActive) fd = prm.kfits[fi];
+		// one 128-byte record per fit: masks, centring constants and its first two tasks (no dependent loads)
+		const KFitDesc fd = prm.kfits[min(fi, prm.nfits - 1)];
 		KFitState<NF> fs;
 		fs.tmemU = tmemBase + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(128 * (warp >> 2));
 		fs.trainBits = 0u; // bit u: the lane's row of slot u is a training row of the fit
 		fs.rowBits = 0u;   // bit u: the lane's row of slot u exists in shared memory
 		fs.under = false;
 		fs.taskBitsA = 0u; fs.taskBitsB = 0u;
-		fs.kindA = -1; fs.kindB = -1;
-		fs.outA = nullptr; fs.outB = nullptr;
-		fs.rrA = 1.0; fs.rrB = 1.0;
-		if (fd.ntasks > 0) {
-			const KTaskDesc td = prm.ktasks[fd.taskBegin];
+		fs.kindA = fitActive ? fd.first[0].kind : -1;
+		fs.kindB = fitActive ? fd.first[1].kind : -1;
+		fs.rrA = fd.first[0].rr;
+		fs.rrB = fd.first[1].rr;
+		fs.outA = fd.first[0].kind == 0 ? prm.mse + (static_cast<size_t>(chrom) * prm.innerDests + fd.first[0].dest) * prm.maxNComp
+		                                : prm.ostat + (static_cast<size_t>(chrom) * prm.outerDests + fd.first[0].dest) * prm.maxNComp * 2;
+		fs.outB = fd.first[1].kind == 0 ? prm.mse + (static_cast<size_t>(chrom) * prm.innerDests + fd.first[1].dest) * prm.maxNComp
+		                                : prm.ostat + (static_cast<size_t>(chrom) * prm.outerDests + fd.first[1].dest) * prm.maxNComp * 2;
+		fs.rntr = fd.rntr;
+		fs.syc = fd.syc;
 #pragma unroll
-			for (int u = 0; u < kKNS; ++u) if ((td.rows[u] >> lane) & 1u) fs.taskBitsA |= 1u << u;
-			fs.kindA = td.kind;
-			fs.rrA = 1.0 / static_cast<double>(td.nrows);
-			fs.outA = td.kind == 0 ? prm.mse + (static_cast<size_t>(chrom) * prm.innerDests + td.dest) * prm.maxNComp
-			                       : prm.ostat + (static_cast<size_t>(chrom) * prm.outerDests + td.dest) * prm.maxNComp * 2;
-		}
-		if (fd.ntasks > 1) {
-			const KTaskDesc td = prm.ktasks[fd.taskBegin + 1];
-#pragma unroll
-			for (int u = 0; u < kKNS; ++u) if ((td.rows[u] >> lane) & 1u) fs.taskBitsB |= 1u << u;
-			fs.kindB = td.kind;
-			fs.rrB = 1.0 / static_cast<double>(td.nrows);
-			fs.outB = td.kind == 0 ? prm.mse + (static_cast<size_t>(chrom) * prm.innerDests + td.dest) * prm.maxNComp
-			                       : prm.ostat + (static_cast<size_t>(chrom) * prm.outerDests + td.dest) * prm.maxNComp * 2;
-		}
-		{
-			double sy = 0.0;
-#pragma unroll
-			for (int u = 0; u < kKNS; ++u) {
-				const int r = 32 * u + lane;
-				if (r < n8) fs.rowBits |= 1u << u;
+		for (int u = 0; u < kKNS; ++u) {
+			const int r = 32 * u + lane;
+			if (r < n8) fs.rowBits |= 1u << u;
+			if (fitActive) {
 				if ((fd.train[u] >> lane) & 1u) fs.trainBits |= 1u << u;
-				fs.yc[u] = (r < n8) ? ys[r] : 0.0;
-				fs.pred[u] = 0.0;
-				if ((fs.trainBits >> u) & 1u) sy += fs.yc[u];
+				if ((fd.first[0].rows[u] >> lane) & 1u) fs.taskBitsA |= 1u << u;
+				if ((fd.first[1].rows[u] >> lane) & 1u) fs.taskBitsB |= 1u << u;
 			}
-#pragma unroll
-			for (int m = 16; m >= 1; m >>= 1) sy += shflXorK(sy, m);
-			fs.rntr = 1.0 / static_cast<double>(fd.ntr);
-			const double ym = sy * fs.rntr;
-			double s2 = 0.0;
-#pragma unroll
-			for (int u = 0; u < kKNS; ++u) {
-				fs.yc[u] = (32 * u + lane < n) ? fs.yc[u] - ym : 0.0;
-				if ((fs.trainBits >> u) & 1u) s2 += fs.yc[u];
-			}
-#pragma unroll
-			for (int m = 16; m >= 1; m >>= 1) s2 += shflXorK(s2, m);
-			fs.syc = s2; // rounding residue of the centring, ~ 1e-16
+			fs.yc[u] = (r < n) ? ys[r] - fd.ym : 0.0; // response centred on the training rows (src/PLSSimpls.cpp:28-49)
+			fs.pred[u] = 0.0;
 		}
 		// t_0 = Z S_0 = K (m . y_c)   (S_0 = X_c'y_c, :126)
 #pragma unroll
@@ -642,6 +616,7 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 		cx.prm = &prm; cx.Km = Km; cx.TA = TA; cx.TB = TB; cx.taW = taW; cx.tbW = tbW;
 		cx.n8 = n8; cx.ldk = ldk; cx.warp = warp; cx.lane = lane; cx.A = A; cx.chrom = chrom;
 		cx.fd = &fd;
+		cx.fitActive = fitActive;
 		cx.tracing = tracing && pass == part * perPart;
 		if (cx.tracing) GSB_KSTAMP(); // 2: first scores
 		// the barriers below are uniform: A is a property of the chromosome
