@@ -731,7 +731,9 @@ void prepareDevice(gsb_engine* e) {
 
 	// ---- K1k: per-lane row masks (lane = row mod 32) of every distinct fit and prediction task
 	e->kspaceFits = 0;
-	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && gsb::kspaceKernelFits(n, 1, e->smemLimit, 8) && !std::getenv("GSB_NO_KSPACE")) {
+	// (PLS_CV and PLS_FIT: the all-rows refit of BICEvaluator is a fit whose "held-out" block is every row)
+	if ((e->cfg.evaluator == GSB_EVAL_PLS_CV || e->cfg.evaluator == GSB_EVAL_PLS_FIT) && nfits > 0 &&
+	    gsb::kspaceKernelFits(n, 1, e->smemLimit, 8) && !std::getenv("GSB_NO_KSPACE")) {
 		std::vector<gsb::KFitDesc> kf(static_cast<size_t>(nfits));
 		std::vector<gsb::KTaskDesc> kt(plan.tasks.size());
 		for (size_t t = 0; t < plan.tasks.size(); ++t) {

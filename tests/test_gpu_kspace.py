@@ -130,3 +130,23 @@ def test_config3_shape_with_wide_subsets(engine, oracle_lib):
             with E.PLSEvaluator(X, y, sv, **kw) as ev:
                 fit, status = ev.evaluate_population(subsets)
         assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("stat", ["BIC", "adjusted.r.squared"])
+def test_bic_evaluator_on_the_kernel_space_kernel(engine, oracle_lib, stat):
+    """BICEvaluator (src/BICEvaluator.cpp:54-91, 144-233): K-fold one-SE rule + a refit on ALL rows whose residuals
+    are taken on those same rows -- for K1k just one more fit whose prediction task covers every row."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(120, 150, seed=15)
+    sv = oracle_lib.make_seedvec(31)
+    subsets = synth.random_subsets(150, 30, 1, 110, seed=4)
+    fo, so = oracle_lib.fit_evaluator(X, y, sv, numSegments=6, statistic=stat, maxNComp=7).evaluate(subsets, threads=4)
+    with forced(GSB_KSPACE_MINK="0", GSB_KSPACE_SPLIT="1", GSB_NO_KSPACE=None):
+        with E.BICEvaluator(X, y, sv, numSegments=6, statistic=stat, maxNComp=7) as ev:
+            fg, sg = ev.evaluate_population(subsets)
+            assert ev.timing()["fit_ctas"] == len(subsets)
+    assert (sg == so).all() and rel_err(fg[so == 0], fo[so == 0]).max() <= REL_TOL
+    with forced(GSB_KSPACE_MINK=None, GSB_KSPACE_SPLIT=None, GSB_NO_KSPACE=None):  # default policy: mixed kernels
+        with E.BICEvaluator(X, y, sv, numSegments=6, statistic=stat, maxNComp=7) as ev:
+            fd, sd = ev.evaluate_population(subsets)
+    assert (sd == so).all() and rel_err(fd[so == 0], fo[so == 0]).max() <= REL_TOL
