@@ -22,6 +22,9 @@
 // column chunks streamed through shared memory with cp.async).  One warp per fit: lane = row (mod 32), the fit's
 // vectors (t, y_c, yhat, tc, the nine U_j) live in registers; masks are per-lane bits, so ANY training sets and
 // held-out blocks work (no atom structure needed).  Two CTA barriers per component (around the product).
+// A fit starts from one 128-byte record (KFitDesc: masks, the host-computed centring constants, its first two tasks).
+// NF = 8 fits per pass is the default; NF = 16 (opt-in) keeps the U_j in tensor memory (tcgen05.st / tcgen05.ld as
+// per-thread scratch) because 512 threads leave only 128 registers each -- measured no faster, see DESIGN.md section 4.
 //
 // Numerics: mathematically the reference's SIMPLS; K squares the conditioning like the Gram-space kernel does.
 // tests/test_kspace_model.py holds the numpy model of exactly these recurrences (<= 6e-12 against the reference on
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	__syncthreads();
 	GSB_KSTAMP(); // 1: K done
 
-	// ---- passes of 8 fits: one warp per fit ----------------------------------------------------------------------
+	// ---- passes of NF fits: one warp per fit ---------------------------------------------------------------------
 	const int passes = (prm.nfits + kKNF - 1) / kKNF;
 	const int perPart = (passes + prm.split - 1) / prm.split;
 	const int passEnd = min(passes, (part + 1) * perPart);
