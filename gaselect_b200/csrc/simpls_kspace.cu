@@ -432,7 +432,9 @@ __device__ __forceinline__ void kspaceDeflate(KFitState<NF>& fs, const KCtx& cx,
 	}
 }
 
-template <int NF>
+// TRACE: the instance that stamps clock64() at its phase boundaries (launched only when prm.trace is set: the stamps
+// and the loads of their destination cost ~3 % in the component loop even when predicated off)
+template <int NF, bool TRACE>
 __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams prm) {
 	constexpr int kKNF = NF, kKThreads = 32 * NF;
 	constexpr int kKBlocks = (55 + NF - 1) / NF; // 2x2-tile blocks of the lower triangle of K per warp (20 tiles: 55 blocks)
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	const int A = min(prm.maxNComp, k);
 	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 
-	const bool tracing = prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
+	const bool tracing = TRACE && prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
 	int stamp = 0;
 #define GSB_KSTAMP() do { if (tracing && stamp < 64) prm.trace[stamp++] = clock64(); } while (0)
 	GSB_KSTAMP();
@@ -674,11 +676,11 @@ int kspaceKernelFits(int n, int A, int smemLimit, int nf) {
 	return kspaceKernelSharedBytes(n, nf) <= smemLimit ? 1 : 0;
 }
 
-template <int NF>
+template <int NF, bool TRACE>
 static cudaError_t launchKspaceOne(const KParams& prm, int bytes, long long grid, cudaStream_t stream) {
-	cudaError_t err = cudaFuncSetAttribute(simplsKspaceKernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	cudaError_t err = cudaFuncSetAttribute(simplsKspaceKernel<NF, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 	if (err != cudaSuccess) return err;
-	simplsKspaceKernel<NF><<<static_cast<unsigned>(grid), 32 * NF, static_cast<size_t>(bytes), stream>>>(prm);
+	simplsKspaceKernel<NF, TRACE><<<static_cast<unsigned>(grid), 32 * NF, static_cast<size_t>(bytes), stream>>>(prm);
 	return cudaGetLastError();
 }
 
@@ -687,7 +689,9 @@ cudaError_t launchKspaceKernel(const KParams& prm, cudaStream_t stream, long lon
 	const long long grid = static_cast<long long>(prm.bucketCount) * prm.split;
 	if (grid <= 0) return cudaSuccess;
 	if (grid > 2147483647LL || prm.split < 1 || (prm.nf != 8 && prm.nf != 16)) return cudaErrorInvalidConfiguration;
-	const cudaError_t err = prm.nf == 8 ? launchKspaceOne<8>(prm, bytes, grid, stream) : launchKspaceOne<16>(prm, bytes, grid, stream);
+	const bool tr = prm.trace != nullptr;
+	const cudaError_t err = prm.nf == 8 ? (tr ? launchKspaceOne<8, true>(prm, bytes, grid, stream) : launchKspaceOne<8, false>(prm, bytes, grid, stream))
+	                                    : (tr ? launchKspaceOne<16, true>(prm, bytes, grid, stream) : launchKspaceOne<16, false>(prm, bytes, grid, stream));
 	if (err != cudaSuccess) return err;
 	if (ctas) *ctas += grid;
 	return cudaSuccess;
