@@ -699,7 +699,9 @@ __device__ __forceinline__ double symvRowSpill(const double* __restrict__ P, con
 // SPILL: packed Gram rows >= rSplit (a multiple of 32) do not fit in shared memory; they are gathered into a
 // per-CTA scratch in global memory (L2-resident while the CTA runs; row stride roundUp(k, 4)) and read from
 // there by every matrix-vector product: own rows as contiguous per-thread runs, column accesses coalesced.
-template <int AREG, bool SPILL>
+// TRACE: the instance with the clock64() stamps, launched only when prm.trace is set (even predicated off they cost
+// a few per cent in the hot loops, measured on the kernel-space kernel)
+template <int AREG, bool SPILL, bool TRACE>
 __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) simplsFitFast(const FitParams prm, const int stageAll, const int rSplit) {
 	extern __shared__ __align__(16) double smem[];
 	static_assert(AREG % 2 == 0 && AREG + 2 <= 16, "one reduction round holds tn^2, q*tn and every projection");
@@ -726,9 +728,9 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	double* spill = SPILL ? prm.spill + static_cast<size_t>(blockIdx.x) * prm.spillStride : nullptr;
 	int phase = 0;
 
-	const bool tracing = prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
+	const bool tracing = TRACE && prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
 	int stamp = 0;
-#define GSB_STAMP() do { if (tracing) prm.trace[stamp++] = clock64(); } while (0)
+#define GSB_STAMP() do { if (TRACE && tracing) prm.trace[stamp++] = clock64(); } while (0)
 	GSB_STAMP();
 
 	// ---- gather ------------------------------------------------------------------------------
@@ -1120,14 +1122,20 @@ cudaError_t launchFast(const FitParams& prm, int kMax, int A, int smemLimit, cud
 	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
 	cudaError_t err;
 	if (rs >= kMax) {
-		err = cudaFuncSetAttribute(simplsFitFast<AREG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
-		if (err != cudaSuccess) return err;
-		simplsFitFast<AREG, false><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
+		if (prm.trace != nullptr) {
+			err = cudaFuncSetAttribute(simplsFitFast<AREG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+			if (err != cudaSuccess) return err;
+			simplsFitFast<AREG, false, true><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
+		} else {
+			err = cudaFuncSetAttribute(simplsFitFast<AREG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+			if (err != cudaSuccess) return err;
+			simplsFitFast<AREG, false, false><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
+		}
 	} else {
 		if (prm.spill == nullptr) return cudaErrorInvalidValue;
-		err = cudaFuncSetAttribute(simplsFitFast<AREG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+		err = cudaFuncSetAttribute(simplsFitFast<AREG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 		if (err != cudaSuccess) return err;
-		simplsFitFast<AREG, true><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, rs);
+		simplsFitFast<AREG, true, false><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, rs);
 	}
 	if (ctas) *ctas += grid;
 	return cudaGetLastError();
