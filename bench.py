@@ -146,7 +146,7 @@ def cpu_leg(w, X, y, subsets, budget_s):
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the K1 launches of ONE step from the committed
 # ncu --set full capture (profiles/r01_summary.txt); only valid for the default workload
-MEASURED_TRAFFIC = {("cfg3", 500): 4.499e8}
+MEASURED_TRAFFIC = {("cfg3", 500): 4.477e8}
 # FP64 tensor-core peak: 148 SMs x 4 sub-partitions x 256 FMA per DMMA.8x8x4 / 16 cycles x 1.965 GHz x 2
 DMMA_PEAK_TFLOPS = 37.2
 
