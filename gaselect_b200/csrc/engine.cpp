@@ -90,10 +90,16 @@ struct PinnedArray {
 	PinnedArray& operator=(const PinnedArray&) = delete;
 };
 
+enum BucketKernel { BK_FIT = 0, BK_SCORES = 1, BK_KSPACE = 2 };
+
 struct Bucket {
 	int begin;
 	int count;
 	int kMax;
+	int kernel;        // BucketKernel, decided when the population is uploaded
+	int nf, cs, vg;    // K1x configuration (fits per CTA, cluster size, loadings in the global scratch)
+	long long vPerCta, vOffset;
+	int vSlots;
 };
 
 // subset-size classes: one K1 launch per class, shared memory sized for the class maximum
@@ -102,6 +108,13 @@ int bucketCeil(int k) {
 	if (k <= 256) return roundUp(k, 16);
 	return roundUp(k, 32);
 }
+
+// profiling / experiment switches, read from the environment ONCE per engine (ensureDevice)
+struct EnvFlags {
+	bool serial = false, noScores = false, noKspace = false, trace = false;
+	int kspaceNf = 8, kspaceMinK = 40, kspaceSplit = 0, desync = 0;
+	int forcedNf = 0, forcedCs = 0, forcedVg = 0;
+};
 
 } // namespace
 
@@ -120,6 +133,7 @@ struct gsb_engine {
 	std::vector<gsb::RowSet> segmentation;
 	gsb::CvShape shape;
 	gsb::FitPlan plan;
+	EnvFlags env;
 
 	// device
 	cudaStream_t stream = nullptr;    // the stream all work is enqueued on
@@ -133,13 +147,27 @@ struct gsb_engine {
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int smCount = 0, smemLimit = 0;
 	int ldz = 0;
-	DeviceArray<double> zpool, gram, s0, xm;
+	DeviceArray<double> zpool;
+	DeviceArray<double> gram, s0, xm; // LMEvaluator only: the all-rows centred Gram (packed) and vectors
 	DeviceArray<gsb::FitDesc> fits;
 	DeviceArray<gsb::TaskDesc> tasks;
 	DeviceArray<gsb::BlockDesc> blocks;
+	std::vector<gsb::BlockDesc> blockDesc;
 	DeviceArray<int> outerRows;
 	double ymAllRows = 0.0;
 	int maxTasks = 0, maxBlockLd = 0;
+
+	// per-fit Gram-space kernel: the unit moment tables (built the first time a size class needs them)
+	bool unitsReady = false;
+	std::vector<int> unitBlocks;      // block id of unit u >= 1
+	std::vector<int> unitOfBlock;     // unit of a block, -1: no training set excludes it
+	int upad = 0;
+	DeviceArray<double> unitTab, unitSum, unitXy;
+	DeviceArray<gsb::PackFit> packFits;
+	// ... and, per resident population, the packed Grams / vectors of every (chromosome, training set)
+	DeviceArray<double> gpack, pvec;
+	DeviceArray<unsigned long long> dPackOff, dVecOff;
+	PinnedArray<unsigned long long> hPackOff, hVecOff;
 
 	// resident population
 	int npop = 0, kMaxPop = 0, tableA = 1;
@@ -151,16 +179,9 @@ struct gsb_engine {
 	PinnedArray<uint32_t> hIdx, hOffsets;
 	PinnedArray<int> hBucket, hStatus;
 	PinnedArray<double> hFitness;
-	DeviceArray<double> spill;       // Gram rows of very large subsets (K1 spill path), one region per size class
-	// K1b (replication-batched kernel): the packed full-data Gram and the group / pair tables
-	DeviceArray<double> gfull, batchScratch;
-	DeviceArray<int> bGroupFits;
-	DeviceArray<gsb::BatchGroup> bGroups;
-	DeviceArray<gsb::BatchPairGroup> bPgs;
-	DeviceArray<gsb::BatchPair> bPairs;
-	DeviceArray<int2> bUnits;
-	int batchGroups = 0, batchNfMax = 0, batchUDoubles = 0, batchPgp = 2, batchMaxK = 0;
 	// K1x (score-space tensor-core kernel): row-permuted copies of Z per replication and the atom tables
+	// (built the first time a size class needs them)
+	bool scoresTried = false;
 	DeviceArray<double> xz, scoreScratch;
 	DeviceArray<gsb::XRepDesc> xReps;
 	DeviceArray<gsb::XGroupDesc> xGroups8, xGroups16;
@@ -203,10 +224,11 @@ void releaseDevice(gsb_engine* e) {
 	e->zpool.release(); e->gram.release(); e->s0.release(); e->xm.release();
 	e->fits.release(); e->tasks.release(); e->blocks.release(); e->outerRows.release();
 	e->traceBuf.release();
-	e->spill.release();
-	e->gfull.release(); e->batchScratch.release(); e->bGroupFits.release(); e->bGroups.release(); e->bPgs.release();
-	e->bPairs.release(); e->bUnits.release();
+	e->unitTab.release(); e->unitSum.release(); e->unitXy.release(); e->packFits.release();
+	e->gpack.release(); e->pvec.release(); e->dPackOff.release(); e->dVecOff.release();
+	e->hPackOff.release(); e->hVecOff.release();
 	e->xz.release(); e->scoreScratch.release(); e->xReps.release(); e->xGroups8.release(); e->xGroups16.release(); e->xFits.release(); e->xTasks.release();
+	e->kFits.release(); e->kTasks.release();
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
@@ -224,6 +246,7 @@ void releaseDevice(gsb_engine* e) {
 	e->stream = nullptr;
 	e->callerStream = false;
 	e->deviceReady = e->zReady = e->prepared = e->populationReady = e->resultsReady = false;
+	e->unitsReady = e->scoresTried = false;
 }
 
 // Selects the device and creates the stream; fails loudly when there is no usable GPU.
@@ -248,7 +271,19 @@ void ensureDevice(gsb_engine* e) {
 		GSB_CUDA(cudaEventCreateWithFlags(&e->evJoin[i], cudaEventDisableTiming));
 	}
 	GSB_CUDA(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
-	if (std::getenv("GSB_TRACE")) { // profiling aid: K1 stamps clock64() at its phase boundaries
+	// profiling / experiment switches: read once, here
+	EnvFlags& env = e->env;
+	env = EnvFlags();
+	env.serial = std::getenv("GSB_SERIAL") != nullptr;
+	env.noScores = std::getenv("GSB_NO_SCORES") != nullptr;
+	env.noKspace = std::getenv("GSB_NO_KSPACE") != nullptr;
+	env.trace = std::getenv("GSB_TRACE") != nullptr;
+	if (const char* v = std::getenv("GSB_KSPACE_NF")) env.kspaceNf = std::atoi(v) == 16 ? 16 : 8;
+	if (const char* v = std::getenv("GSB_KSPACE_MINK")) env.kspaceMinK = std::atoi(v);
+	if (const char* v = std::getenv("GSB_KSPACE_SPLIT")) env.kspaceSplit = std::atoi(v);
+	if (const char* v = std::getenv("GSB_DESYNC")) env.desync = std::atoi(v);
+	if (const char* v = std::getenv("GSB_SCORE_CFG")) std::sscanf(v, "%d,%d,%d", &env.forcedNf, &env.forcedCs, &env.forcedVg);
+	if (env.trace) { // profiling aid: K1 stamps clock64() at its phase boundaries
 		e->traceBuf.reserve(64);
 		GSB_CUDA(cudaMemset(e->traceBuf.ptr, 0, 64 * sizeof(long long)));
 	}
@@ -289,313 +324,181 @@ void uploadZ(gsb_engine* e, size_t poolDoubles) {
 	e->zReady = true;
 }
 
-// K0: block copies, DMMA SYRK of the full data and of every excluded block, per-fit combination.
-void prepareDevice(gsb_engine* e) {
-	ensureDevice(e);
-	const int n = e->n, p = e->p, P2 = p + 2;
-	const gsb::FitPlan& plan = e->plan;
-	const int nfits = static_cast<int>(plan.fits.size());
-	const int nblocks = static_cast<int>(plan.blocks.size());
-	const int ldz = roundUp(n, 4);
-
-	// ---- held-out row blocks, each a contiguous column-major copy (coalesced prediction reads)
-	std::vector<gsb::BlockDesc> bdesc(static_cast<size_t>(nblocks));
-	std::vector<uint32_t> blockRows;
-	std::vector<size_t> blockRowOff(static_cast<size_t>(nblocks), 0);
-	size_t pool = static_cast<size_t>(ldz) * P2;
-	for (int b = 0; b < nblocks; ++b) {
-		const gsb::PlanBlock& pb = plan.blocks[static_cast<size_t>(b)];
-		gsb::BlockDesc& d = bdesc[static_cast<size_t>(b)];
-		d.nrows = static_cast<int>(pb.rows.size());
-		if (pb.allRows) {
-			d.zOff = 0;
-			d.ld = ldz;
-		} else {
-			d.ld = roundUp(d.nrows, 4);
-			d.zOff = pool;
-			pool += static_cast<size_t>(d.ld) * P2;
-			blockRowOff[static_cast<size_t>(b)] = blockRows.size();
-			blockRows.insert(blockRows.end(), pb.rows.begin(), pb.rows.end());
-		}
-	}
-	e->zReady = false;
-	uploadZ(e, pool);
-	DeviceArray<uint32_t> dRows;
-	dRows.upload(blockRows, e->stream);
-	for (int b = 0; b < nblocks; ++b) {
-		if (plan.blocks[static_cast<size_t>(b)].allRows) continue;
-		const gsb::BlockDesc& d = bdesc[static_cast<size_t>(b)];
-		gsb::launchBlockGather(e->zpool.ptr, ldz, P2, nullptr, dRows.ptr + blockRowOff[static_cast<size_t>(b)], d.nrows,
-		                       e->zpool.ptr + d.zOff, d.ld, e->stream);
-	}
-	GSB_CUDA(cudaGetLastError());
-
-	// ---- SYRK units: the full data, then every block some fit excludes
-	std::vector<int> unitOfBlock(static_cast<size_t>(nblocks), -1);
-	std::vector<int> unitBlocks; // block id per unit >= 1
-	for (int f = 0; f < nfits; ++f) {
-		for (size_t x = 0; x < plan.fits[static_cast<size_t>(f)].exclBlocks.size(); ++x) {
-			const int b = plan.fits[static_cast<size_t>(f)].exclBlocks[x];
-			if (unitOfBlock[static_cast<size_t>(b)] < 0) {
-				unitBlocks.push_back(b);
-				unitOfBlock[static_cast<size_t>(b)] = static_cast<int>(unitBlocks.size());
-			}
-		}
-	}
-	const int units = 1 + static_cast<int>(unitBlocks.size());
-	const int ldm = roundUp(P2, 4);
+// One SYRK pass (K0's contraction) over the units [u0, u0 + cnt): unit 0 = all rows of Z, unit u >= 1 = the block copy of
+// unitBlocks[u - 1].  Results in mPool (cnt matrices of P2 x ldm); device pointer array in dOutPtrs.
+void syrkUnits(gsb_engine* e, int u0, int cnt, DeviceArray<double>& mPool, DeviceArray<double*>& dOutPtrs, std::vector<double*>& outPtrs,
+               double& flops) {
+	const int n = e->n, P2 = e->p + 2, ldm = roundUp(P2, 4);
 	const size_t mDoubles = static_cast<size_t>(P2) * ldm;
-	const size_t triP = static_cast<size_t>(gsb::tri(static_cast<unsigned long long>(p)));
-	const size_t gramDoubles = triP * static_cast<size_t>(nfits);
-
-	size_t freeB = 0, totalB = 0;
-	GSB_CUDA(cudaMemGetInfo(&freeB, &totalB));
-	const double need = 8.0 * (static_cast<double>(mDoubles) * units + static_cast<double>(gramDoubles) +
-	                           2.0 * static_cast<double>(nfits) * p);
-	if (need > 0.92 * static_cast<double>(freeB)) {
-		char buf[256];
-		std::snprintf(buf, sizeof(buf), "Gram tables need %.1f GB of device memory, %.1f GB are free", need / 1e9,
-		              static_cast<double>(freeB) / 1e9);
-		throw std::string(buf);
-	}
-
-	DeviceArray<double> mPool;
-	mPool.reserve(mDoubles * static_cast<size_t>(units));
-	GSB_CUDA(cudaMemsetAsync(mPool.ptr, 0, mDoubles * static_cast<size_t>(units) * sizeof(double), e->stream));
-	std::vector<const double*> unitPtrs(static_cast<size_t>(units));
-	std::vector<double*> outPtrs(static_cast<size_t>(units));
-	std::vector<int> unitLd(static_cast<size_t>(units)), unitRows(static_cast<size_t>(units));
-	std::vector<const double*> mOfBlock(static_cast<size_t>(std::max(nblocks, 1)), nullptr);
-	double flops = 0.0;
-	for (int u = 0; u < units; ++u) {
-		outPtrs[static_cast<size_t>(u)] = mPool.ptr + mDoubles * static_cast<size_t>(u);
+	mPool.reserve(mDoubles * static_cast<size_t>(cnt));
+	GSB_CUDA(cudaMemsetAsync(mPool.ptr, 0, mDoubles * static_cast<size_t>(cnt) * sizeof(double), e->stream));
+	std::vector<const double*> unitPtrs(static_cast<size_t>(cnt));
+	std::vector<int> unitLd(static_cast<size_t>(cnt)), unitRows(static_cast<size_t>(cnt));
+	outPtrs.assign(static_cast<size_t>(cnt), nullptr);
+	for (int i = 0; i < cnt; ++i) {
+		const int u = u0 + i;
+		outPtrs[static_cast<size_t>(i)] = mPool.ptr + mDoubles * static_cast<size_t>(i);
 		if (u == 0) {
-			unitPtrs[0] = e->zpool.ptr;
-			unitLd[0] = ldz;
-			unitRows[0] = ldz;
+			unitPtrs[static_cast<size_t>(i)] = e->zpool.ptr;
+			unitLd[static_cast<size_t>(i)] = e->ldz;
+			unitRows[static_cast<size_t>(i)] = e->ldz;
 			flops += static_cast<double>(n) * P2 * (P2 + 1.0);
 		} else {
-			const int b = unitBlocks[static_cast<size_t>(u - 1)];
-			const gsb::BlockDesc& d = bdesc[static_cast<size_t>(b)];
-			unitPtrs[static_cast<size_t>(u)] = e->zpool.ptr + d.zOff;
-			unitLd[static_cast<size_t>(u)] = d.ld;
-			unitRows[static_cast<size_t>(u)] = d.ld;
-			mOfBlock[static_cast<size_t>(b)] = outPtrs[static_cast<size_t>(u)];
+			const gsb::BlockDesc& d = e->blockDesc[static_cast<size_t>(e->unitBlocks[static_cast<size_t>(u - 1)])];
+			unitPtrs[static_cast<size_t>(i)] = e->zpool.ptr + d.zOff;
+			unitLd[static_cast<size_t>(i)] = d.ld;
+			unitRows[static_cast<size_t>(i)] = d.ld;
 			flops += static_cast<double>(d.nrows) * P2 * (P2 + 1.0);
 		}
 	}
-	DeviceArray<const double*> dUnitPtrs, dMOfBlock;
-	DeviceArray<double*> dOutPtrs;
-	DeviceArray<int> dUnitLd, dUnitRows, dExclIndex, dExclCount, dFitIds, dFitNtr;
-	DeviceArray<unsigned long long> dGramOffs;
-	DeviceArray<double> dYm;
+	DeviceArray<const double*> dUnitPtrs;
+	DeviceArray<int> dUnitLd, dUnitRows;
 	dUnitPtrs.upload(unitPtrs, e->stream);
 	dOutPtrs.upload(outPtrs, e->stream);
 	dUnitLd.upload(unitLd, e->stream);
 	dUnitRows.upload(unitRows, e->stream);
-	dMOfBlock.upload(mOfBlock, e->stream);
-
-	GSB_CUDA(cudaEventRecord(e->ev[0], e->stream));
 	// grid.y is limited to 65535 units per launch
-	for (int u0 = 0; u0 < units; u0 += 32768) {
-		const int cnt = std::min(32768, units - u0);
-		gsb::launchGramSyrk(dUnitPtrs.ptr + u0, dUnitLd.ptr + u0, dUnitRows.ptr + u0, dOutPtrs.ptr + u0, cnt, P2, ldm, e->stream);
+	for (int c0 = 0; c0 < cnt; c0 += 32768) {
+		const int c = std::min(32768, cnt - c0);
+		gsb::launchGramSyrk(dUnitPtrs.ptr + c0, dUnitLd.ptr + c0, dUnitRows.ptr + c0, dOutPtrs.ptr + c0, c, P2, ldm, e->stream);
 	}
 	GSB_CUDA(cudaGetLastError());
-	GSB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+	GSB_CUDA(cudaStreamSynchronize(e->stream)); // the host arrays above go out of scope
+}
 
-	// ---- per training set: centred Gram (packed), s0, xm, ym
-	std::vector<int> exclIndex(static_cast<size_t>(nfits) * 2, 0), exclCount(static_cast<size_t>(nfits), 0);
-	std::vector<int> fitIds(static_cast<size_t>(nfits)), fitNtr(static_cast<size_t>(nfits));
-	std::vector<unsigned long long> gramOffs(static_cast<size_t>(nfits));
-	for (int f = 0; f < nfits; ++f) {
-		const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
-		exclCount[static_cast<size_t>(f)] = static_cast<int>(pf.exclBlocks.size());
-		for (size_t x = 0; x < pf.exclBlocks.size(); ++x) exclIndex[static_cast<size_t>(f) * 2 + x] = pf.exclBlocks[x];
-		fitIds[static_cast<size_t>(f)] = f;
-		fitNtr[static_cast<size_t>(f)] = static_cast<int>(pf.rows.size());
-		gramOffs[static_cast<size_t>(f)] = static_cast<unsigned long long>(triP) * static_cast<unsigned long long>(f);
-	}
-	dExclIndex.upload(exclIndex, e->stream);
-	dExclCount.upload(exclCount, e->stream);
-	dFitIds.upload(fitIds, e->stream);
-	dFitNtr.upload(fitNtr, e->stream);
-	dGramOffs.upload(gramOffs, e->stream);
-	dYm.reserve(static_cast<size_t>(nfits));
-	e->gram.reserve(gramDoubles);
-	e->s0.reserve(static_cast<size_t>(nfits) * p);
-	e->xm.reserve(static_cast<size_t>(nfits) * p);
-	for (int f0 = 0; f0 < nfits; f0 += 32768) {
-		const int cnt = std::min(32768, nfits - f0);
-		gsb::launchGramCombine(mPool.ptr, dMOfBlock.ptr, dExclIndex.ptr + static_cast<size_t>(f0) * 2, dExclCount.ptr + f0,
-		                       dFitIds.ptr + f0, dFitNtr.ptr + f0, cnt, p, ldm, e->gram.ptr, dGramOffs.ptr, e->s0.ptr,
-		                       e->xm.ptr, dYm.ptr, e->stream);
-	}
+// LMEvaluator: the centred Gram of ALL rows over all columns (packed), s0 and the column means: what K3 gathers from
+void buildAllRowsGram(gsb_engine* e) {
+	const int n = e->n, p = e->p, P2 = p + 2, ldm = roundUp(P2, 4);
+	const size_t triP = static_cast<size_t>(gsb::tri(static_cast<unsigned long long>(p)));
+	DeviceArray<double> mPool, dYm;
+	DeviceArray<double*> dOutPtrs;
+	std::vector<double*> outPtrs;
+	double flops = 0.0;
+	GSB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+	syrkUnits(e, 0, 1, mPool, dOutPtrs, outPtrs, flops);
+	GSB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+	DeviceArray<const double*> dMOfBlock;
+	DeviceArray<int> dZero2, dZero1, dN1;
+	DeviceArray<unsigned long long> dOff0;
+	const double* noBlock = nullptr;
+	const int zeros2[2] = {0, 0};
+	const int zero1 = 0;
+	const unsigned long long off0 = 0;
+	dMOfBlock.upload(&noBlock, 1, e->stream);
+	dZero2.upload(zeros2, 2, e->stream);
+	dZero1.upload(&zero1, 1, e->stream);
+	dN1.upload(&n, 1, e->stream);
+	dOff0.upload(&off0, 1, e->stream);
+	dYm.reserve(1);
+	e->gram.reserve(triP);
+	e->s0.reserve(static_cast<size_t>(p));
+	e->xm.reserve(static_cast<size_t>(p));
+	gsb::launchGramCombine(mPool.ptr, dMOfBlock.ptr, dZero2.ptr, dZero1.ptr, dZero1.ptr, dN1.ptr, 1, p, ldm, e->gram.ptr, dOff0.ptr,
+	                       e->s0.ptr, e->xm.ptr, dYm.ptr, e->stream);
 	GSB_CUDA(cudaGetLastError());
 	GSB_CUDA(cudaEventRecord(e->ev[2], e->stream));
-	std::vector<double> ym(static_cast<size_t>(nfits));
-	GSB_CUDA(cudaMemcpyAsync(ym.data(), dYm.ptr, static_cast<size_t>(nfits) * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+	GSB_CUDA(cudaMemcpyAsync(&e->ymAllRows, dYm.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
 	GSB_CUDA(cudaStreamSynchronize(e->stream));
 	float msSyrk = 0.f, msAll = 0.f;
 	GSB_CUDA(cudaEventElapsedTime(&msSyrk, e->ev[0], e->ev[1]));
 	GSB_CUDA(cudaEventElapsedTime(&msAll, e->ev[0], e->ev[2]));
+	e->info.setup_ms = msAll;
+	e->info.gram_dmma_ms = msSyrk;
+	e->info.gram_flops = flops;
+	e->info.gram_bytes = static_cast<int64_t>((triP + 2 * static_cast<size_t>(p)) * sizeof(double));
+}
 
-	// ---- descriptors
-	std::vector<gsb::FitDesc> fdesc(static_cast<size_t>(nfits));
-	for (int f = 0; f < nfits; ++f) {
-		const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
-		gsb::FitDesc& d = fdesc[static_cast<size_t>(f)];
-		d.gramOff = gramOffs[static_cast<size_t>(f)];
-		d.ym = ym[static_cast<size_t>(f)];
-		d.ntr = static_cast<int>(pf.rows.size());
-		d.taskBegin = pf.taskBegin;
-		d.taskCount = pf.taskCount;
-		d.pad = 0;
+// K0 for the per-fit Gram-space kernel, built the first time a subset-size class needs it: the FP64 tensor-core SYRK
+// M_u = Z_u'Z_u of every unit (the full data and each block some training set excludes), the units interleaved per packed
+// entry (gram_build.cu).  The SYRK scratch is walked in chunks of units that fit beside the tables.
+void buildUnitTables(gsb_engine* e) {
+	if (e->unitsReady) return;
+	const int p = e->p, P2 = p + 2, ldm = roundUp(P2, 4);
+	const gsb::FitPlan& plan = e->plan;
+	const int nfits = static_cast<int>(plan.fits.size());
+	const int units = 1 + static_cast<int>(e->unitBlocks.size());
+	const int upad = roundUp(units, 4);
+	const size_t mDoubles = static_cast<size_t>(P2) * ldm;
+	const size_t triP = static_cast<size_t>(gsb::tri(static_cast<unsigned long long>(p)));
+	const double tableBytes = 8.0 * (static_cast<double>(triP) + 2.0 * p) * upad;
+	size_t freeB = 0, totalB = 0;
+	GSB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+	const double room = 0.90 * static_cast<double>(freeB) - tableBytes;
+	if (room < 8.0 * static_cast<double>(mDoubles)) {
+		char buf[256];
+		std::snprintf(buf, sizeof(buf), "the Gram tables of the per-fit kernel need %.1f GB of device memory, %.1f GB are free",
+		              (tableBytes + 8.0 * static_cast<double>(mDoubles)) / 1e9, static_cast<double>(freeB) / 1e9);
+		throw std::string(buf);
 	}
-	std::vector<gsb::TaskDesc> tdesc(plan.tasks.size());
-	for (size_t t = 0; t < plan.tasks.size(); ++t) {
-		tdesc[t].block = plan.tasks[t].block;
-		tdesc[t].kind = plan.tasks[t].kind;
-		tdesc[t].dest = plan.tasks[t].dest;
-		tdesc[t].pad = 0;
-	}
-	e->maxTasks = 0;
-	e->maxBlockLd = 0;
-	for (int f = 0; f < nfits; ++f) e->maxTasks = std::max(e->maxTasks, plan.fits[static_cast<size_t>(f)].taskCount);
-	for (size_t t = 0; t < plan.tasks.size(); ++t) e->maxBlockLd = std::max(e->maxBlockLd, bdesc[static_cast<size_t>(plan.tasks[t].block)].ld);
-	e->fits.upload(fdesc, e->stream);
-	e->tasks.upload(tdesc, e->stream);
-	e->blocks.upload(bdesc, e->stream);
-	e->outerRows.upload(plan.outerRows, e->stream);
-	e->ymAllRows = nfits > 0 ? ym[0] : 0.0;
-	GSB_CUDA(cudaStreamSynchronize(e->stream));
-
-	// ---- K1b: fits grouped per replication, (block, fit) pairs, and the packed full-data Gram
-	e->batchGroups = 0;
-	e->batchMaxK = 0;
-	if (e->cfg.evaluator != GSB_EVAL_LM && nfits > 0) {
-		const int I = std::max(1, plan.innerPerGroup), O = std::max(1, plan.groupsPerReplication);
-		std::vector<int> fitRep(static_cast<size_t>(nfits), 1 << 30);
-		for (size_t t = 0; t < plan.tasks.size(); ++t) {
-			const gsb::PlanTask& pt = plan.tasks[t];
-			const int g = pt.kind == gsb::TASK_OUTER ? pt.dest : pt.dest / I;
-			fitRep[static_cast<size_t>(pt.fit)] = std::min(fitRep[static_cast<size_t>(pt.fit)], g / O);
-		}
-		std::vector<int> order(static_cast<size_t>(nfits));
-		for (int f = 0; f < nfits; ++f) order[static_cast<size_t>(f)] = f;
-		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fitRep[static_cast<size_t>(a)] < fitRep[static_cast<size_t>(b)]; });
-		std::vector<int> groupFits;
-		std::vector<gsb::BatchGroup> groups;
-		std::vector<gsb::BatchPairGroup> pgs;
-		std::vector<gsb::BatchPair> pairs;
-		std::vector<int2> units;
-		int nfMax = 0, maxPairs = 1, maxSlabs = 0;
-		struct Entry { int block, fitLocal, corr, kind, dest; };
-		for (size_t b0 = 0; b0 < order.size();) {
-			size_t b1 = b0;
-			while (b1 < order.size() && fitRep[static_cast<size_t>(order[b1])] == fitRep[static_cast<size_t>(order[b0])]) ++b1;
-			const size_t count = b1 - b0, chunks = (count + 15) / 16, per = (count + chunks - 1) / chunks;
-			for (size_t c0 = b0; c0 < b1; c0 += per) {
-				const size_t c1 = std::min(b1, c0 + per);
-				gsb::BatchGroup g;
-				g.fitBegin = static_cast<int>(groupFits.size());
-				g.nfits = static_cast<int>(c1 - c0);
-				g.pgBegin = static_cast<int>(pgs.size());
-				g.unitBegin = static_cast<int>(units.size());
-				g.pad0 = g.pad1 = 0;
-				std::vector<Entry> entries;
-				for (size_t x = c0; x < c1; ++x) {
-					const int fit = order[x], fl = static_cast<int>(x - c0);
-					groupFits.push_back(fit);
-					const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(fit)];
-					const size_t first = entries.size();
-					for (size_t q = 0; q < pf.exclBlocks.size(); ++q) {
-						Entry en = {pf.exclBlocks[q], fl, 1, -1, 0};
-						entries.push_back(en);
-					}
-					for (int t = pf.taskBegin; t < pf.taskBegin + pf.taskCount; ++t) {
-						const gsb::PlanTask& pt = plan.tasks[static_cast<size_t>(t)];
-						bool attached = false;
-						for (size_t q = first; q < entries.size() && !attached; ++q) {
-							if (entries[q].block == pt.block && entries[q].kind < 0) {
-								entries[q].kind = pt.kind;
-								entries[q].dest = pt.dest;
-								attached = true;
-							}
-						}
-						if (!attached) {
-							Entry en = {pt.block, fl, 0, pt.kind, pt.dest};
-							entries.push_back(en);
-						}
-					}
-				}
-				std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.block < b.block; });
-				int slabs = 0;
-				for (size_t q0 = 0; q0 < entries.size();) {
-					size_t q1 = q0;
-					while (q1 < entries.size() && q1 - q0 < 8 && entries[q1].block == entries[q0].block) ++q1;
-					gsb::BatchPairGroup pg;
-					pg.block = entries[q0].block;
-					pg.npairs = static_cast<int>(q1 - q0);
-					pg.pairBegin = static_cast<int>(pairs.size());
-					pg.slabBegin = slabs;
-					pg.nslabs = (bdesc[static_cast<size_t>(pg.block)].ld + 31) / 32;
-					pg.ncorr = 0;
-					pg.pad0 = pg.pad1 = 0;
-					for (size_t q = q0; q < q1; ++q) {
-						gsb::BatchPair bp = {entries[q].fitLocal, entries[q].corr, entries[q].kind, entries[q].dest};
-						pairs.push_back(bp);
-						pg.ncorr += entries[q].corr ? 1 : 0;
-					}
-					for (int sl = 0; sl < pg.nslabs; ++sl) units.push_back(make_int2(static_cast<int>(pgs.size()), sl));
-					slabs += pg.nslabs;
-					maxPairs = std::max(maxPairs, pg.npairs);
-					pgs.push_back(pg);
-					q0 = q1;
-				}
-				g.npg = static_cast<int>(pgs.size()) - g.pgBegin;
-				g.nunits = static_cast<int>(units.size()) - g.unitBegin;
-				maxSlabs = std::max(maxSlabs, slabs);
-				nfMax = std::max(nfMax, g.nfits);
-				groups.push_back(g);
-			}
-			b0 = b1;
-		}
-		e->batchPgp = roundUp(maxPairs, 2);
-		e->batchUDoubles = maxSlabs * 32 * e->batchPgp;
-		e->batchNfMax = nfMax;
-		e->batchGroups = static_cast<int>(groups.size());
-		e->batchMaxK = gsb::batchKernelMaxK(nfMax, e->batchUDoubles, e->smemLimit);
-		e->bGroupFits.upload(groupFits, e->stream);
-		e->bGroups.upload(groups, e->stream);
-		e->bPgs.upload(pgs, e->stream);
-		e->bPairs.upload(pairs, e->stream);
-		e->bUnits.upload(units, e->stream);
-
-		// packed Z'Z over all rows: the combination kernel with no excluded block
-		DeviceArray<int> dZero2, dZero1, dN1;
-		DeviceArray<unsigned long long> dOff0;
-		DeviceArray<double> dS0x, dXmx, dYmx;
-		const int zeros2[2] = {0, 0};
-		const int zero1 = 0;
-		const unsigned long long off0 = 0;
-		dZero2.upload(zeros2, 2, e->stream);
-		dZero1.upload(&zero1, 1, e->stream);
-		dN1.upload(&n, 1, e->stream);
-		dOff0.upload(&off0, 1, e->stream);
-		dS0x.reserve(static_cast<size_t>(p));
-		dXmx.reserve(static_cast<size_t>(p));
-		dYmx.reserve(1);
-		e->gfull.reserve(triP);
-		gsb::launchGramCombine(mPool.ptr, dMOfBlock.ptr, dZero2.ptr, dZero1.ptr, dZero1.ptr, dN1.ptr, 1, p, ldm, e->gfull.ptr, dOff0.ptr,
-		                       dS0x.ptr, dXmx.ptr, dYmx.ptr, e->stream);
+	int chunk = static_cast<int>(std::min<double>(units, std::floor(room / (8.0 * static_cast<double>(mDoubles)))));
+	chunk = std::max(1, std::min(chunk, 32768));
+	e->unitTab.reserve(triP * static_cast<size_t>(upad));
+	e->unitSum.reserve(static_cast<size_t>(p) * upad);
+	e->unitXy.reserve(static_cast<size_t>(p) * upad);
+	std::vector<double> unitSy(static_cast<size_t>(units), 0.0);
+	DeviceArray<double> mPool;
+	DeviceArray<double*> dOutPtrs;
+	std::vector<double*> outPtrs;
+	double flops = 0.0;
+	float msSyrkAll = 0.f, msAll = 0.f;
+	for (int u0 = 0; u0 < units; u0 += chunk) {
+		const int cnt = std::min(chunk, units - u0);
+		GSB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+		syrkUnits(e, u0, cnt, mPool, dOutPtrs, outPtrs, flops);
+		GSB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+		gsb::launchUnitInterleave(reinterpret_cast<const double* const*>(dOutPtrs.ptr), u0, cnt, p, ldm, upad, e->unitTab.ptr,
+		                          e->unitSum.ptr, e->unitXy.ptr, e->stream);
 		GSB_CUDA(cudaGetLastError());
+		GSB_CUDA(cudaEventRecord(e->ev[2], e->stream));
+		// sum of yc over the rows of each unit: row "ones", column "y" of its moment matrix
+		for (int i = 0; i < cnt; ++i) {
+			GSB_CUDA(cudaMemcpyAsync(&unitSy[static_cast<size_t>(u0 + i)], outPtrs[static_cast<size_t>(i)] + static_cast<size_t>(p + 1) * ldm + p,
+			                         sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+		}
 		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		float a = 0.f, b = 0.f;
+		GSB_CUDA(cudaEventElapsedTime(&a, e->ev[0], e->ev[1]));
+		GSB_CUDA(cudaEventElapsedTime(&b, e->ev[0], e->ev[2]));
+		msSyrkAll += a;
+		msAll += b;
 	}
+	mPool.release();
+	// training sets as full data minus excluded units; every moment is combined in this order (full, - first, - second)
+	std::vector<gsb::PackFit> pf(static_cast<size_t>(nfits));
+	for (int f = 0; f < nfits; ++f) {
+		const gsb::PlanFit& fit = plan.fits[static_cast<size_t>(f)];
+		gsb::PackFit& d = pf[static_cast<size_t>(f)];
+		d.u1 = d.u2 = -1;
+		double sy = unitSy[0];
+		for (size_t x = 0; x < fit.exclBlocks.size() && x < 2; ++x) {
+			const int u = e->unitOfBlock[static_cast<size_t>(fit.exclBlocks[x])];
+			(x == 0 ? d.u1 : d.u2) = u;
+			sy -= unitSy[static_cast<size_t>(u)];
+		}
+		d.nT = static_cast<double>(fit.rows.size());
+		d.sy = sy;
+	}
+	e->packFits.upload(pf, e->stream);
+	GSB_CUDA(cudaStreamSynchronize(e->stream));
+	e->upad = upad;
+	e->unitsReady = true;
+	e->info.setup_ms += msAll;
+	e->info.gram_dmma_ms += msSyrkAll;
+	e->info.gram_flops += flops;
+	e->info.gram_bytes = static_cast<int64_t>(tableBytes);
+}
 
+// K1x tables, built the first time a subset-size class is given to the score-space kernel (since K1k: plans with
+// 160 < n <= 192 rows, or GSB_NO_KSPACE=1)
+void buildScoreTables(gsb_engine* e) {
+	if (e->scoresTried) return;
+	e->scoresTried = true;
+	const int n = e->n, P2 = e->p + 2, ldz = e->ldz;
+	const gsb::FitPlan& plan = e->plan;
+	const int nfits = static_cast<int>(plan.fits.size());
 	// ---- K1x: atoms (disjoint row blocks) per replication, fits as masks of excluded atoms
 	e->scoreGroups8 = e->scoreGroups16 = 0;
-	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && !std::getenv("GSB_NO_SCORES")) {
+	if (e->cfg.evaluator == GSB_EVAL_PLS_CV && nfits > 0 && !e->env.noScores) {
 		const int I = std::max(1, plan.innerPerGroup), O = std::max(1, plan.groupsPerReplication);
 		const int R = std::max(1, plan.groups / O);
 		std::vector<int> fitRep(static_cast<size_t>(nfits), 1 << 30);
@@ -729,11 +632,107 @@ void prepareDevice(gsb_engine* e) {
 		}
 	}
 
+}
+
+// K0 at prepare time: the globally centred data, contiguous copies of the held-out blocks, the descriptors of the fit plan
+// and the K1k row masks.  The moment tables of the per-fit kernel (buildUnitTables) and the K1x copies (buildScoreTables)
+// are built when a subset-size class first needs them; the LM evaluator's all-rows Gram is built here.
+void prepareDevice(gsb_engine* e) {
+	ensureDevice(e);
+	const int n = e->n, p = e->p, P2 = p + 2;
+	const gsb::FitPlan& plan = e->plan;
+	const int nfits = static_cast<int>(plan.fits.size());
+	const int nblocks = static_cast<int>(plan.blocks.size());
+	const int ldz = roundUp(n, 4);
+	e->unitsReady = e->scoresTried = false;
+	e->scoreGroups8 = e->scoreGroups16 = 0;
+	std::memset(&e->info, 0, sizeof(e->info));
+
+	// ---- held-out row blocks, each a contiguous column-major copy (coalesced prediction reads)
+	std::vector<gsb::BlockDesc>& bdesc = e->blockDesc;
+	bdesc.assign(static_cast<size_t>(nblocks), gsb::BlockDesc());
+	std::vector<uint32_t> blockRows;
+	std::vector<size_t> blockRowOff(static_cast<size_t>(nblocks), 0);
+	size_t pool = static_cast<size_t>(ldz) * P2;
+	for (int b = 0; b < nblocks; ++b) {
+		const gsb::PlanBlock& pb = plan.blocks[static_cast<size_t>(b)];
+		gsb::BlockDesc& d = bdesc[static_cast<size_t>(b)];
+		d.nrows = static_cast<int>(pb.rows.size());
+		if (pb.allRows) {
+			d.zOff = 0;
+			d.ld = ldz;
+		} else {
+			d.ld = roundUp(d.nrows, 4);
+			d.zOff = pool;
+			pool += static_cast<size_t>(d.ld) * P2;
+			blockRowOff[static_cast<size_t>(b)] = blockRows.size();
+			blockRows.insert(blockRows.end(), pb.rows.begin(), pb.rows.end());
+		}
+	}
+	e->zReady = false;
+	uploadZ(e, pool);
+	DeviceArray<uint32_t> dRows;
+	dRows.upload(blockRows, e->stream);
+	for (int b = 0; b < nblocks; ++b) {
+		if (plan.blocks[static_cast<size_t>(b)].allRows) continue;
+		const gsb::BlockDesc& d = bdesc[static_cast<size_t>(b)];
+		gsb::launchBlockGather(e->zpool.ptr, ldz, P2, nullptr, dRows.ptr + blockRowOff[static_cast<size_t>(b)], d.nrows,
+		                       e->zpool.ptr + d.zOff, d.ld, e->stream);
+	}
+	GSB_CUDA(cudaGetLastError());
+	GSB_CUDA(cudaStreamSynchronize(e->stream));
+
+	// ---- units of the moment tables: the full data, then every block some fit excludes
+	e->unitOfBlock.assign(static_cast<size_t>(nblocks), -1);
+	e->unitBlocks.clear();
+	for (int f = 0; f < nfits; ++f) {
+		for (size_t x = 0; x < plan.fits[static_cast<size_t>(f)].exclBlocks.size(); ++x) {
+			const int b = plan.fits[static_cast<size_t>(f)].exclBlocks[x];
+			if (e->unitOfBlock[static_cast<size_t>(b)] < 0) {
+				e->unitBlocks.push_back(b);
+				e->unitOfBlock[static_cast<size_t>(b)] = static_cast<int>(e->unitBlocks.size());
+			}
+		}
+	}
+
+	// ---- descriptors
+	std::vector<gsb::FitDesc> fdesc(static_cast<size_t>(nfits));
+	for (int f = 0; f < nfits; ++f) {
+		const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
+		gsb::FitDesc& d = fdesc[static_cast<size_t>(f)];
+		// mean of the (globally centred) response over the training rows (src/PLSSimpls.cpp:28-49)
+		double sy = 0.0;
+		for (size_t i = 0; i < pf.rows.size(); ++i) sy += e->y[pf.rows[i]] - e->yMean;
+		d.ym = sy / static_cast<double>(std::max<size_t>(1, pf.rows.size()));
+		d.ntr = static_cast<int>(pf.rows.size());
+		d.taskBegin = pf.taskBegin;
+		d.taskCount = pf.taskCount;
+		d.pad = 0;
+	}
+	std::vector<gsb::TaskDesc> tdesc(plan.tasks.size());
+	for (size_t t = 0; t < plan.tasks.size(); ++t) {
+		tdesc[t].block = plan.tasks[t].block;
+		tdesc[t].kind = plan.tasks[t].kind;
+		tdesc[t].dest = plan.tasks[t].dest;
+		tdesc[t].pad = 0;
+	}
+	e->maxTasks = 0;
+	e->maxBlockLd = 0;
+	for (int f = 0; f < nfits; ++f) e->maxTasks = std::max(e->maxTasks, plan.fits[static_cast<size_t>(f)].taskCount);
+	for (size_t t = 0; t < plan.tasks.size(); ++t) e->maxBlockLd = std::max(e->maxBlockLd, bdesc[static_cast<size_t>(plan.tasks[t].block)].ld);
+	e->fits.upload(fdesc, e->stream);
+	e->tasks.upload(tdesc, e->stream);
+	e->blocks.upload(bdesc, e->stream);
+	e->outerRows.upload(plan.outerRows, e->stream);
+	GSB_CUDA(cudaStreamSynchronize(e->stream));
+
+	if (e->cfg.evaluator == GSB_EVAL_LM) buildAllRowsGram(e);
+
 	// ---- K1k: per-lane row masks (lane = row mod 32) of every distinct fit and prediction task
 	e->kspaceFits = 0;
 	// (PLS_CV and PLS_FIT: the all-rows refit of BICEvaluator is a fit whose "held-out" block is every row)
 	if ((e->cfg.evaluator == GSB_EVAL_PLS_CV || e->cfg.evaluator == GSB_EVAL_PLS_FIT) && nfits > 0 &&
-	    gsb::kspaceKernelFits(n, 1, e->smemLimit, 8) && !std::getenv("GSB_NO_KSPACE")) {
+	    gsb::kspaceKernelFits(n, 1, e->smemLimit, 8) && !e->env.noKspace) {
 		std::vector<gsb::KFitDesc> kf(static_cast<size_t>(nfits));
 		std::vector<gsb::KTaskDesc> kt(plan.tasks.size());
 		for (size_t t = 0; t < plan.tasks.size(); ++t) {
@@ -781,7 +780,6 @@ void prepareDevice(gsb_engine* e) {
 		e->kspaceFits = nfits;
 	}
 
-	mPool.release(); // give the SYRK scratch back before the population tables are allocated
 
 	gsb_info& inf = e->info;
 	inf.n = n; inf.p = p;
@@ -795,14 +793,99 @@ void prepareDevice(gsb_engine* e) {
 	inf.distinct_blocks = nblocks;
 	inf.prediction_tasks = static_cast<int32_t>(plan.tasks.size());
 	inf.sm_count = e->smCount;
-	inf.gram_bytes = static_cast<int64_t>((gramDoubles + 2 * static_cast<size_t>(nfits) * p) * sizeof(double));
 	inf.block_bytes = static_cast<int64_t>((pool - static_cast<size_t>(ldz) * P2) * sizeof(double));
 	inf.sdfact_effective = e->shape.sdfact;
-	inf.setup_ms = msAll;
-	inf.gram_dmma_ms = msSyrk;
-	inf.gram_flops = flops;
 	e->prepared = true;
 	e->populationReady = e->resultsReady = false;
+}
+
+// Which K1 kernel serves each subset-size class of the resident population, decided once per upload; builds the tables
+// a kernel needs the first time a class is given to it, and lays out the per-generation packed Grams of the per-fit kernel.
+void planBuckets(gsb_engine* e) {
+	const EnvFlags& env = e->env;
+	const int nfits = static_cast<int>(e->plan.fits.size());
+	const bool kspaceOn = e->kspaceFits > 0 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit, 8) && !env.noKspace;
+	// K1x configurations in order of preference (measured, profiles/kb_cfg.sh): the cost is dominated by a per-CTA,
+	// per-component overhead, so the fewest CTAs win: 16 fits per CTA, the stored loadings in the global scratch
+	// (vGlobal) as soon as that keeps the subset in one CTA, then clusters of 2 and 3 CTAs splitting the columns
+	static const int kScoreMinK = 40;
+	static const int kScoreCfg[8][3] = {{16, 1, 0}, {8, 1, 0}, {8, 1, 1}, {8, 2, 0}, {16, 2, 1}, {8, 2, 1}, {16, 3, 1}, {8, 3, 1}};
+	bool wantScores = false, wantFit = false;
+	// K1k takes every class above kspaceMinK (its cost per fit does not depend on the subset size)
+	for (size_t b = 0; b < e->buckets.size(); ++b) {
+		Bucket& bk = e->buckets[b];
+		bk.kernel = (kspaceOn && bk.kMax > env.kspaceMinK) ? BK_KSPACE : BK_FIT;
+		if (bk.kernel == BK_FIT && (bk.kMax > kScoreMinK || env.forcedNf > 0)) wantScores = true;
+	}
+	// the K1k classes must be contiguous at the top (one launch): a class below a per-fit class goes back to the per-fit kernel
+	bool top = true;
+	for (size_t b = e->buckets.size(); b-- > 0;) {
+		if (e->buckets[b].kernel != BK_KSPACE) top = false;
+		else if (!top) e->buckets[b].kernel = BK_FIT;
+	}
+	wantScores = wantScores && e->cfg.evaluator == GSB_EVAL_PLS_CV && e->tableA <= gsb::kScoreComponents && !env.noScores &&
+	             e->n <= 32 * gsb::kScoreMaxSlots;
+	if (wantScores) buildScoreTables(e);
+	const bool scoresOn = wantScores && e->scoreGroups8 > 0;
+	long long vTotal = 0;
+	for (size_t b = 0; b < e->buckets.size(); ++b) {
+		Bucket& bk = e->buckets[b];
+		if (bk.kernel != BK_FIT) continue;
+		if (scoresOn && env.forcedNf > 0 && bk.kMax <= gsb::scoreKernelMaxK(e->scoreNr, env.forcedNf, env.forcedCs, env.forcedVg, e->smemLimit)) {
+			bk.kernel = BK_SCORES;
+			bk.nf = env.forcedNf; bk.cs = env.forcedCs; bk.vg = env.forcedVg;
+		}
+		// small subsets: the per-fit kernel (one CTA per fit, many CTAs per SM) is faster below ~40 columns
+		for (int c = 0; scoresOn && env.forcedNf == 0 && bk.kMax > kScoreMinK && c < 8 && bk.kernel == BK_FIT; ++c) {
+			if (bk.kMax <= gsb::scoreKernelMaxK(e->scoreNr, kScoreCfg[c][0], kScoreCfg[c][1], kScoreCfg[c][2], e->smemLimit)) {
+				bk.kernel = BK_SCORES;
+				bk.nf = kScoreCfg[c][0]; bk.cs = kScoreCfg[c][1]; bk.vg = kScoreCfg[c][2];
+			}
+		}
+		if (bk.kernel == BK_SCORES && bk.vg) {
+			const long long groupsHere = bk.nf == 16 ? e->scoreGroups16 : e->scoreGroups8;
+			bk.vPerCta = gsb::scoreKernelScratchDoubles(bk.kMax, bk.nf, bk.cs);
+			bk.vOffset = vTotal;
+			bk.vSlots = gsb::scoreKernelScratchSlots(bk.kMax, bk.nf, bk.cs, e->scoreNr, groupsHere * bk.count * bk.cs);
+			vTotal += bk.vPerCta * (bk.vSlots < 0 ? -bk.vSlots : bk.vSlots);
+		}
+		if (bk.kernel == BK_FIT) wantFit = true;
+	}
+	if (vTotal > 0) e->scoreScratch.reserve(static_cast<size_t>(vTotal));
+
+	// per-fit kernel: one slab of packed Gram and one of vectors per (chromosome, training set)
+	e->hPackOff.reserve(static_cast<size_t>(e->npop) + 1);
+	e->hVecOff.reserve(static_cast<size_t>(e->npop) + 1);
+	for (int c = 0; c <= e->npop; ++c) e->hPackOff.ptr[c] = e->hVecOff.ptr[c] = 0ull;
+	if (!wantFit) return;
+	buildUnitTables(e);
+	unsigned long long packTotal = 0, vecTotal = 0;
+	for (size_t b = 0; b < e->buckets.size(); ++b) {
+		const Bucket& bk = e->buckets[b];
+		if (bk.kernel != BK_FIT) continue;
+		for (int i = 0; i < bk.count; ++i) {
+			const int c = e->hBucket.ptr[bk.begin + i];
+			const unsigned long long k = e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c];
+			e->hPackOff.ptr[c] = packTotal;
+			e->hVecOff.ptr[c] = vecTotal;
+			packTotal += gsb::packedDoubles(k) * static_cast<unsigned long long>(nfits);
+			vecTotal += 2ull * ((k + 1ull) & ~1ull) * static_cast<unsigned long long>(nfits);
+		}
+	}
+	if (packTotal + vecTotal > e->gpack.capacity + e->pvec.capacity) {
+		size_t freeB = 0, totalB = 0;
+		GSB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+		const double need = 8.0 * static_cast<double>(packTotal + vecTotal);
+		const double have = static_cast<double>(freeB) + 8.0 * static_cast<double>(e->gpack.capacity + e->pvec.capacity);
+		if (need > 0.95 * have) {
+			char buf[256];
+			std::snprintf(buf, sizeof(buf), "the packed Grams of this population need %.1f GB of device memory, %.1f GB are free: evaluate it in smaller batches",
+			              need / 1e9, have / 1e9);
+			throw std::string(buf);
+		}
+	}
+	e->gpack.reserve(static_cast<size_t>(packTotal) + 2);
+	e->pvec.reserve(static_cast<size_t>(vecTotal) + 2);
 }
 
 int prepareChecked(gsb_engine* e) {
@@ -1029,30 +1112,36 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 		const int rc = prepareChecked(e);
 		if (rc != GSB_OK) return rc;
 	}
+	// validate the whole CSR before any resident state is touched
+	const int lmMaxK = std::min(gsb::olsKernelMaxK(e->smemLimit), e->n - 2);
+	for (int c = 0; c < npop; ++c) {
+		if (offsets[c + 1] < offsets[c]) return fail(e, GSB_ERR_INVALID_ARGUMENT, "population offsets must be non-decreasing");
+		const int k = static_cast<int>(offsets[c + 1] - offsets[c]);
+		for (uint32_t i = offsets[c]; i < offsets[c + 1]; ++i) {
+			if (idx[i] >= static_cast<uint32_t>(e->p)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "column index out of range");
+		}
+		if (e->cfg.evaluator == GSB_EVAL_LM && k > lmMaxK) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the OLS kernel (k <= min(n - 2, shared-memory limit))");
+		if (e->cfg.evaluator != GSB_EVAL_LM && k > 1024) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the SIMPLS kernel (k <= 1024)");
+	}
+	e->populationReady = e->resultsReady = false;
 	try {
 		ensureDevice(e);
 		const size_t total = npop > 0 ? offsets[npop] : 0;
 		e->hIdx.reserve(total + 1);
 		e->hOffsets.reserve(static_cast<size_t>(npop) + 1);
 		e->hBucket.reserve(static_cast<size_t>(npop) + 1);
-		const int lmMaxK = std::min(gsb::olsKernelMaxK(e->smemLimit), e->n - 2);
 		int kMaxPop = 0;
 		for (int c = 0; c < npop; ++c) {
-			if (offsets[c + 1] < offsets[c]) return fail(e, GSB_ERR_INVALID_ARGUMENT, "population offsets must be non-decreasing");
 			const uint32_t b = offsets[c], en = offsets[c + 1];
-			const int k = static_cast<int>(en - b);
 			bool sorted = true;
 			for (uint32_t i = b; i < en; ++i) {
 				const uint32_t v = idx[i];
-				if (v >= static_cast<uint32_t>(e->p)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "column index out of range");
 				if (i > b && v < idx[i - 1]) sorted = false;
 				e->hIdx.ptr[i] = v;
 			}
 			if (!sorted) std::sort(e->hIdx.ptr + b, e->hIdx.ptr + en); // the fit does not depend on the column order
 			e->hOffsets.ptr[c] = b;
-			kMaxPop = std::max(kMaxPop, k);
-			if (e->cfg.evaluator == GSB_EVAL_LM && k > lmMaxK) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the OLS kernel (k <= min(n - 2, shared-memory limit))");
-			if (e->cfg.evaluator != GSB_EVAL_LM && k > 1024) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the SIMPLS kernel (k <= 1024)");
+			kMaxPop = std::max(kMaxPop, static_cast<int>(en - b));
 		}
 		e->hOffsets.ptr[npop] = static_cast<uint32_t>(total);
 
@@ -1068,7 +1157,8 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 			const int k = static_cast<int>(offsets[order[i] + 1] - offsets[order[i]]);
 			const int cls = bucketCeil(k);
 			if (e->buckets.empty() || bucketCeil(e->buckets.back().kMax) != cls) {
-				Bucket b = {static_cast<int>(i), 0, 0};
+				Bucket b = Bucket();
+				b.begin = static_cast<int>(i);
 				e->buckets.push_back(b);
 			}
 			e->buckets.back().count += 1;
@@ -1079,10 +1169,15 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 		e->npop = npop;
 		e->kMaxPop = kMaxPop;
 		e->tableA = std::max(1, std::min(e->shape.maxNComp, kMaxPop));
+		if (e->cfg.evaluator != GSB_EVAL_LM) planBuckets(e);
 		GSB_CUDA(cudaEventRecord(e->ev[0], e->stream));
 		e->dIdx.upload(e->hIdx.ptr, total, e->stream);
 		e->dOffsets.upload(e->hOffsets.ptr, static_cast<size_t>(npop) + 1, e->stream);
 		e->dBucket.upload(e->hBucket.ptr, order.size(), e->stream);
+		if (e->cfg.evaluator != GSB_EVAL_LM) {
+			e->dPackOff.upload(e->hPackOff.ptr, static_cast<size_t>(npop) + 1, e->stream);
+			e->dVecOff.upload(e->hVecOff.ptr, static_cast<size_t>(npop) + 1, e->stream);
+		}
 		GSB_CUDA(cudaEventRecord(e->ev[1], e->stream));
 		e->dFitness.reserve(static_cast<size_t>(npop));
 		e->dStatus.reserve(static_cast<size_t>(npop));
@@ -1099,6 +1194,8 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 		e->resultsReady = false;
 	} catch (const CudaFailure& f) {
 		return failCuda(e, f);
+	} catch (const std::string& msg) {
+		return fail(e, GSB_ERR_MEMORY, msg);
 	} catch (const std::bad_alloc&) {
 		return fail(e, GSB_ERR_MEMORY, "host allocation failed");
 	}
@@ -1142,101 +1239,25 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
 		} else {
 			const int innerDests = e->plan.groups * e->plan.innerPerGroup;
+			const EnvFlags& env = e->env;
 			// largest subsets first, classes dealt round-robin to the side streams (fork / join on events)
-			const int nside = (e->buckets.size() > 1 && !std::getenv("GSB_SERIAL")) ? gsb_engine::kSideStreams : 0;
+			const int nside = (e->buckets.size() > 1 && !env.serial) ? gsb_engine::kSideStreams : 0;
 			if (nside) {
 				GSB_CUDA(cudaEventRecord(e->evFork, e->stream));
 				for (int i = 0; i < nside; ++i) GSB_CUDA(cudaStreamWaitEvent(e->side[i], e->evFork, 0));
 			}
-			// size classes whose packed Gram exceeds shared memory spill their last rows to a global scratch
-			std::vector<long long> spillPerCta(e->buckets.size(), 0), spillOffset(e->buckets.size(), 0);
-			long long spillTotal = 0;
-			// size classes the replication-batched kernel takes (K1b): every group of fits of a chromosome in one CTA
-			const bool batchOn = e->batchGroups > 0 && e->tableA <= gsb::kBatchComponents && std::getenv("GSB_BATCH");
-			std::vector<char> useBatch(e->buckets.size(), 0);
-			std::vector<long long> scratchPerCta(e->buckets.size(), 0), scratchOffset(e->buckets.size(), 0);
-			long long scratchTotal = 0;
-			// K1x configurations in order of preference (measured, profiles/kb_cfg.sh): the cost is dominated by a per-CTA,
-			// per-component overhead, so the fewest CTAs win: 16 fits per CTA, the stored loadings in the global scratch
-			// (vGlobal) as soon as that keeps the subset in one CTA, then clusters of 2 and 3 CTAs splitting the columns
-			const bool scoresOn = e->scoreGroups8 > 0 && e->tableA <= gsb::kScoreComponents && !std::getenv("GSB_NO_SCORES");
-			static const int kScoreMinK = 40;
-			static const int kScoreCfg[8][3] = {{16, 1, 0}, {8, 1, 0}, {8, 1, 1}, {8, 2, 0}, {16, 2, 1}, {8, 2, 1}, {16, 3, 1}, {8, 3, 1}};
-			std::vector<char> useScores(e->buckets.size(), 0);
-			std::vector<int> scoreNf(e->buckets.size(), 0), scoreCs(e->buckets.size(), 0), scoreVg(e->buckets.size(), 0);
-			std::vector<long long> vPerCta(e->buckets.size(), 0), vOffset(e->buckets.size(), 0);
-			std::vector<int> vSlots(e->buckets.size(), 0);
-			long long vTotal = 0;
-			int forcedNf = 0, forcedCs = 0, forcedVg = 0; // GSB_SCORE_CFG=nf,cs,vg: profiling aid
-			int desyncMode = 0;
-			if (const char* ds = std::getenv("GSB_DESYNC")) desyncMode = std::atoi(ds);
-			if (const char* fc = std::getenv("GSB_SCORE_CFG")) std::sscanf(fc, "%d,%d,%d", &forcedNf, &forcedCs, &forcedVg);
 			// K1k takes every size class above kspaceMinK in ONE launch (its cost per fit does not depend on the subset
-			// size; below, the per-fit and score-space kernels are cheaper): the classes are contiguous in dBucket
-			const bool kspaceOn = e->kspaceFits > 0 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit, 8) && !std::getenv("GSB_NO_KSPACE");
-			// 8 fits per pass.  GSB_KSPACE_NF=16: 16 fits per pass (two tensor-core column tiles on every fragment of K, the
-			// fits' stored vectors in tensor memory; needs n <= 152) -- measured no faster (1.28 vs 1.26 ms per 296
-			// chromosomes): the warp-local phases are bound by FP64 / shuffle issue, not by latency, so twice the warps
-			// take twice the time; kept as a tested option
-			int kspaceNf = 8;
-			if (const char* nfv = std::getenv("GSB_KSPACE_NF")) {
-				if (std::atoi(nfv) == 16 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit, 16)) kspaceNf = 16;
-			}
-			int kspaceMinK = 40, kspaceSplit = 0;
-			if (const char* mk = std::getenv("GSB_KSPACE_MINK")) kspaceMinK = std::atoi(mk);
-			if (const char* sp = std::getenv("GSB_KSPACE_SPLIT")) kspaceSplit = std::atoi(sp);
-			std::vector<char> useKspace(e->buckets.size(), 0);
+			// size; below, the per-fit kernel is cheaper): the classes are contiguous in dBucket
 			size_t kspaceFirst = e->buckets.size();
-			for (size_t b = e->buckets.size(); kspaceOn && b-- > 0;) {
-				if (e->buckets[b].kMax <= kspaceMinK) break;
-				useKspace[b] = 1;
+			for (size_t b = e->buckets.size(); b-- > 0;) {
+				if (e->buckets[b].kernel != BK_KSPACE) break;
 				kspaceFirst = b;
 			}
-			for (size_t b = 0; b < e->buckets.size(); ++b) {
-				if (useKspace[b]) continue;
-				if (scoresOn && forcedNf > 0 && e->buckets[b].kMax <= gsb::scoreKernelMaxK(e->scoreNr, forcedNf, forcedCs, forcedVg, e->smemLimit)) {
-					useScores[b] = 1;
-					scoreNf[b] = forcedNf;
-					scoreCs[b] = forcedCs;
-					scoreVg[b] = forcedVg;
-				}
-				// small subsets: the per-fit kernel (one CTA per fit, many CTAs per SM) is faster below ~40 columns
-				const bool small = e->buckets[b].kMax <= kScoreMinK;
-				for (int c = 0; scoresOn && forcedNf == 0 && !small && c < 8 && !useScores[b]; ++c) {
-					if (e->buckets[b].kMax <= gsb::scoreKernelMaxK(e->scoreNr, kScoreCfg[c][0], kScoreCfg[c][1], kScoreCfg[c][2], e->smemLimit)) {
-						useScores[b] = 1;
-						scoreNf[b] = kScoreCfg[c][0];
-						scoreCs[b] = kScoreCfg[c][1];
-						scoreVg[b] = kScoreCfg[c][2];
-					}
-				}
-				if (useScores[b] && scoreVg[b]) {
-					const long long groupsHere = scoreNf[b] == 16 ? e->scoreGroups16 : e->scoreGroups8;
-					vPerCta[b] = gsb::scoreKernelScratchDoubles(e->buckets[b].kMax, scoreNf[b], scoreCs[b]);
-					vOffset[b] = vTotal;
-					const long long ctasHere = groupsHere * e->buckets[b].count * scoreCs[b];
-					vSlots[b] = gsb::scoreKernelScratchSlots(e->buckets[b].kMax, scoreNf[b], scoreCs[b], e->scoreNr, ctasHere);
-					vTotal += vPerCta[b] * (vSlots[b] < 0 ? -vSlots[b] : vSlots[b]);
-				}
-				useBatch[b] = !useScores[b] && batchOn && e->buckets[b].kMax <= e->batchMaxK;
-				if (!useBatch[b]) continue;
-				scratchPerCta[b] = gsb::batchKernelScratchDoubles(e->buckets[b].kMax, e->batchNfMax, e->batchUDoubles);
-				scratchOffset[b] = scratchTotal;
-				scratchTotal += scratchPerCta[b] * static_cast<long long>(e->buckets[b].count) * e->batchGroups;
-			}
-			for (size_t b = 0; b < e->buckets.size(); ++b) {
-				if (useBatch[b] || useScores[b] || useKspace[b]) continue;
-				spillPerCta[b] = gsb::fitKernelSpillDoubles(e->buckets[b].kMax, e->tableA, e->smemLimit, e->maxTasks, e->maxBlockLd);
-				spillOffset[b] = spillTotal;
-				spillTotal += spillPerCta[b] * static_cast<long long>(e->buckets[b].count) * static_cast<long long>(e->plan.fits.size());
-			}
-			if (scratchTotal > 0) e->batchScratch.reserve(static_cast<size_t>(scratchTotal));
-			if (vTotal > 0) e->scoreScratch.reserve(static_cast<size_t>(vTotal));
-			if (spillTotal > 0) e->spill.reserve(static_cast<size_t>(spillTotal));
 			int slot = 0;
 			if (kspaceFirst < e->buckets.size()) {
 				cudaStream_t launchStream = nside ? e->side[slot % nside] : e->stream;
 				++slot;
+				const int kspaceNf = (env.kspaceNf == 16 && gsb::kspaceKernelFits(e->n, e->tableA, e->smemLimit, 16)) ? 16 : 8;
 				gsb::KParams kp;
 				kp.zpool = e->zpool.ptr;
 				kp.kfits = e->kFits.ptr;
@@ -1252,7 +1273,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				// component of a pass ~6, its first scores ~6, K = Z Z' ~0.37 per column
 				const int passes = (e->kspaceFits + kspaceNf - 1) / kspaceNf;
 				kp.nf = kspaceNf;
-				int split = kspaceSplit;
+				int split = env.kspaceSplit;
 				if (split <= 0) {
 					double kbar = 0.0;
 					for (int i = 0; i < kp.bucketCount; ++i) {
@@ -1294,84 +1315,70 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 					e->timing.fit_tensor_gflop = dmma * 512.0 * 1e-9;
 				}
 			}
-			for (size_t bi = e->buckets.size(); bi-- > 0; ++slot) {
-				const size_t b = bi;
-				if (useKspace[b]) { --slot; continue; }
+			for (size_t bi = kspaceFirst; bi-- > 0; ++slot) {
+				const Bucket& bk = e->buckets[bi];
 				cudaStream_t launchStream = nside ? e->side[slot % nside] : e->stream;
-				if (useScores[b]) {
+				if (bk.kernel == BK_SCORES) {
 					gsb::XParams xp;
 					xp.zpool = e->xz.ptr;
 					xp.reps = e->xReps.ptr;
-					xp.groups = scoreNf[b] == 16 ? e->xGroups16.ptr : e->xGroups8.ptr;
+					xp.groups = bk.nf == 16 ? e->xGroups16.ptr : e->xGroups8.ptr;
 					xp.xfits = e->xFits.ptr;
 					xp.xtasks = e->xTasks.ptr;
 					xp.idx = e->dIdx.ptr;
 					xp.offsets = e->dOffsets.ptr;
-					xp.bucket = e->dBucket.ptr + e->buckets[b].begin;
-					xp.bucketCount = e->buckets[b].count;
-					xp.ngroups = scoreNf[b] == 16 ? e->scoreGroups16 : e->scoreGroups8;
+					xp.bucket = e->dBucket.ptr + bk.begin;
+					xp.bucketCount = bk.count;
+					xp.ngroups = bk.nf == 16 ? e->scoreGroups16 : e->scoreGroups8;
 					xp.nr = e->scoreNr;
-					xp.nf = scoreNf[b];
+					xp.nf = bk.nf;
 					xp.trace = e->traceBuf.ptr;
-					xp.vscratch = scoreVg[b] ? e->scoreScratch.ptr + vOffset[b] : nullptr;
-					xp.vstride = vPerCta[b];
-					xp.vslots = (scoreVg[b] && vSlots[b] < 0) ? -vSlots[b] : 0;
-					xp.desync = desyncMode;
+					xp.vscratch = bk.vg ? e->scoreScratch.ptr + bk.vOffset : nullptr;
+					xp.vstride = bk.vPerCta;
+					xp.vslots = (bk.vg && bk.vSlots < 0) ? -bk.vSlots : 0;
+					xp.desync = env.desync;
 					xp.p = e->p;
 					xp.maxNComp = e->tableA;
 					xp.innerDests = innerDests;
 					xp.outerDests = e->plan.groups;
 					xp.mse = e->dMse.ptr;
 					xp.ostat = e->dOstat.ptr;
-					GSB_CUDA(gsb::launchScoreKernel(xp, e->buckets[b].kMax, e->tableA, scoreCs[b], scoreVg[b], e->smemLimit, launchStream, &ctas));
+					GSB_CUDA(gsb::launchScoreKernel(xp, bk.kMax, e->tableA, bk.cs, bk.vg, e->smemLimit, launchStream, &ctas));
 					++launches;
 					continue;
 				}
-				if (useBatch[b]) {
-					gsb::BatchParams bp;
-					bp.gfull = e->gfull.ptr;
-					bp.s0 = e->s0.ptr;
-					bp.xm = e->xm.ptr;
-					bp.zpool = e->zpool.ptr;
-					bp.fits = e->fits.ptr;
-					bp.blocks = e->blocks.ptr;
-					bp.groupFits = e->bGroupFits.ptr;
-					bp.groups = e->bGroups.ptr;
-					bp.pgs = e->bPgs.ptr;
-					bp.pairs = e->bPairs.ptr;
-					bp.units = e->bUnits.ptr;
-					bp.idx = e->dIdx.ptr;
-					bp.offsets = e->dOffsets.ptr;
-					bp.bucket = e->dBucket.ptr + e->buckets[b].begin;
-					bp.bucketCount = e->buckets[b].count;
-					bp.ngroups = e->batchGroups;
-					bp.p = e->p;
-					bp.maxNComp = e->tableA;
-					bp.innerDests = innerDests;
-					bp.outerDests = e->plan.groups;
-					bp.mse = e->dMse.ptr;
-					bp.ostat = e->dOstat.ptr;
-					bp.scratch = e->batchScratch.ptr + scratchOffset[b];
-					bp.scratchStride = scratchPerCta[b];
-					bp.uDoubles = e->batchUDoubles;
-					bp.pgp = e->batchPgp;
-					bp.nfMax = e->batchNfMax;
-					GSB_CUDA(gsb::launchBatchKernel(bp, e->buckets[b].kMax, e->tableA, e->smemLimit, launchStream, &ctas));
-					++launches;
-					continue;
-				}
+				// per-fit Gram-space kernel: first the packed Grams and vectors of every (chromosome, training set) of the
+				// class, then one CTA per (chromosome, training set), on the same stream
+				gsb::PackParams pp;
+				pp.unitTab = e->unitTab.ptr;
+				pp.unitSum = e->unitSum.ptr;
+				pp.unitXy = e->unitXy.ptr;
+				pp.pfits = e->packFits.ptr;
+				pp.idx = e->dIdx.ptr;
+				pp.offsets = e->dOffsets.ptr;
+				pp.bucket = e->dBucket.ptr + bk.begin;
+				pp.bucketCount = bk.count;
+				pp.nfits = static_cast<int>(e->plan.fits.size());
+				pp.upad = e->upad;
+				pp.gpack = e->gpack.ptr;
+				pp.pvec = e->pvec.ptr;
+				pp.packOff = e->dPackOff.ptr;
+				pp.vecOff = e->dVecOff.ptr;
+				GSB_CUDA(gsb::launchGramPack(pp, bk.kMax, launchStream));
+				launches += 2;
 				gsb::FitParams prm;
-				prm.gram = e->gram.ptr;
-				prm.s0 = e->s0.ptr;
-				prm.xm = e->xm.ptr;
+				prm.gpack = e->gpack.ptr;
+				prm.pvec = e->pvec.ptr;
+				prm.packOff = e->dPackOff.ptr;
+				prm.vecOff = e->dVecOff.ptr;
 				prm.zpool = e->zpool.ptr;
 				prm.fits = e->fits.ptr;
 				prm.tasks = e->tasks.ptr;
 				prm.blocks = e->blocks.ptr;
 				prm.idx = e->dIdx.ptr;
 				prm.offsets = e->dOffsets.ptr;
-				prm.bucket = e->dBucket.ptr + e->buckets[b].begin;
-				prm.bucketCount = e->buckets[b].count;
+				prm.bucket = e->dBucket.ptr + bk.begin;
+				prm.bucketCount = bk.count;
 				prm.nfits = static_cast<int>(e->plan.fits.size());
 				prm.p = e->p;
 				prm.maxNComp = e->tableA;
@@ -1383,9 +1390,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.trace = e->traceBuf.ptr;
 				prm.maxTasks = e->maxTasks;
 				prm.maxBlockLd = e->maxBlockLd;
-				prm.spill = spillPerCta[b] > 0 ? e->spill.ptr + spillOffset[b] : nullptr;
-				prm.spillStride = spillPerCta[b];
-				GSB_CUDA(gsb::launchFitKernel(prm, e->buckets[b].kMax, e->tableA, e->smemLimit, launchStream, &ctas));
+				GSB_CUDA(gsb::launchFitKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas));
 				++launches;
 			}
 			for (int i = 0; i < nside; ++i) {
@@ -1618,7 +1623,8 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
 		dFitNtr.upload(&ntr, 1, e->stream);
 		dGOff.upload(&goff, 1, e->stream);
 		gsb::launchGramSyrk(dUnit.ptr, dLd.ptr, dNr.ptr, dOutPtr.ptr, 1, K2, ldm, e->stream);
-		dGram.reserve(static_cast<size_t>(gsb::tri(static_cast<unsigned long long>(k))));
+		dGram.reserve(static_cast<size_t>(gsb::packedDoubles(static_cast<unsigned long long>(k))));
+		GSB_CUDA(cudaMemsetAsync(dGram.ptr, 0, static_cast<size_t>(gsb::packedDoubles(static_cast<unsigned long long>(k))) * sizeof(double), e->stream));
 		dS0.reserve(static_cast<size_t>(k));
 		dXm.reserve(static_cast<size_t>(k));
 		dYm.reserve(1);
@@ -1629,7 +1635,7 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
 		GSB_CUDA(cudaMemcpyAsync(&ymc, dYm.ptr, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
 		GSB_CUDA(cudaStreamSynchronize(e->stream));
 		gsb::FitDesc fd;
-		fd.gramOff = 0; fd.ym = ymc; fd.ntr = ntr; fd.taskBegin = 0; fd.taskCount = 0; fd.pad = 0;
+		fd.ym = ymc; fd.ntr = ntr; fd.taskBegin = 0; fd.taskCount = 0; fd.pad = 0;
 		std::vector<uint32_t> ident(static_cast<size_t>(k));
 		std::iota(ident.begin(), ident.end(), 0u);
 		const uint32_t off[2] = {0u, static_cast<uint32_t>(k)};
@@ -1639,12 +1645,21 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
 		dBucket.upload(&zero, 1, e->stream);
 		dOut.reserve(static_cast<size_t>(k) * A + A);
 		dDummy.reserve(16);
+		// the kernel's slab layout: s0 then xm, each padded to an even count (the packed Gram is padded in place)
+		const int kp = roundUp(k, 2);
+		DeviceArray<double> dVec;
+		DeviceArray<unsigned long long> dZeroOff;
+		dVec.reserve(static_cast<size_t>(2 * kp));
+		GSB_CUDA(cudaMemsetAsync(dVec.ptr, 0, static_cast<size_t>(2 * kp) * sizeof(double), e->stream));
+		GSB_CUDA(cudaMemcpyAsync(dVec.ptr, dS0.ptr, static_cast<size_t>(k) * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+		GSB_CUDA(cudaMemcpyAsync(dVec.ptr + kp, dXm.ptr, static_cast<size_t>(k) * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+		dZeroOff.upload(&goff, 1, e->stream);
 		gsb::FitParams prm;
-		prm.gram = dGram.ptr; prm.s0 = dS0.ptr; prm.xm = dXm.ptr; prm.zpool = dSub.ptr;
+		prm.gpack = dGram.ptr; prm.pvec = dVec.ptr; prm.packOff = dZeroOff.ptr; prm.vecOff = dZeroOff.ptr; prm.zpool = dSub.ptr;
 		prm.fits = dFit.ptr; prm.tasks = nullptr; prm.blocks = nullptr;
 		prm.idx = dIdx.ptr; prm.offsets = dOff.ptr; prm.bucket = dBucket.ptr; prm.bucketCount = 1; prm.nfits = 1;
 		prm.p = k; prm.maxNComp = A; prm.innerDests = 0; prm.outerDests = 0;
-		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr; prm.trace = nullptr; prm.maxTasks = 0; prm.maxBlockLd = 0; prm.spill = nullptr; prm.spillStride = 0;
+		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr; prm.trace = nullptr; prm.maxTasks = 0; prm.maxBlockLd = 0;
 		GSB_CUDA(gsb::launchFitKernel(prm, k, A, e->smemLimit, e->stream, nullptr));
 		std::vector<double> out(static_cast<size_t>(k) * A + A);
 		GSB_CUDA(cudaMemcpyAsync(out.data(), dOut.ptr, out.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));

@@ -6,9 +6,15 @@
 //   1. gramSyrkKernel  -- FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) SYRK  M_u = Z_u' Z_u  of the
 //      augmented matrix Z = [Xc | yc | 1] for the full data and for every distinct held-out block;
 //      lower-triangular 64x64 output tiles, operands staged through shared memory.
-//   2. combine kernels -- each training set's centred moments from full-data sums minus the sums
-//      of the blocks it excludes:  G_T = (M_full - sum_b M_b)[0:p,0:p] - n_T xm xm'  etc.
-//      (SURVEY.md Appendix B), written as packed lower triangles that K1 gathers from.
+//   2. unitInterleaveKernel -- the moments of all units side by side per packed entry (i, j):
+//      unitTab[tri(i) + j][u] = M_u[i][j]; likewise the column sums and x'y per column.  Once per engine.
+//   3. gramPackVectorsKernel / gramPackKernel (PER GENERATION, ahead of K1) -- each training set's centred
+//      moments of a chromosome's SELECTED columns from full-data sums minus the sums of the blocks it
+//      excludes:  G_T = (M_full - sum_b M_b)[sel, sel] - n_T xm xm'  etc..  One
+//      contiguous run of unitTab holds the entry of every unit, so the DRAM sectors it reads are fully
+//      used by the chromosome's training sets, and K1 reads its packed Gram back as one contiguous slab.
+//   4. combine kernels -- the same combination over ALL columns for one training set (LMEvaluator's
+//      all-rows Gram, gsb_simpls).
 #include "kernels.cuh"
 
 namespace gsb {
@@ -195,6 +201,122 @@ __global__ void combineGramKernel(const double* __restrict__ mFull, const double
 	gramPool[gramOffs[fit] + tri(static_cast<unsigned long long>(i)) + j] = g;
 }
 
+// unitTab[(tri(i) + j) * upad + u] = M_u[i][j] for the units u in [unitBegin, unitBegin + unitCount) (<= kInterleaveUnits per
+// launch), whose moment matrices are mUnits[srcBegin ...]; rows i = p and p + 1 of M_u are x'y and the column sums:
+// they go to unitXy / unitSum [j][upad].
+constexpr int kInterleaveUnits = 64;
+__global__ void __launch_bounds__(256) unitInterleaveKernel(const double* const* __restrict__ mUnits, int srcBegin, int unitBegin, int unitCount,
+                                                           int p, int ldm, int upad, double* __restrict__ unitTab,
+                                                           double* __restrict__ unitSum, double* __restrict__ unitXy) {
+	__shared__ double tile[32][kInterleaveUnits + 1];
+	const int i = blockIdx.x;
+	const int j0 = blockIdx.y * 32;
+	const int jEnd = min(i < p ? i + 1 : p, j0 + 32);
+	if (j0 >= jEnd) return;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int ul = warp; ul < unitCount; ul += 8) {
+		const double* __restrict__ m = mUnits[srcBegin + ul];
+		if (j0 + lane < jEnd) tile[lane][ul] = m[static_cast<size_t>(i) * ldm + j0 + lane];
+	}
+	__syncthreads();
+	const int nj = jEnd - j0;
+	for (int t = threadIdx.x; t < nj * unitCount; t += 256) {
+		const int jl = t / unitCount, ul = t - jl * unitCount;
+		const size_t j = static_cast<size_t>(j0 + jl);
+		double* dst = i < p ? unitTab + (tri(static_cast<unsigned long long>(i)) + j) * upad : (i == p ? unitXy : unitSum) + j * upad;
+		dst[unitBegin + ul] = tile[jl][ul];
+	}
+}
+
+constexpr int kPackThreads = 256;
+
+// s0 = X_T'y_T - sx sy / n_T and xm = sx / n_T of the selected columns for every training set of a chromosome
+// (the arithmetic of combineVectorsKernel); grid: (32-column tiles, chromosomes of the launch)
+__global__ void __launch_bounds__(kPackThreads) gramPackVectorsKernel(const PackParams prm) {
+	extern __shared__ __align__(16) double psm[];
+	const int chrom = prm.bucket[blockIdx.y];
+	const uint32_t selBegin = prm.offsets[chrom];
+	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
+	const int a0 = blockIdx.x * 32;
+	if (a0 >= k) return;
+	const int na = min(32, k - a0);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ldt = prm.upad + 1;
+	double* __restrict__ tSum = psm;
+	double* __restrict__ tXy = psm + 32 * ldt;
+	for (int a = warp; a < na; a += kPackThreads / 32) {
+		const size_t col = prm.idx[selBegin + a0 + a];
+		for (int u = lane; u < prm.upad; u += 32) {
+			tSum[a * ldt + u] = prm.unitSum[col * prm.upad + u];
+			tXy[a * ldt + u] = prm.unitXy[col * prm.upad + u];
+		}
+	}
+	__syncthreads();
+	const int kp = (k + 1) & ~1;
+	double* __restrict__ out = prm.pvec + prm.vecOff[chrom];
+	if (lane < na) {
+		for (int f = warp; f < prm.nfits; f += kPackThreads / 32) {
+			const PackFit pf = prm.pfits[f];
+			double sx = tSum[lane * ldt], xy = tXy[lane * ldt];
+			if (pf.u1 >= 0) { sx -= tSum[lane * ldt + pf.u1]; xy -= tXy[lane * ldt + pf.u1]; }
+			if (pf.u2 >= 0) { sx -= tSum[lane * ldt + pf.u2]; xy -= tXy[lane * ldt + pf.u2]; }
+			out[static_cast<size_t>(f) * 2 * kp + a0 + lane] = xy - sx * pf.sy / pf.nT;
+			out[static_cast<size_t>(f) * 2 * kp + kp + a0 + lane] = sx / pf.nT;
+		}
+	}
+}
+
+// The packed centred Gram of the selected columns for every training set of a chromosome (the arithmetic of
+// combineGramKernel).  grid: (tiles of `entries` packed entries, chromosomes of the launch).  A warp fetches the
+// unit run of an entry (upad contiguous doubles: every sector it touches is used), the CTA then writes, per
+// training set, `entries` consecutive doubles of that set's slab.
+__global__ void __launch_bounds__(kPackThreads) gramPackKernel(const PackParams prm, const int entries) {
+	extern __shared__ __align__(16) double psm[];
+	const int chrom = prm.bucket[blockIdx.y];
+	const uint32_t selBegin = prm.offsets[chrom];
+	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
+	const int ntri = k * (k + 1) / 2;
+	const int e0 = blockIdx.x * entries;
+	if (e0 >= ntri) return;
+	const int ne = min(entries, ntri - e0);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ldt = prm.upad + 1;
+	double* __restrict__ tile = psm;
+	int* __restrict__ ai = reinterpret_cast<int*>(psm + entries * ldt);
+	int* __restrict__ aj = ai + entries;
+	for (int e = warp; e < ne; e += kPackThreads / 32) {
+		const int E = e0 + e;
+		int i = static_cast<int>((sqrtf(8.0f * static_cast<float>(E) + 1.0f) - 1.0f) * 0.5f);
+		while ((i + 1) * (i + 2) / 2 <= E) ++i;
+		while (i * (i + 1) / 2 > E) --i;
+		const int j = E - i * (i + 1) / 2;
+		// ascending column lists: sel[i] >= sel[j]
+		const unsigned long long gi = prm.idx[selBegin + i], gj = prm.idx[selBegin + j];
+		const double* __restrict__ run = prm.unitTab + (tri(gi) + gj) * prm.upad;
+		for (int u = lane; u < prm.upad; u += 32) tile[e * ldt + u] = run[u];
+		if (lane == 0) { ai[e] = i; aj[e] = j; }
+	}
+	__syncthreads();
+	const int kp = (k + 1) & ~1;
+	const size_t slab = static_cast<size_t>(packedDoubles(static_cast<unsigned long long>(k)));
+	double* __restrict__ out = prm.gpack + prm.packOff[chrom];
+	const double* __restrict__ vec = prm.pvec + prm.vecOff[chrom];
+	for (int e = lane; e < ne; e += 32) {
+		const int i = ai[e], j = aj[e];
+		const double t0 = tile[e * ldt];
+		for (int f = warp; f < prm.nfits; f += kPackThreads / 32) {
+			const PackFit pf = prm.pfits[f];
+			const double* __restrict__ xmf = vec + static_cast<size_t>(f) * 2 * kp + kp;
+			double g = t0;
+			if (pf.u1 >= 0) g -= tile[e * ldt + pf.u1];
+			if (pf.u2 >= 0) g -= tile[e * ldt + pf.u2];
+			g -= pf.nT * xmf[i] * xmf[j];
+			out[static_cast<size_t>(f) * slab + e0 + e] = g;
+		}
+	}
+	if (blockIdx.x == 0 && (ntri & 1) && threadIdx.x < prm.nfits) out[static_cast<size_t>(threadIdx.x) * slab + ntri] = 0.0; // the padding double
+}
+
 // dst[:, c] = z[rows, cols ? cols[c] : c], zero-padded to ld rows
 __global__ void blockGatherKernel(const double* __restrict__ z, int ldz, const uint32_t* __restrict__ cols,
                                   const uint32_t* __restrict__ rows, int nrows, double* __restrict__ dst, int ld) {
@@ -227,6 +349,38 @@ void launchGramCombine(const double* mFull, const double* const* mBlocks, const 
 	dim3 gg(static_cast<unsigned>((p + 255) / 256), static_cast<unsigned>(p), static_cast<unsigned>(nfitsChunk));
 	combineGramKernel<<<gg, 256, 0, stream>>>(mFull, mBlocks, exclIndex, exclCount, fitIds, fitNtr, p, ldm, gramPool,
 	                                          gramOffs, xm);
+}
+
+// mUnits[0 .. unitCount) are the moment matrices of the units unitBegin .. unitBegin + unitCount - 1
+void launchUnitInterleave(const double* const* mUnits, int unitBegin, int unitCount, int p, int ldm, int upad, double* unitTab,
+                          double* unitSum, double* unitXy, cudaStream_t stream) {
+	for (int u0 = 0; u0 < unitCount; u0 += kInterleaveUnits) {
+		const int cnt = min(kInterleaveUnits, unitCount - u0);
+		dim3 grid(static_cast<unsigned>(p + 2), static_cast<unsigned>((p + 31) / 32));
+		unitInterleaveKernel<<<grid, 256, 0, stream>>>(mUnits, u0, unitBegin + u0, cnt, p, ldm, upad, unitTab, unitSum, unitXy);
+	}
+}
+
+// the vectors and then the packed Grams of every training set for the chromosomes of one launch (subsets <= kMax)
+cudaError_t launchGramPack(const PackParams& prm, int kMax, cudaStream_t stream) {
+	if (prm.bucketCount <= 0 || prm.nfits <= 0 || kMax <= 0) return cudaSuccess;
+	if (prm.bucketCount > 65535 || prm.nfits > 65535) return cudaErrorInvalidConfiguration;
+	const int ldt = prm.upad + 1;
+	const int vbytes = 2 * 32 * ldt * static_cast<int>(sizeof(double));
+	cudaError_t err = cudaFuncSetAttribute(gramPackVectorsKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vbytes);
+	if (err != cudaSuccess) return err;
+	dim3 gv(static_cast<unsigned>((kMax + 31) / 32), static_cast<unsigned>(prm.bucketCount));
+	gramPackVectorsKernel<<<gv, kPackThreads, static_cast<size_t>(vbytes), stream>>>(prm);
+	// entries per CTA: a tile of at most ~56 KB
+	int entries = 64;
+	while (entries > 8 && entries * ldt * 8 > 56 * 1024) entries >>= 1;
+	const int gbytes = entries * ldt * static_cast<int>(sizeof(double)) + 2 * entries * static_cast<int>(sizeof(int));
+	err = cudaFuncSetAttribute(gramPackKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gbytes);
+	if (err != cudaSuccess) return err;
+	const int ntri = kMax * (kMax + 1) / 2;
+	dim3 gg(static_cast<unsigned>((ntri + entries - 1) / entries), static_cast<unsigned>(prm.bucketCount));
+	gramPackKernel<<<gg, kPackThreads, static_cast<size_t>(gbytes), stream>>>(prm, entries);
+	return cudaGetLastError();
 }
 
 void launchBlockGather(const double* z, int ldz, int ncols, const uint32_t* cols, const uint32_t* rows, int nrows,

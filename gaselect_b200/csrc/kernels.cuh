@@ -5,9 +5,15 @@
 //                       multiple of 4 with zeros (they do not change any Gram)
 //   blocks   per distinct held-out block b: ld_b x P2 column-major copy of Z[rows_b, :] so that a
 //                       selected column of a block is one contiguous, coalesced segment
-//   gram     per distinct training set T: packed lower triangle (row-major, tri(p) doubles) of
-//                       the centred Gram  Xc_T' Xc_T - n_T xm xm'
-//   fitvec   per T: s0 = Xc_T' yc_T (p), xm = column means over T (p)
+//   unitTab  per packed entry (i, j <= i) of the p x p lower triangle: the moment sum_rows z_i z_j of every
+//                       "unit" (unit 0 = all rows, unit u >= 1 = a held-out block some training set excludes), the
+//                       units of one entry contiguous: [tri(i) + j][upad].  One run of upad doubles is everything
+//                       any training set's Gram needs of that entry: no 8-byte gathers from per-fit tables
+//   unitSum, unitXy     per column i: sum_rows z_i and sum_rows z_i y of every unit, [i][upad]
+//   gpack    per generation, per (chromosome, distinct training set T): packed lower triangle (tri(k) doubles,
+//                       padded to an even count) of the centred Gram  Xc_T' Xc_T - n_T xm xm'  of the SELECTED
+//                       columns, written by gramPackKernel, read back contiguously (one TMA bulk copy) by K1
+//   pvec     per (chromosome, T): s0 = Xc_T' yc_T and xm = column means over T of the selected columns
 #ifndef GASELECT_B200_KERNELS_CUH
 #define GASELECT_B200_KERNELS_CUH
 
@@ -18,12 +24,18 @@
 namespace gsb {
 
 struct FitDesc {
-	unsigned long long gramOff; // offset (doubles) into the gram pool
 	double ym;                  // mean of yc over the training rows
 	int ntr;
 	int taskBegin;
 	int taskCount;
 	int pad;
+};
+
+// a training set as full data minus excluded units (gramPackKernel)
+struct PackFit {
+	int u1, u2;   // excluded units (indices into a unitTab run), -1: none
+	double nT;    // number of training rows
+	double sy;    // sum of yc over the training rows (unit sums combined in the same order as every other moment)
 };
 
 struct TaskDesc {
@@ -41,9 +53,10 @@ struct BlockDesc {
 
 // everything K1 needs, passed by value
 struct FitParams {
-	const double* gram;
-	const double* s0;   // nfits x p
-	const double* xm;   // nfits x p
+	const double* gpack;               // per chromosome: nfits slabs of packedDoubles(k) (the fits' centred packed Grams)
+	const double* pvec;                // per chromosome: nfits slabs of 2 x roundUp(k, 2): s0, then xm
+	const unsigned long long* packOff; // per chromosome: offset (doubles) of its first slab in gpack
+	const unsigned long long* vecOff;  // per chromosome: offset (doubles) of its first slab in pvec
 	const double* zpool;
 	const FitDesc* fits;
 	const TaskDesc* tasks;
@@ -61,8 +74,6 @@ struct FitParams {
 	double* ostat;           // [chrom][outerDest][maxNComp][2] = (sum e, sum e^2)
 	double* coefOut;         // optional (gsb_simpls): [k x A] + A intercepts for fit 0 / bucket[0]
 	long long* trace;        // optional (profiling): clock64() stamps of one CTA per launch
-	double* spill;           // optional: per-CTA scratch for Gram rows beyond shared memory (large subsets)
-	long long spillStride;   // doubles per CTA
 	int maxTasks;            // most prediction tasks any fit has
 	int maxBlockLd;          // largest padded row count of a held-out block
 };
@@ -109,69 +120,6 @@ struct OlsParams {
 	int* status;
 };
 
-
-// ---- K1b (simpls_batch.cu): all fits of a replication in one CTA ------------------------------------------
-// A "group" is a set of <= 16 training sets (fits) of the plan, normally the fits of one CV replication.  Every
-// fit's training Gram is the full-data Gram minus its <= 2 excluded row blocks, so the group shares ONE gathered
-// Gram in shared memory; what differs per fit are rank-|block| corrections applied from the block rows.
-// A "pair" is (block, fit): the block rows times the fit's direction vector.  It feeds the Gram correction of
-// the fit (corr != 0: the block is excluded from the fit's training rows) and / or a prediction task.
-struct BatchGroup {
-	int fitBegin;  // into groupFits
-	int nfits;
-	int pgBegin;   // into pgs
-	int npg;
-	int unitBegin; // into units: (pair-group, 32-row slab)
-	int nunits;
-	int pad0, pad1;
-};
-
-struct BatchPairGroup {
-	int block;
-	int npairs;    // <= 8, all on `block`
-	int pairBegin; // into pairs
-	int slabBegin; // first 32-row slab of this pair-group in the group's U buffer
-	int nslabs;
-	int ncorr;     // pairs with corr != 0
-	int pad0, pad1;
-};
-
-struct BatchPair {
-	int fitLocal; // index of the fit inside its group
-	int corr;     // the block is excluded from the fit's training rows
-	int kind;     // -1: no prediction task; 0 inner (MSEP table); 1 outer (pooled residual statistics)
-	int dest;
-};
-
-struct BatchParams {
-	const double* gfull; // packed lower triangle of Z'Z over all rows
-	const double* s0;    // nfits x p
-	const double* xm;    // nfits x p
-	const double* zpool;
-	const FitDesc* fits;
-	const BlockDesc* blocks;
-	const int* groupFits;
-	const BatchGroup* groups;
-	const BatchPairGroup* pgs;
-	const BatchPair* pairs;
-	const int2* units;
-	const uint32_t* idx;
-	const uint32_t* offsets;
-	const int* bucket;
-	int bucketCount;
-	int ngroups;
-	int p;
-	int maxNComp;
-	int innerDests;
-	int outerDests;
-	double* mse;
-	double* ostat;
-	double* scratch;          // per-CTA: stored loadings, per-fit s0 / x-bar columns, running predictions
-	long long scratchStride;  // doubles per CTA
-	int uDoubles;             // doubles of the U buffer (largest group)
-	int pgp;                  // row stride of U (pairs per pair-group, even)
-	int nfMax;                // largest group
-};
 
 // ---- K1x (simpls_scores.cu): score-space SIMPLS on the FP64 tensor cores, 8 fits of one replication per CTA --
 // Applies when the training sets of a replication are unions of a few disjoint row blocks ("atoms": the outer
@@ -278,6 +226,26 @@ struct KParams {
 
 
 __host__ __device__ inline unsigned long long tri(unsigned long long i) { return i * (i + 1ull) / 2ull; }
+// doubles of one packed k x k lower triangle in gpack (even: 16-byte aligned slabs for the bulk copies)
+__host__ __device__ inline unsigned long long packedDoubles(unsigned long long k) { return (tri(k) + 1ull) & ~1ull; }
+
+// gramPackKernel: the chromosomes of one launch
+struct PackParams {
+	const double* unitTab;  // [tri(p)][upad]
+	const double* unitSum;  // [p][upad]
+	const double* unitXy;   // [p][upad]
+	const PackFit* pfits;
+	const uint32_t* idx;
+	const uint32_t* offsets;
+	const int* bucket;
+	int bucketCount;
+	int nfits;
+	int upad;
+	double* gpack;
+	double* pvec;
+	const unsigned long long* packOff;
+	const unsigned long long* vecOff;
+};
 
 // launchers (definitions next to the kernels)
 void launchGramSyrk(const double* const* unitPtrs, const int* unitLd, const int* unitRows, double* const* outPtrs,
@@ -285,16 +253,14 @@ void launchGramSyrk(const double* const* unitPtrs, const int* unitLd, const int*
 void launchGramCombine(const double* mFull, const double* const* mBlocks, const int* exclIndex, const int* exclCount,
                        const int* fitIds, const int* fitNtr, int nfitsChunk, int p, int ldm, double* gramPool,
                        const unsigned long long* gramOffs, double* s0, double* xm, double* ym, cudaStream_t stream);
+void launchUnitInterleave(const double* const* mUnits, int unitBegin, int unitCount, int p, int ldm, int upad, double* unitTab,
+                          double* unitSum, double* unitXy, cudaStream_t stream);
+cudaError_t launchGramPack(const PackParams& prm, int kMax, cudaStream_t stream);
 void launchBlockGather(const double* z, int ldz, int ncols, const uint32_t* cols, const uint32_t* rows, int nrows,
                        double* dst, int ld, cudaStream_t stream);
 int fitKernelSharedBytes(int k, int A);
 int fitKernelMaxK(int A, int smemLimit);
-long long fitKernelSpillDoubles(int kMax, int A, int smemLimit, int maxTasks, int maxBlockLd);
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
-int batchKernelMaxK(int nfMax, int uDoubles, int smemLimit);
-long long batchKernelScratchDoubles(int kMax, int nfMax, int uDoubles);
-cudaError_t launchBatchKernel(const BatchParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
-constexpr int kBatchComponents = 10;
 int scoreKernelMaxK(int nr, int nf, int clusterSize, int vGlobal, int smemLimit);
 long long scoreKernelScratchDoubles(int kMax, int nf, int clusterSize);
 int scoreKernelScratchSlots(int kMax, int nf, int clusterSize, int nr, long long ctas);

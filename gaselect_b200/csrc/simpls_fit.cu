@@ -15,14 +15,14 @@
 //   simplsFitFast<10, SPILL>   A <= 10 components, k <= 384 -- everything at BASELINE configs 3-5.  One thread
 //       per Gram row; the per-row SIMPLS state (S, s0, x-bar, the stored loadings, the cumulative
 //       coefficients) lives in registers; shared memory holds the packed Gram, S and reduction scratch.
-//       SPILL: the packed rows that do not fit in shared memory (k > 212) live in an L2-resident scratch.
+//       SPILL: the packed rows that do not fit in shared memory (k > 212) are read in place from the fit's slab (L2).
 //   simplsFitKernel<RPT, GSMEM> the generic path: any number of components (BASELINE config 1 runs up to 30
 //       per fit), loadings and coefficients in shared memory; GSMEM = false reads the Gram in place.
 //
 // Data movement
-//   * gather: the k(k+1)/2 selected entries of the training set's packed Gram go from HBM/L2
-//     straight into shared memory with 8-byte cp.async (LDGSTS): no register staging, every
-//     thread has all of its copies in flight at once;
+//   * the training set's packed centred Gram of the selected columns (k(k+1)/2 doubles) has been written as one
+//     contiguous slab by gramPackKernel (gram_build.cu) just before this launch; the fast path fetches it with ONE
+//     TMA bulk copy (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) issued by one thread;
 //   * the symmetric matrix-vector product reads the packed triangle conflict-free (consecutive
 //     rows start at consecutive triangular numbers, distinct modulo 16); one thread per row,
 //     four independent accumulators, warp-uniform split into "left of the diagonal band" (own
@@ -50,14 +50,37 @@ constexpr int kMaxWarps = 12; // 384 threads: subsets up to k = 384 on the spill
 
 __device__ __forceinline__ double shflXor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-__device__ __forceinline__ void cpAsync8(double* dst, const double* src) {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src));
-}
 __device__ __forceinline__ void cpAsync16(double* dst, const double* src) {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src));
 }
 __device__ __forceinline__ void cpAsyncWaitAll() {
 	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// TMA bulk copy (global -> shared, SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ uint32_t smemAddrF(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInitF(uint64_t* bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smemAddrF(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTxF(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smemAddrF(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWaitF(uint64_t* bar, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile(
+			"{\n"
+			".reg .pred p;\n"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+			"selp.u32 %0, 1, 0, p;\n"
+			"}\n" : "=r"(done) : "r"(smemAddrF(bar)), "r"(parity) : "memory");
+	} while (!done);
+}
+__device__ __forceinline__ void bulkLoadF(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smemAddrF(dst)),
+	             "l"(src), "r"(bytes), "r"(smemAddrF(bar))
+	             : "memory");
 }
 
 // Sum NV values over the CTA (nw warps); every thread receives bitwise-identical totals.
@@ -143,35 +166,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(smem + cv.sel);
 	int phase = 0;
 
-	// ---- gather (PLS::viewSelectColumns + viewSelectRows, as Gram entries) -----------------
+	// ---- the fit's packed Gram and vectors (PLS::viewSelectColumns + viewSelectRows, as moments; gramPackKernel) ----
 	for (int i = tid; i < k; i += NT) sel[i] = prm.idx[selBegin + i];
-	__syncthreads();
-	const double* __restrict__ gsrc = prm.gram + fd.gramOff;
+	const int kp = roundUp(k, 2);
+	const size_t slab = static_cast<size_t>(packedDoubles(static_cast<unsigned long long>(k)));
+	const double* __restrict__ gsrc = prm.gpack + prm.packOff[chrom] + static_cast<size_t>(fi) * slab;
+	const double* __restrict__ vsrc = prm.pvec + prm.vecOff[chrom] + static_cast<size_t>(fi) * 2 * kp;
 	if (GSMEM) {
-		// packed row a = entries (a, 0..a); rows are dealt to the warps, lanes cover the columns
-		uint32_t selB[kMaxWarps];
-#pragma unroll
-		for (int j = 0; j < kMaxWarps; ++j) selB[j] = (lane + 32 * j < k) ? sel[lane + 32 * j] : 0u;
-		for (int a = warp; a < k; a += NW) {
-			const double* __restrict__ grow = gsrc + tri(sel[a]);
-			double* __restrict__ prow = P + a * (a + 1) / 2;
-#pragma unroll
-			for (int j = 0; j < kMaxWarps; ++j) {
-				if (32 * j <= a) {
-					const int b = lane + 32 * j;
-					if (b <= a) cpAsync8(prow + b, grow + selB[j]);
-				}
-			}
-		}
+		for (int i = tid; i < static_cast<int>(slab >> 1); i += NT) cpAsync16(P + 2 * i, gsrc + 2 * i);
 	}
 	{
-		const double* __restrict__ s0g = prm.s0 + static_cast<size_t>(fi) * prm.p;
-		const double* __restrict__ xmg = prm.xm + static_cast<size_t>(fi) * prm.p;
 		for (int i = tid; i < k; i += NT) {
-			const double s = __ldg(s0g + sel[i]);
-			S[i] = s;
-			s0s[i] = s;
-			xms[i] = __ldg(xmg + sel[i]);
+			const double sv = __ldg(vsrc + i);
+			S[i] = sv;
+			s0s[i] = sv;
+			xms[i] = __ldg(vsrc + kp + i);
 		}
 		for (int i = tid; i < k * Apad; i += NT) coef[i] = 0.0;
 	}
@@ -236,12 +245,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 		} else {
 #pragma unroll
 			for (int u = 0; u < RPT; ++u) {
-				const uint32_t rs = sel[row[u]];
-				const unsigned long long rt = tri(rs);
+				const int rt = row[u] * (row[u] + 1) / 2;
 				double a0 = 0.0;
 				for (int c = 0; c < k; ++c) {
-					const uint32_t selc = sel[c];
-					const unsigned long long addr = (c <= row[u]) ? rt + selc : tri(selc) + rs;
+					const int addr = (c <= row[u]) ? rt + c : c * (c + 1) / 2 + row[u];
 					a0 = fma(__ldg(gsrc + addr), S[c], a0);
 				}
 				w[u] = a0;
@@ -477,7 +484,7 @@ struct FastCarve {
 };
 
 // wantXt < 0: host decision; else the number of held-out blocks staged per pass (0, 1 or 2), as told
-// rowsInSmem: packed Gram rows kept in shared memory (k on the plain path; the rest is spilled to an L2 scratch)
+// rowsInSmem: packed Gram rows kept in shared memory (k on the plain path; the rest is read in place from the fit's slab in L2)
 __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTasks, int maxBlockLd, int wantXt, int rowsInSmem) {
 	FastCarve c;
 	const int Apad = roundUp(A, 2);
@@ -619,10 +626,10 @@ __device__ __forceinline__ double symvRow(const double* __restrict__ P, const do
 	return (a0 + a1) + (a2 + a3);
 }
 
-// The same row when the Gram rows [rs, k) live in the global scratch (rs is a multiple of 32 or k, so a warp's
-// rows are all on one side).  Scratch row a - rs holds entries (a, 0..a) with stride ldS (a multiple of 4).
-__device__ __forceinline__ double symvRowSpill(const double* __restrict__ P, const double* __restrict__ S, const double* spill,
-                                               int k, int rs, int ldS, int r, int rlo, int rhi) {
+// The same row when only the packed rows [0, rs) are in shared memory (rs is a multiple of 32 or k, so a warp's rows
+// are all on one side): the rows [rs, k) are read in place from the fit's packed slab gp in global memory (L2).
+__device__ __forceinline__ double symvRowSpill(const double* __restrict__ P, const double* __restrict__ S, const double* __restrict__ gp,
+                                               int k, int rs, int r, int rlo, int rhi) {
 	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 	int c = 0;
 	if (rlo < rs) {
@@ -659,46 +666,46 @@ __device__ __forceinline__ double symvRowSpill(const double* __restrict__ P, con
 			tc += c + 1;
 		}
 	} else {
-		// ... this warp's rows are spilled: own row as 32-byte runs from the scratch (L2)
-		const double* gr = spill + static_cast<size_t>(r - rs) * ldS;
+		// ... this warp's rows are spilled: own packed row, per-thread runs from L2
+		const double* __restrict__ gr = gp + static_cast<size_t>(r) * (r + 1) / 2;
 		for (; c + 3 < rlo; c += 4) {
-			const double2 g01 = __ldcg(reinterpret_cast<const double2*>(gr + c));
-			const double2 g23 = __ldcg(reinterpret_cast<const double2*>(gr + c + 2));
 			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
 			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
-			a0 = fma(g01.x, s01.x, a0);
-			a1 = fma(g01.y, s01.y, a1);
-			a2 = fma(g23.x, s23.x, a2);
-			a3 = fma(g23.y, s23.y, a3);
+			a0 = fma(__ldcg(gr + c), s01.x, a0);
+			a1 = fma(__ldcg(gr + c + 1), s01.y, a1);
+			a2 = fma(__ldcg(gr + c + 2), s23.x, a2);
+			a3 = fma(__ldcg(gr + c + 3), s23.y, a3);
 		}
 		for (; c < rlo; ++c) a0 = fma(__ldcg(gr + c), S[c], a0);
 		for (; c <= rhi; ++c) { // the band: (r, c) for c <= r, else (c, r) of another spilled row
-			const double g = (c <= r) ? __ldcg(gr + c) : __ldcg(spill + static_cast<size_t>(c - rs) * ldS + r);
+			const double g = (c <= r) ? __ldcg(gr + c) : __ldcg(gp + static_cast<size_t>(c) * (c + 1) / 2 + r);
 			a1 = fma(g, S[c], a1);
 		}
 	}
 	// below the band / beyond the shared rows: column r of the spilled rows c (coalesced over the lanes)
 	c = max(c, rs);
-	const double* gc = spill + r;
+	const double* __restrict__ gc = gp + r;
+	size_t tc = static_cast<size_t>(c) * (c + 1) / 2;
 	for (; c + 3 < k; c += 4) {
 		const double2 s01 = *reinterpret_cast<const double2*>(S + c);
 		const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
-		const double g0 = __ldcg(gc + static_cast<size_t>(c - rs) * ldS);
-		const double g1 = __ldcg(gc + static_cast<size_t>(c + 1 - rs) * ldS);
-		const double g2 = __ldcg(gc + static_cast<size_t>(c + 2 - rs) * ldS);
-		const double g3 = __ldcg(gc + static_cast<size_t>(c + 3 - rs) * ldS);
-		a0 = fma(g0, s01.x, a0);
-		a1 = fma(g1, s01.y, a1);
-		a2 = fma(g2, s23.x, a2);
-		a3 = fma(g3, s23.y, a3);
+		const size_t t1 = tc + c + 1, t2 = t1 + c + 2, t3 = t2 + c + 3;
+		a0 = fma(__ldcg(gc + tc), s01.x, a0);
+		a1 = fma(__ldcg(gc + t1), s01.y, a1);
+		a2 = fma(__ldcg(gc + t2), s23.x, a2);
+		a3 = fma(__ldcg(gc + t3), s23.y, a3);
+		tc = t3 + c + 4;
 	}
-	for (; c < k; ++c) a3 = fma(__ldcg(gc + static_cast<size_t>(c - rs) * ldS), S[c], a3);
+	for (; c < k; ++c) {
+		a3 = fma(__ldcg(gc + tc), S[c], a3);
+		tc += c + 1;
+	}
 	return (a0 + a1) + (a2 + a3);
 }
 
-// SPILL: packed Gram rows >= rSplit (a multiple of 32) do not fit in shared memory; they are gathered into a
-// per-CTA scratch in global memory (L2-resident while the CTA runs; row stride roundUp(k, 4)) and read from
-// there by every matrix-vector product: own rows as contiguous per-thread runs, column accesses coalesced.
+// SPILL: packed Gram rows >= rSplit (a multiple of 32) do not fit in shared memory; every matrix-vector product reads
+// them in place from the fit's slab (L2-resident while the CTA runs): own rows as per-thread runs, column accesses
+// coalesced.
 // TRACE: the instance with the clock64() stamps, launched only when prm.trace is set (even predicated off they cost
 // a few per cent in the hot loops, measured on the kernel-space kernel)
 template <int AREG, bool SPILL, bool TRACE>
@@ -724,48 +731,29 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	double* __restrict__ S = smem + cv.S;
 	double* red = smem + cv.red;
 	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(smem + cv.sel);
-	const int ldS = roundUp(k, 4);
-	double* spill = SPILL ? prm.spill + static_cast<size_t>(blockIdx.x) * prm.spillStride : nullptr;
 	int phase = 0;
+	__shared__ __align__(8) uint64_t gramBar;
 
 	const bool tracing = TRACE && prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
 	int stamp = 0;
 #define GSB_STAMP() do { if (TRACE && tracing) prm.trace[stamp++] = clock64(); } while (0)
 	GSB_STAMP();
 
-	// ---- gather ------------------------------------------------------------------------------
-	for (int i = tid; i < k; i += NT) sel[i] = prm.idx[selBegin + i];
-	__syncthreads();
-	const double* __restrict__ gsrc = prm.gram + fd.gramOff;
-	{
-		uint32_t selB[MAXW];
-#pragma unroll
-		for (int j = 0; j < MAXW; ++j) selB[j] = (lane + 32 * j < k) ? sel[lane + 32 * j] : 0u;
-		for (int a = warp; a < rs; a += NW) {
-			const double* __restrict__ grow = gsrc + tri(sel[a]);
-			double* __restrict__ prow = P + a * (a + 1) / 2;
-#pragma unroll
-			for (int j = 0; j < MAXW; ++j) {
-				if (32 * j <= a) {
-					const int b = lane + 32 * j;
-					if (b <= a) cpAsync8(prow + b, grow + selB[j]);
-				}
-			}
-		}
-		if (SPILL) {
-			for (int a = rs + warp; a < k; a += NW) {
-				const double* __restrict__ grow = gsrc + tri(sel[a]);
-				double* srow = spill + static_cast<size_t>(a - rs) * ldS;
-#pragma unroll
-				for (int j = 0; j < MAXW; ++j) {
-					if (32 * j <= a) {
-						const int b = lane + 32 * j;
-						if (b <= a) srow[b] = __ldg(grow + selB[j]);
-					}
-				}
-			}
+	// ---- the fit's packed Gram: one contiguous slab (gramPackKernel), fetched by TMA bulk copies ------------------
+	const int kp = roundUp(k, 2);
+	const size_t slab = static_cast<size_t>(packedDoubles(static_cast<unsigned long long>(k)));
+	const double* __restrict__ gsrc = prm.gpack + prm.packOff[chrom] + static_cast<size_t>(fi) * slab;
+	const double* __restrict__ vsrc = prm.pvec + prm.vecOff[chrom] + static_cast<size_t>(fi) * 2 * kp;
+	if (tid == 0) {
+		mbarInitF(&gramBar, 1);
+		// rows [0, rs) (all of them unless SPILL); the slab is padded to an even number of doubles
+		const uint32_t bytes = static_cast<uint32_t>(packedDoubles(static_cast<unsigned long long>(rs)) * sizeof(double));
+		mbarExpectTxF(&gramBar, bytes);
+		for (uint32_t o = 0; o < bytes; o += 32768u) {
+			bulkLoadF(reinterpret_cast<char*>(P) + o, reinterpret_cast<const char*>(gsrc) + o, min(32768u, bytes - o), &gramBar);
 		}
 	}
+	for (int i = tid; i < k; i += NT) sel[i] = prm.idx[selBegin + i];
 	// descriptors of the held-out blocks this fit predicts (needed much later: load them now)
 	TaskDesc td[2];
 	BlockDesc bd[2];
@@ -783,17 +771,16 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	const int r = valid ? tid : k - 1;
 	double sOwn, s0Own, xmOwn;
 	{
-		const uint32_t sr = sel[r];
-		s0Own = __ldg(prm.s0 + static_cast<size_t>(fi) * prm.p + sr);
-		xmOwn = __ldg(prm.xm + static_cast<size_t>(fi) * prm.p + sr);
+		s0Own = __ldg(vsrc + r);
+		xmOwn = __ldg(vsrc + kp + r);
 		sOwn = s0Own;
 		if (valid) S[r] = sOwn;
 	}
 	double vOwn[AREG], cOwn[AREG];
 #pragma unroll
 	for (int j = 0; j < AREG; ++j) { vOwn[j] = 0.0; cOwn[j] = 0.0; }
-	cpAsyncWaitAll();
-	__syncthreads();
+	__syncthreads();          // sel, S; the barrier's initialisation
+	mbarWaitF(&gramBar, 0u);  // the packed Gram has landed
 	GSB_STAMP(); // 1: gather done
 
 	// rows of a warp are consecutive: [rlo, rhi] is warp-uniform
@@ -805,7 +792,7 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	double cum = 0.0;
 #pragma unroll 1
 	for (int comp = 0; comp < A; ++comp) {
-		const double w = SPILL ? symvRowSpill(P, S, spill, k, rs, ldS, r, rlo, rhi) : symvRow(P, S, k, r, rlo, rhi);
+		const double w = SPILL ? symvRowSpill(P, S, gsrc, k, rs, r, rlo, rhi) : symvRow(P, S, k, r, rlo, rhi);
 
 		// ONE round: tn^2 = S'GS (:138), q*tn = s0'S (:148), projections V_j'w on every stored loading
 		double r1[2 + AREG];
@@ -1132,7 +1119,6 @@ cudaError_t launchFast(const FitParams& prm, int kMax, int A, int smemLimit, cud
 			simplsFitFast<AREG, false, false><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
 		}
 	} else {
-		if (prm.spill == nullptr) return cudaErrorInvalidValue;
 		err = cudaFuncSetAttribute(simplsFitFast<AREG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 		if (err != cudaSuccess) return err;
 		simplsFitFast<AREG, true, false><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, rs);
@@ -1169,20 +1155,10 @@ int fitKernelMaxK(int A, int smemLimit) {
 	return k;
 }
 
-// Doubles of global scratch one CTA of a bucket needs for the Gram rows that do not fit in shared memory (0: none).
-long long fitKernelSpillDoubles(int kMax, int A, int smemLimit, int maxTasks, int maxBlockLd) {
-	const int Ak = (A < kMax) ? A : kMax;
-	if (Ak > kFastComponents || kMax > kMaxWarps * 32) return 0;
-	const int rs = fastRowsInSmem(kMax, Ak, maxTasks, maxBlockLd, smemLimit);
-	if (rs <= 0 || rs >= kMax) return 0;
-	return static_cast<long long>(kMax - rs) * roundUp(kMax, 4);
-}
-
 // One launch for a bucket of chromosomes whose subset sizes are all <= kMax.
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
 	const int Ak = (A < kMax) ? A : kMax;
-	if (Ak <= kFastComponents && kMax <= kMaxWarps * 32 && fastRowsInSmem(kMax, Ak, prm.maxTasks, prm.maxBlockLd, smemLimit) > 0 &&
-	    (prm.spill != nullptr || fastRowsInSmem(kMax, Ak, prm.maxTasks, prm.maxBlockLd, smemLimit) >= kMax)) {
+	if (Ak <= kFastComponents && kMax <= kMaxWarps * 32 && fastRowsInSmem(kMax, Ak, prm.maxTasks, prm.maxBlockLd, smemLimit) > 0) {
 		return launchFast<kFastComponents>(prm, kMax, Ak, smemLimit, stream, ctas); // per-row state in registers
 	}
 	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true, roundUp(kMax, 32) / 32).total * 8 <= smemLimit) {
