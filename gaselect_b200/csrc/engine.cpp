@@ -97,6 +97,7 @@ struct Bucket {
 	int count;
 	int kMax;
 	int kernel;        // BucketKernel, decided when the population is uploaded
+	bool split;        // BK_FIT: fit-only kernel + predictBlocksKernel (else the per-fit kernel predicts in place)
 	int nf, cs, vg;    // K1x configuration (fits per CTA, cluster size, loadings in the global scratch)
 	long long vPerCta, vOffset;
 	int vSlots;
@@ -111,7 +112,7 @@ int bucketCeil(int k) {
 
 // profiling / experiment switches, read from the environment ONCE per engine (ensureDevice)
 struct EnvFlags {
-	bool serial = false, noScores = false, noKspace = false, trace = false;
+	bool serial = false, noScores = false, noKspace = false, trace = false, noPredict = false, noTmem = false;
 	int kspaceNf = 8, kspaceMinK = 40, kspaceSplit = 0, desync = 0;
 	int forcedNf = 0, forcedCs = 0, forcedVg = 0;
 };
@@ -166,8 +167,13 @@ struct gsb_engine {
 	DeviceArray<gsb::PackFit> packFits;
 	// ... and, per resident population, the packed Grams / vectors of every (chromosome, training set)
 	DeviceArray<double> gpack, pvec;
-	DeviceArray<unsigned long long> dPackOff, dVecOff;
-	PinnedArray<unsigned long long> hPackOff, hVecOff;
+	DeviceArray<unsigned long long> dPackOff, dVecOff, dCoefOff;
+	PinnedArray<unsigned long long> hPackOff, hVecOff, hCoefOff;
+	// ... and the fits' coefficient rows for the prediction kernel, whose task lists are per held-out block
+	DeviceArray<double> coefScratch;
+	DeviceArray<int> activeBlocks, blockTaskOff;
+	DeviceArray<gsb::PredTask> predTasks;
+	int nActiveBlocks = 0;
 
 	// resident population
 	int npop = 0, kMaxPop = 0, tableA = 1;
@@ -225,8 +231,9 @@ void releaseDevice(gsb_engine* e) {
 	e->fits.release(); e->tasks.release(); e->blocks.release(); e->outerRows.release();
 	e->traceBuf.release();
 	e->unitTab.release(); e->unitSum.release(); e->unitXy.release(); e->packFits.release();
-	e->gpack.release(); e->pvec.release(); e->dPackOff.release(); e->dVecOff.release();
-	e->hPackOff.release(); e->hVecOff.release();
+	e->gpack.release(); e->pvec.release(); e->dPackOff.release(); e->dVecOff.release(); e->dCoefOff.release();
+	e->hPackOff.release(); e->hVecOff.release(); e->hCoefOff.release();
+	e->coefScratch.release(); e->activeBlocks.release(); e->blockTaskOff.release(); e->predTasks.release();
 	e->xz.release(); e->scoreScratch.release(); e->xReps.release(); e->xGroups8.release(); e->xGroups16.release(); e->xFits.release(); e->xTasks.release();
 	e->kFits.release(); e->kTasks.release();
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
@@ -278,6 +285,8 @@ void ensureDevice(gsb_engine* e) {
 	env.noScores = std::getenv("GSB_NO_SCORES") != nullptr;
 	env.noKspace = std::getenv("GSB_NO_KSPACE") != nullptr;
 	env.trace = std::getenv("GSB_TRACE") != nullptr;
+	env.noTmem = std::getenv("GSB_TMEM") == nullptr;          // opt-in experiment: the fit's Gram rows in tensor memory (simpls_tmem.cu; measured slower)
+	env.noPredict = std::getenv("GSB_NO_PREDICT") != nullptr; // per-fit kernel predicts in place (the previous arrangement)
 	if (const char* v = std::getenv("GSB_KSPACE_NF")) env.kspaceNf = std::atoi(v) == 16 ? 16 : 8;
 	if (const char* v = std::getenv("GSB_KSPACE_MINK")) env.kspaceMinK = std::atoi(v);
 	if (const char* v = std::getenv("GSB_KSPACE_SPLIT")) env.kspaceSplit = std::atoi(v);
@@ -720,6 +729,29 @@ void prepareDevice(gsb_engine* e) {
 	e->maxBlockLd = 0;
 	for (int f = 0; f < nfits; ++f) e->maxTasks = std::max(e->maxTasks, plan.fits[static_cast<size_t>(f)].taskCount);
 	for (size_t t = 0; t < plan.tasks.size(); ++t) e->maxBlockLd = std::max(e->maxBlockLd, bdesc[static_cast<size_t>(plan.tasks[t].block)].ld);
+	{ // prediction tasks grouped by held-out block (predict_blocks.cu)
+		std::vector<std::vector<gsb::PredTask>> perBlock(static_cast<size_t>(nblocks));
+		for (size_t t = 0; t < plan.tasks.size(); ++t) {
+			gsb::PredTask pt;
+			pt.fit = plan.tasks[t].fit;
+			pt.kind = plan.tasks[t].kind;
+			pt.dest = plan.tasks[t].dest;
+			pt.pad = 0;
+			perBlock[static_cast<size_t>(plan.tasks[t].block)].push_back(pt);
+		}
+		std::vector<int> active, off(1, 0);
+		std::vector<gsb::PredTask> flat;
+		for (int b = 0; b < nblocks; ++b) {
+			if (perBlock[static_cast<size_t>(b)].empty()) continue;
+			active.push_back(b);
+			flat.insert(flat.end(), perBlock[static_cast<size_t>(b)].begin(), perBlock[static_cast<size_t>(b)].end());
+			off.push_back(static_cast<int>(flat.size()));
+		}
+		e->nActiveBlocks = static_cast<int>(active.size());
+		e->activeBlocks.upload(active, e->stream);
+		e->blockTaskOff.upload(off, e->stream);
+		e->predTasks.upload(flat, e->stream);
+	}
 	e->fits.upload(fdesc, e->stream);
 	e->tasks.upload(tdesc, e->stream);
 	e->blocks.upload(bdesc, e->stream);
@@ -856,13 +888,16 @@ void planBuckets(gsb_engine* e) {
 	// per-fit kernel: one slab of packed Gram and one of vectors per (chromosome, training set)
 	e->hPackOff.reserve(static_cast<size_t>(e->npop) + 1);
 	e->hVecOff.reserve(static_cast<size_t>(e->npop) + 1);
-	for (int c = 0; c <= e->npop; ++c) e->hPackOff.ptr[c] = e->hVecOff.ptr[c] = 0ull;
+	e->hCoefOff.reserve(static_cast<size_t>(e->npop) + 1);
+	for (int c = 0; c <= e->npop; ++c) e->hPackOff.ptr[c] = e->hVecOff.ptr[c] = e->hCoefOff.ptr[c] = 0ull;
 	if (!wantFit) return;
 	buildUnitTables(e);
-	unsigned long long packTotal = 0, vecTotal = 0;
+	unsigned long long packTotal = 0, vecTotal = 0, coefTotal = 0;
 	for (size_t b = 0; b < e->buckets.size(); ++b) {
-		const Bucket& bk = e->buckets[b];
+		Bucket& bk = e->buckets[b];
 		if (bk.kernel != BK_FIT) continue;
+		// fit-only kernel + one tensor-core prediction per (chromosome, held-out block) where the fast path serves the class
+		bk.split = !env.noPredict && e->nActiveBlocks > 0 && bk.kMax <= gsb::kPredMaxK && gsb::fitOnlyKernelServes(bk.kMax, e->tableA, e->smemLimit);
 		for (int i = 0; i < bk.count; ++i) {
 			const int c = e->hBucket.ptr[bk.begin + i];
 			const unsigned long long k = e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c];
@@ -870,13 +905,18 @@ void planBuckets(gsb_engine* e) {
 			e->hVecOff.ptr[c] = vecTotal;
 			packTotal += gsb::packedDoubles(k) * static_cast<unsigned long long>(nfits);
 			vecTotal += 2ull * ((k + 1ull) & ~1ull) * static_cast<unsigned long long>(nfits);
+			if (bk.split) {
+				e->hCoefOff.ptr[c] = coefTotal;
+				const unsigned long long A = std::min<unsigned long long>(static_cast<unsigned long long>(e->tableA), k);
+				coefTotal += ((k + 2ull) * A * static_cast<unsigned long long>(nfits) + 1ull) & ~1ull;
+			}
 		}
 	}
-	if (packTotal + vecTotal > e->gpack.capacity + e->pvec.capacity) {
+	if (packTotal + vecTotal + coefTotal > e->gpack.capacity + e->pvec.capacity + e->coefScratch.capacity) {
 		size_t freeB = 0, totalB = 0;
 		GSB_CUDA(cudaMemGetInfo(&freeB, &totalB));
-		const double need = 8.0 * static_cast<double>(packTotal + vecTotal);
-		const double have = static_cast<double>(freeB) + 8.0 * static_cast<double>(e->gpack.capacity + e->pvec.capacity);
+		const double need = 8.0 * static_cast<double>(packTotal + vecTotal + coefTotal);
+		const double have = static_cast<double>(freeB) + 8.0 * static_cast<double>(e->gpack.capacity + e->pvec.capacity + e->coefScratch.capacity);
 		if (need > 0.95 * have) {
 			char buf[256];
 			std::snprintf(buf, sizeof(buf), "the packed Grams of this population need %.1f GB of device memory, %.1f GB are free: evaluate it in smaller batches",
@@ -886,6 +926,7 @@ void planBuckets(gsb_engine* e) {
 	}
 	e->gpack.reserve(static_cast<size_t>(packTotal) + 2);
 	e->pvec.reserve(static_cast<size_t>(vecTotal) + 2);
+	if (coefTotal > 0) e->coefScratch.reserve(static_cast<size_t>(coefTotal) + 2);
 }
 
 int prepareChecked(gsb_engine* e) {
@@ -1177,6 +1218,7 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 		if (e->cfg.evaluator != GSB_EVAL_LM) {
 			e->dPackOff.upload(e->hPackOff.ptr, static_cast<size_t>(npop) + 1, e->stream);
 			e->dVecOff.upload(e->hVecOff.ptr, static_cast<size_t>(npop) + 1, e->stream);
+			e->dCoefOff.upload(e->hCoefOff.ptr, static_cast<size_t>(npop) + 1, e->stream);
 		}
 		GSB_CUDA(cudaEventRecord(e->ev[1], e->stream));
 		e->dFitness.reserve(static_cast<size_t>(npop));
@@ -1390,8 +1432,40 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.trace = e->traceBuf.ptr;
 				prm.maxTasks = e->maxTasks;
 				prm.maxBlockLd = e->maxBlockLd;
-				GSB_CUDA(gsb::launchFitKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas));
-				++launches;
+				prm.coefScratch = e->coefScratch.ptr;
+				prm.coefOff = e->dCoefOff.ptr;
+				if (bk.split) {
+					if (!env.noTmem && gsb::tmemKernelServes(bk.kMax, e->tableA, e->smemLimit)) {
+						GSB_CUDA(gsb::launchTmemKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas)); // Gram in tensor memory
+					} else {
+						GSB_CUDA(gsb::launchFitOnlyKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas));
+					}
+					gsb::PredictParams pr;
+					pr.zpool = e->zpool.ptr;
+					pr.blocks = e->blocks.ptr;
+					pr.activeBlocks = e->activeBlocks.ptr;
+					pr.nActive = e->nActiveBlocks;
+					pr.blockTaskOff = e->blockTaskOff.ptr;
+					pr.ptasks = e->predTasks.ptr;
+					pr.coef = e->coefScratch.ptr;
+					pr.coefOff = e->dCoefOff.ptr;
+					pr.idx = e->dIdx.ptr;
+					pr.offsets = e->dOffsets.ptr;
+					pr.bucket = e->dBucket.ptr + bk.begin;
+					pr.bucketCount = bk.count;
+					pr.p = e->p;
+					pr.maxNComp = e->tableA;
+					pr.innerDests = innerDests;
+					pr.outerDests = e->plan.groups;
+					pr.lda = gsb::predictKernelLda(e->maxBlockLd);
+					pr.mse = e->dMse.ptr;
+					pr.ostat = e->dOstat.ptr;
+					GSB_CUDA(gsb::launchPredictKernel(pr, launchStream, nullptr)); // fit_ctas counts the fits' CTAs
+					launches += 2;
+				} else {
+					GSB_CUDA(gsb::launchFitKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas));
+					++launches;
+				}
 			}
 			for (int i = 0; i < nside; ++i) {
 				GSB_CUDA(cudaEventRecord(e->evJoin[i], e->side[i]));
@@ -1660,6 +1734,7 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
 		prm.idx = dIdx.ptr; prm.offsets = dOff.ptr; prm.bucket = dBucket.ptr; prm.bucketCount = 1; prm.nfits = 1;
 		prm.p = k; prm.maxNComp = A; prm.innerDests = 0; prm.outerDests = 0;
 		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr; prm.trace = nullptr; prm.maxTasks = 0; prm.maxBlockLd = 0;
+		prm.coefScratch = nullptr; prm.coefOff = nullptr;
 		GSB_CUDA(gsb::launchFitKernel(prm, k, A, e->smemLimit, e->stream, nullptr));
 		std::vector<double> out(static_cast<size_t>(k) * A + A);
 		GSB_CUDA(cudaMemcpyAsync(out.data(), dOut.ptr, out.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));

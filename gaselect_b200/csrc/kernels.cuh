@@ -76,6 +76,43 @@ struct FitParams {
 	long long* trace;        // optional (profiling): clock64() stamps of one CTA per launch
 	int maxTasks;            // most prediction tasks any fit has
 	int maxBlockLd;          // largest padded row count of a held-out block
+	// fit-only launches (launchFitOnlyKernel): no prediction in the kernel; per (chromosome, fit) the rows
+	// [coef (k x A); -1 (A); intercepts (A)] go to coefScratch for predictBlocksKernel (predict_blocks.cu)
+	double* coefScratch;
+	const unsigned long long* coefOff; // per chromosome: offset (doubles) of its first fit's rows
+};
+
+// ---- K1p (predict_blocks.cu): held-out prediction of the per-fit path, one CTA per (held-out block, chromosome) ----
+constexpr int kPredMaxK = 1024;   // largest subset (column list staged in shared memory)
+constexpr int kPredMaxTasks = 6;  // (fit, block) tasks per pass: 6 x 10 component counts <= 64 columns
+
+struct PredTask {
+	int fit;
+	int kind; // 0 inner (MSEP table), 1 outer (pooled residual statistics)
+	int dest;
+	int pad;
+};
+
+struct PredictParams {
+	const double* zpool;
+	const BlockDesc* blocks;
+	const int* activeBlocks;  // blocks that some task predicts
+	int nActive;
+	const int* blockTaskOff;  // per active block: its tasks in ptasks (CSR)
+	const PredTask* ptasks;
+	const double* coef;       // coefScratch of the fit-only kernel
+	const unsigned long long* coefOff;
+	const uint32_t* idx;
+	const uint32_t* offsets;
+	const int* bucket;
+	int bucketCount;
+	int p;
+	int maxNComp;
+	int innerDests;
+	int outerDests;
+	int lda;                  // leading dimension of the staged block slice: >= min(128, largest block ld), == 4 mod 16
+	double* mse;
+	double* ostat;
 };
 
 struct ReduceParams {
@@ -261,6 +298,12 @@ void launchBlockGather(const double* z, int ldz, int ncols, const uint32_t* cols
 int fitKernelSharedBytes(int k, int A);
 int fitKernelMaxK(int A, int smemLimit);
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
+bool fitOnlyKernelServes(int kMax, int A, int smemLimit);
+cudaError_t launchFitOnlyKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
+bool tmemKernelServes(int kMax, int A, int smemLimit);
+cudaError_t launchTmemKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
+int predictKernelLda(int maxBlockLd);
+cudaError_t launchPredictKernel(const PredictParams& prm, cudaStream_t stream, long long* ctas);
 int scoreKernelMaxK(int nr, int nf, int clusterSize, int vGlobal, int smemLimit);
 long long scoreKernelScratchDoubles(int kMax, int nf, int clusterSize);
 int scoreKernelScratchSlots(int kMax, int nf, int clusterSize, int nr, long long ctas);

@@ -38,6 +38,7 @@
 // the subtraction (all at once) rather than one after the other as src/PLSSimpls.cpp:57-63 does; the two
 // orders differ by the loss of orthogonality of V, i.e. at rounding level.
 #include "kernels.cuh"
+#include "fit_common.cuh"
 
 namespace gsb {
 
@@ -47,41 +48,6 @@ constexpr int kChunk = 10;  // components per prediction pass (accumulators held
 constexpr int kDots = 6;    // loadings projected in the same reduction round as S'w and s0'S
 constexpr int kRedMax = 20; // widest reduction (values per thread)
 constexpr int kMaxWarps = 12; // 384 threads: subsets up to k = 384 on the spill path
-
-__device__ __forceinline__ double shflXor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-
-__device__ __forceinline__ void cpAsync16(double* dst, const double* src) {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src));
-}
-__device__ __forceinline__ void cpAsyncWaitAll() {
-	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
-// TMA bulk copy (global -> shared, SASS UBLKCP) completing on an mbarrier
-__device__ __forceinline__ uint32_t smemAddrF(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbarInitF(uint64_t* bar, int count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smemAddrF(bar)), "r"(count));
-	asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbarExpectTxF(uint64_t* bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smemAddrF(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWaitF(uint64_t* bar, uint32_t parity) {
-	uint32_t done;
-	do {
-		asm volatile(
-			"{\n"
-			".reg .pred p;\n"
-			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-			"selp.u32 %0, 1, 0, p;\n"
-			"}\n" : "=r"(done) : "r"(smemAddrF(bar)), "r"(parity) : "memory");
-	} while (!done);
-}
-__device__ __forceinline__ void bulkLoadF(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smemAddrF(dst)),
-	             "l"(src), "r"(bytes), "r"(smemAddrF(bar))
-	             : "memory");
-}
 
 // Sum NV values over the CTA (nw warps); every thread receives bitwise-identical totals.
 template <int NV>
@@ -110,7 +76,6 @@ __device__ __forceinline__ void blockSum(double (&v)[NV], double* red, int& phas
 }
 
 
-__host__ __device__ inline int roundUp(int v, int m) { return (v + m - 1) / m * m; }
 
 // shared-memory carve-up (in doubles)
 struct Carve {
@@ -527,41 +492,18 @@ __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTask
 	return c;
 }
 
-// Sum 16 values per lane over the warp: afterwards every lane L holds the total of value (L >> 1).
-__device__ __forceinline__ double warpSum16(double (&v)[16], int lane) {
-#pragma unroll
-	for (int h = 8; h >= 1; h >>= 1) {
-		const bool up = (lane & (2 * h)) != 0;
-#pragma unroll
-		for (int i = 0; i < h; ++i) {
-			const double send = up ? v[i] : v[i + h];
-			const double keep = up ? v[i + h] : v[i];
-			v[i] = keep + shflXor(send, 2 * h);
-		}
-	}
-	return v[0] + shflXor(v[0], 1);
-}
-
-// CTA-wide totals of NV <= 16 values; every thread receives all of them, bitwise identical.
-template <int NV>
-__device__ __forceinline__ void blockSum16(double (&x)[NV], double* red, int& phase, int nw, int lane, int warp) {
-	double v[16];
-#pragma unroll
-	for (int i = 0; i < 16; ++i) v[i] = (i < NV) ? x[i] : 0.0;
-	double tot = warpSum16(v, lane);
-	if (nw > 1) {
-		double* buf = red + phase * (nw * 16);
-		if ((lane & 1) == 0) buf[warp * 16 + (lane >> 1)] = tot;
-		__syncthreads();
-		tot = buf[lane & 15];
-		for (int w = 1; w < nw; ++w) tot += buf[w * 16 + (lane & 15)];
-		phase ^= 1;
-#pragma unroll
-		for (int i = 0; i < NV; ++i) x[i] = __shfl_sync(0xffffffffu, tot, i);
-	} else {
-#pragma unroll
-		for (int i = 0; i < NV; ++i) x[i] = __shfl_sync(0xffffffffu, tot, 2 * i);
-	}
+// fit-only instances (no prediction in the kernel: predict_blocks.cu): the packed Gram rows [0, rowsInSmem), S, reduction scratch
+__host__ __device__ inline FastCarve fitOnlyCarve(int k, int nw, int rowsInSmem) {
+	FastCarve c;
+	const int rs = min(k, rowsInSmem);
+	int o = 0;
+	c.P = o; o += roundUp(rs * (rs + 1) / 2, 2);
+	c.S = o; o += roundUp(k, 2);
+	c.red = o; o += 2 * nw * 16;
+	c.sel = o;
+	c.total = o;
+	c.coef = c.part = c.stage = c.stageCols = c.xt = c.xtTasks = 0;
+	return c;
 }
 
 // One row of w = G S from the packed triangle in shared memory.  Thread r owns row r; the rows of a warp
@@ -708,11 +650,11 @@ __device__ __forceinline__ double symvRowSpill(const double* __restrict__ P, con
 // coalesced.
 // TRACE: the instance with the clock64() stamps, launched only when prm.trace is set (even predicated off they cost
 // a few per cent in the hot loops, measured on the kernel-space kernel)
-template <int AREG, bool SPILL, bool TRACE>
+// PRED: the held-out rows are predicted in the kernel; else the coefficients leave it for predictBlocksKernel
+template <int AREG, bool SPILL, bool TRACE, bool PRED>
 __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) simplsFitFast(const FitParams prm, const int stageAll, const int rSplit) {
 	extern __shared__ __align__(16) double smem[];
 	static_assert(AREG % 2 == 0 && AREG + 2 <= 16, "one reduction round holds tn^2, q*tn and every projection");
-	constexpr int MAXW = SPILL ? kMaxWarps : 8; // warps a CTA of this instantiation can have (bounds the unrolled gather)
 	const int NT = blockDim.x, NW = NT >> 5;
 
 	const int ci = blockIdx.x % prm.bucketCount;
@@ -726,7 +668,7 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
 	const int rs = SPILL ? min(k, rSplit) : k; // Gram rows [0, rs) live in shared memory
-	const FastCarve cv = fastCarve(k, A, NW, prm.maxTasks, prm.maxBlockLd, stageAll, rs);
+	const FastCarve cv = PRED ? fastCarve(k, A, NW, prm.maxTasks, prm.maxBlockLd, stageAll, rs) : fitOnlyCarve(k, NW, rs);
 	double* __restrict__ P = smem + cv.P;
 	double* __restrict__ S = smem + cv.S;
 	double* red = smem + cv.red;
@@ -753,13 +695,13 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 			bulkLoadF(reinterpret_cast<char*>(P) + o, reinterpret_cast<const char*>(gsrc) + o, min(32768u, bytes - o), &gramBar);
 		}
 	}
-	for (int i = tid; i < k; i += NT) sel[i] = prm.idx[selBegin + i];
+	if (PRED) for (int i = tid; i < k; i += NT) sel[i] = prm.idx[selBegin + i];
 	// descriptors of the held-out blocks this fit predicts (needed much later: load them now)
 	TaskDesc td[2];
 	BlockDesc bd[2];
 #pragma unroll
 	for (int t = 0; t < 2; ++t) {
-		if (t < fd.taskCount) {
+		if (PRED && t < fd.taskCount) {
 			td[t] = prm.tasks[fd.taskBegin + t];
 			bd[t] = prm.blocks[td[t].block];
 		} else {
@@ -825,6 +767,31 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 		}
 		__syncthreads();
 		GSB_STAMP(); // 2 + comp
+	}
+
+	if (!PRED) {
+		// ---- the rows [coef; -1; intercepts] of this fit leave the kernel (predict_blocks.cu) ---------------
+		double* __restrict__ cdst = prm.coefScratch + prm.coefOff[chrom] + static_cast<size_t>(fi) * (static_cast<size_t>(k) + 2) * A;
+		if (valid) {
+#pragma unroll
+			for (int j = 0; j < AREG; ++j) if (j < A) cdst[static_cast<size_t>(r) * A + j] = cOwn[j];
+		}
+		// intercepts b0[a] = ym - xm'coef[:,a] (:162)
+		double b0s[AREG];
+#pragma unroll
+		for (int j = 0; j < AREG; ++j) b0s[j] = (valid && j < A) ? xmOwn * cOwn[j] : 0.0;
+		blockSum16<AREG>(b0s, red, phase, NW, lane, warp);
+		if (tid == 0) {
+#pragma unroll
+			for (int j = 0; j < AREG; ++j) {
+				if (j < A) {
+					cdst[static_cast<size_t>(k) * A + j] = -1.0;
+					cdst[static_cast<size_t>(k + 1) * A + j] = fd.ym - b0s[j];
+				}
+			}
+		}
+		GSB_STAMP();
+		return;
 	}
 
 	// ---- the Gram area is dead: coefficients go there, the held-out rows are fetched ---------------
@@ -1097,12 +1064,21 @@ inline int fastRowsInSmem(int k, int A, int maxTasks, int maxBlockLd, int smemLi
 	return rs >= 32 ? rs : 0;
 }
 
-template <int AREG>
+// fit-only instances: rows of the packed Gram that fit in shared memory (a multiple of 32, or k)
+inline int fitOnlyRowsInSmem(int k, int smemLimit) {
+	const int nw = roundUp(k, 32) / 32;
+	if (fitOnlyCarve(k, nw, k).total * 8 <= smemLimit) return k;
+	int rs = (k / 32) * 32;
+	while (rs >= 32 && fitOnlyCarve(k, nw, rs).total * 8 > smemLimit) rs -= 32;
+	return rs >= 32 ? rs : 0;
+}
+
+template <int AREG, bool PRED>
 cudaError_t launchFast(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
 	const int threads = roundUp(kMax, 32);
-	const int rs = fastRowsInSmem(kMax, A, prm.maxTasks, prm.maxBlockLd, smemLimit);
+	const int rs = PRED ? fastRowsInSmem(kMax, A, prm.maxTasks, prm.maxBlockLd, smemLimit) : fitOnlyRowsInSmem(kMax, smemLimit);
 	if (rs <= 0) return cudaErrorInvalidValue;
-	const FastCarve cv = fastCarve(kMax, A, threads / 32, prm.maxTasks, prm.maxBlockLd, -1, rs);
+	const FastCarve cv = PRED ? fastCarve(kMax, A, threads / 32, prm.maxTasks, prm.maxBlockLd, -1, rs) : fitOnlyCarve(kMax, threads / 32, rs);
 	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double);
 	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
 	if (grid <= 0) return cudaSuccess;
@@ -1110,18 +1086,18 @@ cudaError_t launchFast(const FitParams& prm, int kMax, int A, int smemLimit, cud
 	cudaError_t err;
 	if (rs >= kMax) {
 		if (prm.trace != nullptr) {
-			err = cudaFuncSetAttribute(simplsFitFast<AREG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+			err = cudaFuncSetAttribute(simplsFitFast<AREG, false, true, PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 			if (err != cudaSuccess) return err;
-			simplsFitFast<AREG, false, true><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
+			simplsFitFast<AREG, false, true, PRED><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
 		} else {
-			err = cudaFuncSetAttribute(simplsFitFast<AREG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+			err = cudaFuncSetAttribute(simplsFitFast<AREG, false, false, PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 			if (err != cudaSuccess) return err;
-			simplsFitFast<AREG, false, false><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
+			simplsFitFast<AREG, false, false, PRED><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, kMax);
 		}
 	} else {
-		err = cudaFuncSetAttribute(simplsFitFast<AREG, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+		err = cudaFuncSetAttribute(simplsFitFast<AREG, true, false, PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 		if (err != cudaSuccess) return err;
-		simplsFitFast<AREG, true, false><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, rs);
+		simplsFitFast<AREG, true, false, PRED><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm, cv.xtTasks, rs);
 	}
 	if (ctas) *ctas += grid;
 	return cudaGetLastError();
@@ -1159,13 +1135,26 @@ int fitKernelMaxK(int A, int smemLimit) {
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
 	const int Ak = (A < kMax) ? A : kMax;
 	if (Ak <= kFastComponents && kMax <= kMaxWarps * 32 && fastRowsInSmem(kMax, Ak, prm.maxTasks, prm.maxBlockLd, smemLimit) > 0) {
-		return launchFast<kFastComponents>(prm, kMax, Ak, smemLimit, stream, ctas); // per-row state in registers
+		return launchFast<kFastComponents, true>(prm, kMax, Ak, smemLimit, stream, ctas); // per-row state in registers
 	}
 	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true, roundUp(kMax, 32) / 32).total * 8 <= smemLimit) {
 		return launchOne<1, true>(prm, kMax, Ak, roundUp(kMax, 32), stream, ctas); // one thread per row
 	}
 	if (kMax > 4 * kMaxWarps * 32 || carve(kMax, Ak, false, kMaxWarps).total * 8 > smemLimit) return cudaErrorInvalidValue;
 	return launchOne<4, false>(prm, kMax, Ak, kMaxWarps * 32, stream, ctas);         // Gram read in place (L2)
+}
+
+// The fit-only instance of the fast path (A <= 10 components, k <= 384) serves this class: its coefficients go to
+// predictBlocksKernel
+bool fitOnlyKernelServes(int kMax, int A, int smemLimit) {
+	const int Ak = (A < kMax) ? A : kMax;
+	return Ak <= kFastComponents && kMax <= kMaxWarps * 32 && fitOnlyRowsInSmem(kMax, smemLimit) > 0;
+}
+
+cudaError_t launchFitOnlyKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas) {
+	const int Ak = (A < kMax) ? A : kMax;
+	if (!fitOnlyKernelServes(kMax, A, smemLimit) || prm.coefScratch == nullptr) return cudaErrorInvalidValue;
+	return launchFast<kFastComponents, false>(prm, kMax, Ak, smemLimit, stream, ctas);
 }
 
 } // namespace gsb
