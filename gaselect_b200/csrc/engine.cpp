@@ -486,6 +486,7 @@ void buildUnitTables(gsb_engine* e) {
 		}
 		d.nT = static_cast<double>(fit.rows.size());
 		d.sy = sy;
+		d.rnT = 1.0 / d.nT;
 	}
 	e->packFits.upload(pf, e->stream);
 	GSB_CUDA(cudaStreamSynchronize(e->stream));

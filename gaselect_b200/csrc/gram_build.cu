@@ -260,61 +260,126 @@ __global__ void __launch_bounds__(kPackThreads) gramPackVectorsKernel(const Pack
 			double sx = tSum[lane * ldt], xy = tXy[lane * ldt];
 			if (pf.u1 >= 0) { sx -= tSum[lane * ldt + pf.u1]; xy -= tXy[lane * ldt + pf.u1]; }
 			if (pf.u2 >= 0) { sx -= tSum[lane * ldt + pf.u2]; xy -= tXy[lane * ldt + pf.u2]; }
-			out[static_cast<size_t>(f) * 2 * kp + a0 + lane] = xy - sx * pf.sy / pf.nT;
-			out[static_cast<size_t>(f) * 2 * kp + kp + a0 + lane] = sx / pf.nT;
+			out[static_cast<size_t>(f) * 2 * kp + a0 + lane] = xy - sx * pf.sy * pf.rnT;
+			out[static_cast<size_t>(f) * 2 * kp + kp + a0 + lane] = sx * pf.rnT;
 		}
 	}
 }
 
 // The packed centred Gram of the selected columns for every training set of a chromosome (the arithmetic of
-// combineGramKernel).  grid: (tiles of `entries` packed entries, chromosomes of the launch).  A warp fetches the
-// unit run of an entry (upad contiguous doubles: every sector it touches is used), the CTA then writes, per
-// training set, `entries` consecutive doubles of that set's slab.
-__global__ void __launch_bounds__(kPackThreads) gramPackKernel(const PackParams prm, const int entries) {
+// combineGramKernel).  One CTA per (tile of 2 rows x 32 columns of the lower triangle, chromosome):
+//   1  the unit runs of its <= 64 entries are fetched (upad contiguous doubles each: every sector touched is used; four
+//      runs per warp in flight: the column ids come from shared memory),
+//   2  a warp per training set: the set's column means of the tile's 32 columns (one coalesced read of the vectors
+//      gramPackVectorsKernel has just written) and of its 2 rows, g = t_full - t_u1 - t_u2 - n_T xm_i xm_j, written as
+//      runs of 32 consecutive doubles of the set's packed slab.
+// The kernel is bound by what it writes (150 slabs per chromosome at config 3/4); shared-memory traffic is 7 wavefronts
+// per 32 entries written.
+constexpr int kPackRows = 2;
+constexpr int kPackCols = 32;
+
+// tiles of a k-column subset: row pairs p = 0 .. ceil(k / 2) - 1 (rows 2p, 2p + 1), column blocks 0 .. (2p + 1) / 32
+__host__ __device__ inline int packTiles(int k) {
+	const int pairs = (k + 1) >> 1;
+	const int m = pairs >> 4, r = pairs & 15;
+	return pairs + 8 * m * (m - 1) + r * m;
+}
+
+__global__ void __launch_bounds__(kPackThreads) gramPackKernel(const PackParams prm) {
 	extern __shared__ __align__(16) double psm[];
 	const int chrom = prm.bucket[blockIdx.y];
 	const uint32_t selBegin = prm.offsets[chrom];
 	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
-	const int ntri = k * (k + 1) / 2;
-	const int e0 = blockIdx.x * entries;
-	if (e0 >= ntri) return;
-	const int ne = min(entries, ntri - e0);
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int ldt = prm.upad + 1;
-	double* __restrict__ tile = psm;
-	int* __restrict__ ai = reinterpret_cast<int*>(psm + entries * ldt);
-	int* __restrict__ aj = ai + entries;
-	for (int e = warp; e < ne; e += kPackThreads / 32) {
-		const int E = e0 + e;
-		int i = static_cast<int>((sqrtf(8.0f * static_cast<float>(E) + 1.0f) - 1.0f) * 0.5f);
-		while ((i + 1) * (i + 2) / 2 <= E) ++i;
-		while (i * (i + 1) / 2 > E) --i;
-		const int j = E - i * (i + 1) / 2;
-		// ascending column lists: sel[i] >= sel[j]
-		const unsigned long long gi = prm.idx[selBegin + i], gj = prm.idx[selBegin + j];
-		const double* __restrict__ run = prm.unitTab + (tri(gi) + gj) * prm.upad;
-		for (int u = lane; u < prm.upad; u += 32) tile[e * ldt + u] = run[u];
-		if (lane == 0) { ai[e] = i; aj[e] = j; }
+	if (static_cast<int>(blockIdx.x) >= packTiles(k)) return;
+	// tile -> (row pair, column block): pairs [16 m, 16 m + 16) have m + 1 column blocks each
+	int t = static_cast<int>(blockIdx.x), m = 0;
+	while (t >= 16 * (m + 1)) { t -= 16 * (m + 1); ++m; }
+	const int pair = 16 * m + t / (m + 1), jb = t % (m + 1);
+	const int i0 = 2 * pair, j0 = 32 * jb;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int upad = prm.upad, ldt = upad | 1; // odd leading dimension: conflict-free across entries
+	constexpr int NC = kPackRows + kPackCols;  // its rows, then its columns
+	constexpr int NE = kPackRows * kPackCols;
+	double* __restrict__ tile = psm;                                          // [NE][ldt] unit runs of the entries (row-major over the tile)
+	PackFit* __restrict__ pfs = reinterpret_cast<PackFit*>(tile + NE * ldt);  // [nfits]
+	uint32_t* __restrict__ cols = reinterpret_cast<uint32_t*>(pfs + prm.nfits); // [NC] global column ids
+
+	if (tid < NC) {
+		const int local = tid < kPackRows ? i0 + tid : j0 + (tid - kPackRows);
+		cols[tid] = prm.idx[selBegin + min(local, k - 1)];
+	}
+	for (int f = tid; f < prm.nfits; f += kPackThreads) pfs[f] = prm.pfits[f];
+	__syncthreads();
+
+	// ---- 1: the runs.  Entry e = row * 32 + column; valid when column <= row < k (lower triangle)
+	for (int e0 = warp * 4; e0 < NE; e0 += (kPackThreads / 32) * 4) {
+		const double* src[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int e = e0 + q;
+			const int i = i0 + e / kPackCols, j = j0 + (e % kPackCols);
+			src[q] = nullptr;
+			if (i < k && j <= i) {
+				// ascending column lists: sel[i] >= sel[j]
+				const unsigned long long gi = cols[e / kPackCols], gj = cols[kPackRows + (e % kPackCols)];
+				src[q] = prm.unitTab + (tri(gi) + gj) * upad;
+			}
+		}
+		for (int u = lane; u < upad; u += 32) {
+			double v[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) v[q] = src[q] ? __ldg(src[q] + u) : 0.0;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) tile[(e0 + q) * ldt + u] = v[q];
+		}
 	}
 	__syncthreads();
+
+	// ---- 2: a warp per training set; lane = column of the tile
 	const int kp = (k + 1) & ~1;
 	const size_t slab = static_cast<size_t>(packedDoubles(static_cast<unsigned long long>(k)));
 	double* __restrict__ out = prm.gpack + prm.packOff[chrom];
 	const double* __restrict__ vec = prm.pvec + prm.vecOff[chrom];
-	for (int e = lane; e < ne; e += 32) {
-		const int i = ai[e], j = aj[e];
-		const double t0 = tile[e * ldt];
-		for (int f = warp; f < prm.nfits; f += kPackThreads / 32) {
-			const PackFit pf = prm.pfits[f];
+	const int j = j0 + lane;
+	const int jc = min(j, k - 1);
+	const bool on0 = i0 < k && j <= i0, on1 = i0 + 1 < k && j <= i0 + 1;
+	const double* __restrict__ tr0 = tile + lane * ldt;
+	const double* __restrict__ tr1 = tile + (kPackCols + lane) * ldt;
+	const double full0 = tr0[0], full1 = tr1[0];
+	const size_t at0 = static_cast<size_t>(tri(static_cast<unsigned long long>(i0))) + j;
+	const size_t at1 = static_cast<size_t>(tri(static_cast<unsigned long long>(i0 + 1))) + j;
+	const int i1c = min(i0 + 1, k - 1);
+	constexpr int FU = 4; // training sets per iteration: their vector reads are in flight together
+	for (int f0 = warp; f0 < prm.nfits; f0 += FU * (kPackThreads / 32)) {
+		double xj[FU], xi0[FU], xi1[FU];
+#pragma unroll
+		for (int q = 0; q < FU; ++q) {
+			const int f = min(f0 + q * (kPackThreads / 32), prm.nfits - 1);
 			const double* __restrict__ xmf = vec + static_cast<size_t>(f) * 2 * kp + kp;
-			double g = t0;
-			if (pf.u1 >= 0) g -= tile[e * ldt + pf.u1];
-			if (pf.u2 >= 0) g -= tile[e * ldt + pf.u2];
-			g -= pf.nT * xmf[i] * xmf[j];
-			out[static_cast<size_t>(f) * slab + e0 + e] = g;
+			xj[q] = __ldg(xmf + jc);
+			xi0[q] = __ldg(xmf + i0);
+			xi1[q] = __ldg(xmf + i1c);
+		}
+#pragma unroll
+		for (int q = 0; q < FU; ++q) {
+			const int f = f0 + q * (kPackThreads / 32);
+			if (f < prm.nfits) {
+				const PackFit pf = pfs[f];
+				double* __restrict__ of = out + static_cast<size_t>(f) * slab;
+				double g0 = full0, g1 = full1;
+				if (pf.u1 >= 0) { g0 -= tr0[pf.u1]; g1 -= tr1[pf.u1]; }
+				if (pf.u2 >= 0) { g0 -= tr0[pf.u2]; g1 -= tr1[pf.u2]; }
+				g0 -= pf.nT * xi0[q] * xj[q];
+				g1 -= pf.nT * xi1[q] * xj[q];
+				if (on0) of[at0] = g0;
+				if (on1) of[at1] = g1;
+			}
 		}
 	}
-	if (blockIdx.x == 0 && (ntri & 1) && threadIdx.x < prm.nfits) out[static_cast<size_t>(threadIdx.x) * slab + ntri] = 0.0; // the padding double
+	// the padding double of an odd triangle
+	if (blockIdx.x == 0 && ((k * (k + 1) / 2) & 1)) {
+		for (int f = tid; f < prm.nfits; f += kPackThreads) out[static_cast<size_t>(f) * slab + static_cast<size_t>(k) * (k + 1) / 2] = 0.0;
+	}
 }
 
 // dst[:, c] = z[rows, cols ? cols[c] : c], zero-padded to ld rows
@@ -371,15 +436,14 @@ cudaError_t launchGramPack(const PackParams& prm, int kMax, cudaStream_t stream)
 	if (err != cudaSuccess) return err;
 	dim3 gv(static_cast<unsigned>((kMax + 31) / 32), static_cast<unsigned>(prm.bucketCount));
 	gramPackVectorsKernel<<<gv, kPackThreads, static_cast<size_t>(vbytes), stream>>>(prm);
-	// entries per CTA: a tile of at most ~56 KB
-	int entries = 64;
-	while (entries > 8 && entries * ldt * 8 > 56 * 1024) entries >>= 1;
-	const int gbytes = entries * ldt * static_cast<int>(sizeof(double)) + 2 * entries * static_cast<int>(sizeof(int));
+	const int ldg = prm.upad | 1;
+	const int NC = kPackRows + kPackCols, NE = kPackRows * kPackCols;
+	const int gbytes = NE * ldg * static_cast<int>(sizeof(double)) + prm.nfits * static_cast<int>(sizeof(PackFit)) +
+	                   NC * static_cast<int>(sizeof(uint32_t)) + 16;
 	err = cudaFuncSetAttribute(gramPackKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gbytes);
 	if (err != cudaSuccess) return err;
-	const int ntri = kMax * (kMax + 1) / 2;
-	dim3 gg(static_cast<unsigned>((ntri + entries - 1) / entries), static_cast<unsigned>(prm.bucketCount));
-	gramPackKernel<<<gg, kPackThreads, static_cast<size_t>(gbytes), stream>>>(prm, entries);
+	dim3 gg(static_cast<unsigned>(packTiles(kMax)), static_cast<unsigned>(prm.bucketCount));
+	gramPackKernel<<<gg, kPackThreads, static_cast<size_t>(gbytes), stream>>>(prm);
 	return cudaGetLastError();
 }
 

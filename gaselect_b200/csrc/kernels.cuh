@@ -36,6 +36,7 @@ struct PackFit {
 	int u1, u2;   // excluded units (indices into a unitTab run), -1: none
 	double nT;    // number of training rows
 	double sy;    // sum of yc over the training rows (unit sums combined in the same order as every other moment)
+	double rnT;   // 1 / nT: the column means are sums * rnT everywhere (vectors and Gram centring agree to the bit)
 };
 
 struct TaskDesc {

@@ -131,7 +131,7 @@ __global__ void kProbe(double* out, long long* clk, int iters, int mode, int row
 			double acc[32], sI[32];
 #pragma unroll
 			for (int j = 0; j < 32; ++j) { acc[j] = 0.0; sI[j] = S[(lane ^ j) + 32 * (it & 7)]; }
-			double accT = 0.0;
+			double accT = 0.0, accU = 0.0, accV = 0.0, accW = 0.0;
 			for (int ch = 0; ch < chunks; ++ch) {
 				uint32_t r[64];
 				const uint32_t a = mine + (uint32_t)((ch * 64) % cols);
@@ -139,12 +139,20 @@ __global__ void kProbe(double* out, long long* clk, int iters, int mode, int row
 				const double sJ = S[((ch * 32) & 255) + lane];
 				waitLd(); tie32(r); tie32(r + 32);
 #pragma unroll
-				for (int j = 0; j < 32; ++j) {
-					const double g = d2(r[2 * j], r[2 * j + 1]);
-					acc[j] = fma(g, sJ, acc[j]);
-					accT = fma(g, sI[j], accT);
+				for (int j = 0; j < 32; j += 4) {
+					const double g0 = d2(r[2 * j], r[2 * j + 1]), g1 = d2(r[2 * j + 2], r[2 * j + 3]);
+					const double g2 = d2(r[2 * j + 4], r[2 * j + 5]), g3 = d2(r[2 * j + 6], r[2 * j + 7]);
+					acc[j] = fma(g0, sJ, acc[j]);
+					accT = fma(g0, sI[j], accT);
+					acc[j + 1] = fma(g1, sJ, acc[j + 1]);
+					accU = fma(g1, sI[j + 1], accU);
+					acc[j + 2] = fma(g2, sJ, acc[j + 2]);
+					accV = fma(g2, sI[j + 2], accV);
+					acc[j + 3] = fma(g3, sJ, acc[j + 3]);
+					accW = fma(g3, sI[j + 3], accW);
 				}
 			}
+			accT = (accT + accU) + (accV + accW);
 #pragma unroll
 			for (int m = 16; m >= 1; m >>= 1) {
 #pragma unroll
