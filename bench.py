@@ -5,13 +5,19 @@ A "step" is ONE generation's fitness pass: every chromosome of the population is
 R*O*(I+1) cross-validated SIMPLS fits (BASELINE.json config "evaluatorPLS repeated double CV
 (10 outer reps, 5/4 segments, <=10 components), n=150 p=1000 NIR-like spectra, population 500").
 At N GPUs every rank scores its own 500-chromosome shard of a 500*N population (weak scaling; the
-units are independent, the only exchange is the all-gather of the fitness vectors over NCCL).
+units are independent, the only exchange is the all-gather of the fitness vectors over NCCL);
+--scaling strong splits ONE generation (500 at cfg3, 2000 at cfg4) over the ranks instead.  Rank 0
+checks once, outside the timed region, that the un-permuted gathered vector equals its own
+single-GPU evaluation of the whole generation bit for bit.  --single-process drives the same N
+GPUs from ONE process through the multi-device engine of the C ABI (gsb_config.devices).
 
   value     device-resident throughput: population already in HBM, K1+K2 enqueued per step
   e2e       through the public call (gsb_evaluate_indices) with HOST buffers: per step the CSR
             lists go host->device and fitness/status come back
-  roofline  K1 (simplsScoreKernel, the score-space FP64 tensor-core kernel; simplsFitFast beyond its capacity)
-            algorithmic bytes / its CUDA-event time
+  roofline  K1 of the workload: cfg3 = simplsKspaceKernel (FP64 tensor pipe: algorithmic FLOPs of SURVEY.md 8d and the
+            DMMA FLOPs issued, against the measured cuBLAS DGEMM rate), cfg4 = the per-fit Gram-space path
+            (gramPack + simplsFitFast + predictBlocks; HBM: algorithmic bytes of SURVEY.md 8d / its CUDA-event time);
+            traffic = DRAM bytes of those launches from the committed ncu pass (profiles/r02_traffic.json) or null
   L2        the path's inputs are small by nature (Z is 1.2 MB): a 256 MB buffer is overwritten before every step,
             inside the timed region, so that no step finds its inputs in L2
   cpu_baseline / --impl reference: the reference's own evaluator code (oracle/_ref, built from
@@ -35,11 +41,14 @@ from gaselect_b200 import synth  # noqa: E402
 
 WORKLOADS = {
     # BASELINE.json configs[2]: the configuration the metric (repeated-CV PLS) is quoted on
-    "cfg3": dict(n=150, p=1000, pop=500, kmin=10, kmax=200, data_seed=777,
+    "cfg3": dict(n=150, p=1000, pop=500, strong_pop=500, kmin=10, kmax=200, data_seed=777,
                  kw=dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)),
     # BASELINE.json configs[3] shape, per-GPU shard of the 2000-chromosome population
-    "cfg4": dict(n=500, p=5000, pop=250, kmin=20, kmax=200, data_seed=778,
+    "cfg4": dict(n=500, p=5000, pop=250, strong_pop=2000, kmin=20, kmax=200, data_seed=778,
                  kw=dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)),
+    # the same with SURVEY.md 8(d)'s subset sizes 20..400 (beyond 232 columns the packed Gram no longer fits in shared memory)
+    "cfg4w": dict(n=500, p=5000, pop=250, strong_pop=2000, kmin=20, kmax=400, data_seed=778,
+                  kw=dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)),
 }
 GA_SEED = 123
 
@@ -53,6 +62,15 @@ def bytes_eval(k, seg_lengths):
     for inner, outer in seg_lengths:
         total += sum(bytes_fit(k, t) for t in inner) + bytes_fit(k, outer)
     return total
+
+
+def flops_eval(k, seg_lengths, max_ncomp):
+    """algorithmic FLOPs of one evaluation in Gram space,
+    flops_fit = A (2 k^2 + 8 k) + 2 k A (A - 1) + 2 n_te k A + 3 n_te A, over the R*O*(I+1) fits the reference runs."""
+    A = min(max_ncomp, k)
+    def flops_fit(nte):
+        return A * (2.0 * k * k + 8.0 * k) + 2.0 * k * A * (A - 1) + 2.0 * nte * k * A + 3.0 * nte * A
+    return sum(sum(flops_fit(t) for t in inner) + flops_fit(outer) for inner, outer in seg_lengths)
 
 
 def group_lengths(seg, inner):
@@ -144,11 +162,28 @@ def cpu_leg(w, X, y, subsets, budget_s):
                       (rounds, len(sample), len(subsets), w["kmin"], w["kmax"], cores, spent)}, done, spent
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the K1 launches of ONE step from the committed
-# ncu --set full capture (profiles/r01_summary.txt); only valid for the default workload
-MEASURED_TRAFFIC = {("cfg3", 500): 4.477e8}
-# FP64 tensor-core peak: 148 SMs x 4 sub-partitions x 256 FMA per DMMA.8x8x4 / 16 cycles x 1.965 GHz x 2
-DMMA_PEAK_TFLOPS = 37.2
+def measured_traffic(workload, pop):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the K1 launches of ONE step, from the committed ncu
+    pass over this command (profiles/r02_traffic.sh -> profiles/r02_traffic.json); None when there is no capture of
+    this workload and population."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get("%s/%d" % (workload, pop))
+    except (OSError, ValueError):
+        return None, None
+    if not rec:
+        return None, None
+    return float(rec["k1_dram_bytes_per_step"]), rec["source"]
+
+
+def fp64_peak():
+    """FP64 tensor peak by BASELINE.md section 3's protocol (cuBLAS DGEMM 8192^3, best of 10 and 4 s sustained:
+    profiles/fp64_peak.py -> profiles/r02_fp64_peak.json); the DMMA issue-rate figure of the microbenchmark
+    (profiles/micro/dmma_probe_b200.txt: one DMMA.8x8x4 per 16 cycles per sub-partition = 37.2 TFLOP/s) as the fallback."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_fp64_peak.json")))
+        return float(rec["fp64_dgemm_tflops_sustained"]), "measured: cuBLAS DGEMM 8192^3 sustained, profiles/r02_fp64_peak.json (burst %.1f)" % rec["fp64_dgemm_tflops"]
+    except (OSError, ValueError, KeyError):
+        return 37.2, "DMMA issue rate, profiles/micro/dmma_probe_b200.txt"
 
 
 def main():
@@ -161,27 +196,38 @@ def main():
     ap.add_argument("--pop", type=int, default=0, help="chromosomes per GPU (default: the workload's)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's population per GPU; strong: ONE generation (cfg3 500, cfg4 2000) split over the GPUs")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive --gpus N devices from this ONE process through the multi-device engine of the C ABI")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    ndev = args.gpus if args.single_process else 1   # devices driven by this process
+    units = world * ndev                              # GPUs of the job
     w = dict(WORKLOADS[args.workload])
     if args.pop:
         w["pop"] = args.pop
+        w["strong_pop"] = args.pop
+    global_pop = w["strong_pop"] if args.scaling == "strong" else w["pop"] * units
+    w["pop"] = -(-global_pop // units)               # chromosomes per GPU (the last GPUs may hold one less)
     X, y = synth.nir_spectra(w["n"], w["p"], seed=w["data_seed"], noise=1e-2)
     config = {"workload": "%s: evaluatorPLS rdCV R=%d outer=%d inner=%d maxNComp=%d, NIR-like n=%d p=%d (noise 1e-2), "
                           "population %d per GPU, subset sizes U[%d,%d]" %
                           (args.workload, w["kw"]["numReplications"], w["kw"]["outerSegments"], w["kw"]["innerSegments"],
                            w["kw"]["maxNComp"], w["n"], w["p"], w["pop"], w["kmin"], w["kmax"]),
-              "population_per_gpu": w["pop"], "global_population": w["pop"] * world, "ga_seed": GA_SEED,
-              "parallelism": "generation of %d chromosomes dealt to %d GPU(s) (equal counts, longest-processing-time-first on "
-                              "the kernels' measured cost); fitness all-gather over NCCL" % (w["pop"] * world, world)}
+              "population_per_gpu": w["pop"], "global_population": global_pop, "ga_seed": GA_SEED,
+              "parallelism": ("generation of %d chromosomes dealt to %d GPU(s) (equal counts, longest-processing-time-first on "
+                              "the kernels' measured cost); " % (global_pop, units)) +
+                             ("ONE process, multi-device engine of the C ABI (gsb_config.devices): peer-copy gather" if args.single_process
+                              else "one process per GPU, fitness all-gather over NCCL")}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        subsets = synth.random_subsets(w["p"], w["pop"], w["kmin"], w["kmax"], seed=42)
+        subsets = synth.random_subsets(w["p"], global_pop, w["kmin"], w["kmax"], seed=42)[: max(w["pop"], 1)]
         lib, kind = reference_library()
         cores = os.cpu_count() or 1
         ev = lib.pls_evaluator(X, y, lib.make_seedvec(GA_SEED), **w["kw"])
@@ -201,7 +247,7 @@ def main():
         sample = "%d chromosomes of the generation per step, %d host threads" % (per_step, cores)
         print(json.dumps({"impl": "reference", "metric": "chromosome fitness evals/sec (repeated-CV PLS)", "value": v,
                           "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": args.scaling,
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -221,71 +267,117 @@ def main():
         # unchanged -- the all-gather costs 12 us, the rest of the 1 -> N GPU gap was this allocation order
         dist.init_process_group("nccl")
 
-    # the (500 * N)-chromosome generation is dealt to the ranks (equal counts, balanced on the kernels' measured cost)
+    # the generation is dealt to the ranks (equal counts, balanced on the kernels' measured cost)
     from gaselect_b200 import multigpu
-    generation = synth.random_subsets(w["p"], w["pop"] * world, w["kmin"], w["kmax"], seed=42)
+    generation = synth.random_subsets(w["p"], global_pop, w["kmin"], w["kmax"], seed=42)
     sizes = [len(s) for s in generation]
     cost = multigpu.kspace_cost(sizes) if w["n"] <= 160 else multigpu.gram_cost(sizes)
-    subsets = [generation[i] for i in multigpu.deal(sizes, world, cost=cost, equal_counts=True)[rank]]
+    shares = multigpu.deal(sizes, world, cost=cost, equal_counts=True)
+    subsets = [generation[i] for i in shares[rank]]  # (single process: everything; the engine deals it to its devices)
     idx, offsets = _capi.to_csr(subsets)
     ks = np.diff(offsets.astype(np.int64))
 
-    ev = E.PLSEvaluator(X, y, GA_SEED, device=local_rank, **w["kw"])
+    if args.single_process:
+        ev = E.PLSEvaluator(X, y, GA_SEED, devices=list(range(ndev)), **w["kw"])
+    else:
+        ev = E.PLSEvaluator(X, y, GA_SEED, device=local_rank, **w["kw"])
     info = ev.prepare()
     # the engine works on torch's current stream, so torch.cuda.Event brackets see its kernels
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    ev.set_stream(stream.cuda_stream)
+    if not args.single_process:
+        ev.set_stream(stream.cuda_stream)
     seg = ev.getSegmentation()
     lengths = group_lengths(seg, info["inner_segments"])
-    algo_bytes = float(sum(bytes_eval(int(k), lengths) for k in ks))
+    all_ks = np.asarray(sizes, dtype=np.int64)
+    algo_bytes = float(sum(bytes_eval(int(k), lengths) for k in all_ks)) / units      # per GPU and step (mean over the GPUs)
+    algo_flops = float(sum(flops_eval(int(k), lengths, info["max_ncomp"]) for k in all_ks)) / units
 
     fitness = np.zeros(len(subsets), dtype=np.float64)
     status = np.zeros(len(subsets), dtype=np.int32)
     ev.upload_population(idx, offsets)
-    f_ptr, s_ptr, npop = ev.device_results()
+    cap = max(len(s) for s in shares)
+    dev = torch.device("cuda", local_rank)
+    d_fit = send = gathered = None
+    if not args.single_process:
+        f_ptr, s_ptr, npop = ev.device_results()
 
-    class _Dev:  # zero-copy view of the engine's result buffer for NCCL
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-    d_fit = torch.as_tensor(_Dev(f_ptr, npop), device=torch.device("cuda", local_rank))
-    gathered = torch.empty(world * npop, dtype=torch.float64, device=d_fit.device) if world > 1 else None
+        class _Dev:  # zero-copy view of the engine's result buffer for NCCL
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        d_fit = torch.as_tensor(_Dev(f_ptr, npop), device=dev)
+        # equal-sized all-gather pieces: the engine's buffer itself when every rank holds `cap` chromosomes
+        send = d_fit if npop == cap else torch.zeros(cap, dtype=torch.float64, device=dev)
+        gathered = torch.empty(world * cap, dtype=torch.float64, device=dev) if world > 1 else None
 
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank))  # 2 x L2
+    flush_bufs = []
+    for d in range(ndev):  # 2 x L2 on every device this process drives
+        flush_bufs.append(torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", local_rank + d)))
+    flush_buf = flush_bufs[0]
+
+    def flush():
+        flush_buf.zero_()  # L2 flush, on the timed stream
+        for b in flush_bufs[1:]:
+            b.zero_()
+
+    def all_gather():
+        if world > 1:
+            if send is not d_fit:
+                send[: d_fit.numel()].copy_(d_fit)
+            dist.all_gather_into_tensor(gathered, send)
 
     def step_resident():
-        flush_buf.zero_()  # L2 flush, on the timed stream
-        ev.enqueue_resident()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_fit)
+        flush()
+        if args.single_process:
+            ev.evaluate_resident()  # the replicas run on their own streams: the call returns when every device is done
+        else:
+            ev.enqueue_resident()
+        all_gather()
 
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        for d in range(ndev):
+            torch.cuda.synchronize(local_rank + d)
 
     # ---- value: device-resident -------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
+    gather_check = None
+    if world > 1 and rank == 0:
+        # the gathered vector, un-permuted, against this GPU's own evaluation of the WHOLE generation: bit for bit
+        got = np.zeros(len(generation), dtype=np.float64)
+        g = gathered.cpu().numpy().reshape(world, cap)
+        for r, share in enumerate(shares):
+            got[share] = g[r, : len(share)]
+        with E.PLSEvaluator(X, y, GA_SEED, device=local_rank, **w["kw"]) as whole:
+            want, wst = whole.evaluate_population(generation)
+        gather_check = {"chromosomes": len(generation), "bit_identical": bool((got == want).all() and (wst == 0).all())}
+        assert gather_check["bit_identical"], "the gathered fitness vector differs from the single-GPU evaluation"
+    if world > 1:
+        dist.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step_resident()
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
+    # one process per GPU: CUDA events on the stream the kernels run on.  Single process, several devices: the engine's
+    # replicas run on their own streams, so the host clock around the synchronous calls is the measure
+    ms = 1e3 * (time.perf_counter() - t_host) if args.single_process else e0.elapsed_time(e1)
     launches = ev.timing()["kernel_launches"] * args.steps
     # K1 timed live with the engine's CUDA events on the same stream, per step
     k1_ms, k2_ms = [], []
     tensor_gflop = 0.0
     for _ in range(args.steps):
-        flush_buf.zero_()
+        flush()
         ev.evaluate_resident()
         t = ev.timing()
         k1_ms.append(t["fit_kernel_ms"])
@@ -302,10 +394,9 @@ def main():
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
-        flush_buf.zero_()
+        flush()
         f2, s2 = ev.evaluate_csr(idx, offsets)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_fit)
+        all_gather()
     e1.record(stream)
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
@@ -313,8 +404,16 @@ def main():
     h2d = int(idx[: int(offsets[-1])].nbytes + offsets.nbytes + 4 * len(subsets))
     d2h = int(fitness.nbytes + status.nbytes)
 
+    if args.single_process:
+        single_check = None
+        if ndev > 1:  # the multi-device engine against one device, bit for bit
+            with E.PLSEvaluator(X, y, GA_SEED, device=local_rank, **w["kw"]) as whole:
+                want, wst = whole.evaluate_population(subsets)
+            single_check = {"chromosomes": len(subsets), "bit_identical": bool((fitness == want).all() and (wst == status).all())}
+            assert single_check["bit_identical"], "the multi-device engine differs from the single-device engine"
+        gather_check = single_check
     if world > 1:
-        tt = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=d_fit.device)
+        tt = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(tt[0]), float(tt[1])
     if rank == 0:
@@ -326,39 +425,56 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         k1 = float(np.mean(k1_ms))
         achieved = algo_bytes / (k1 * 1e-3) / 1e9
+        peak64, peak64_src = fp64_peak()
+        traffic, traffic_src = measured_traffic(args.workload, w["pop"])
+        kspace = tensor_gflop > 0.0  # the kernel-space kernel ran (n <= 160, <= 10 components): the FP64 tensor pipe binds
+        hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+               "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+               "algorithmic_bytes_per_step": algo_bytes,
+               "note": "SURVEY 8(d)'s algorithmic bytes (the logical inputs of every fit in the Gram formulation) of one GPU's share / K1 time"}
+        tensor = {"bound": "tensor", "achieved": algo_flops * 1e-9 / max(k1, 1e-9), "peak": peak64, "unit": "TFLOP/s",
+                  "frac": algo_flops * 1e-9 / max(k1, 1e-9) / peak64, "peak_source": peak64_src,
+                  "algorithmic_gflop_per_step": algo_flops * 1e-9,
+                  "issued_dmma_gflop_per_step": tensor_gflop, "issued_tflops": tensor_gflop / max(k1, 1e-9),
+                  "issued_frac": tensor_gflop / max(k1, 1e-9) / peak64,
+                  "note": "achieved = SURVEY 8(d)'s ALGORITHMIC Gram-space FLOPs (flops_fit over the R*O*(I+1) fits the reference runs) / K1 "
+                          "time; issued = DMMA.8x8x4 x 512 FLOP the kernel-space kernel really executes (2 n^2 per component and fit, "
+                          "independent of the subset size), from the launch geometry"}
+        if kspace:
+            main, other, other_key = tensor, hbm, "hbm_model"
+            kernel = ("K1 = simplsKspaceKernel (kernel-space SIMPLS on the FP64 tensor cores: one K = Z Z' per chromosome in shared memory, "
+                      "subsets of more than 40 columns) + gramPack / simplsFitFast / predictBlocks (per-fit Gram-space path; the rest), "
+                      "all launches of a step")
+            other = dict(other, note=other["note"] + "; the kernel-space kernel does not move those bytes (see traffic): kept for comparison "
+                                                        "with round 1, not as the binding roofline")
+        else:
+            main, other, other_key = hbm, tensor, "fp64"
+            kernel = ("K1 = gramPackKernel (per-generation packed Grams, HBM-bound) + simplsFitFast (Gram-space SIMPLS, one CTA per "
+                      "(chromosome, training set)) + predictBlocksKernel (held-out prediction on the FP64 tensor cores), all launches of a step")
+        roof = dict(main, kernel=kernel, k1_ms_per_step=k1, k2_ms_per_step=float(np.mean(k2_ms)), traffic=traffic,
+                    traffic_source=traffic_src)
+        roof[other_key] = other
         line = {
             "metric": "chromosome fitness evals/sec (repeated-CV PLS)",
-            "value": w["pop"] * world * args.steps / (ms * 1e-3), "unit": "evals/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "value": global_pop * args.steps / (ms * 1e-3), "unit": "evals/s",
+            "n_gpus": units, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, l2="explicit flush: a 256 MB buffer (2 x L2) is overwritten before every step, inside the "
-                                      "timed region (the path's own inputs, the 1.2 MB of centred data, would stay in L2)",
+                                      "timed region (the path's small shared inputs, %.1f MB of centred data, would otherwise stay in L2)"
+                                      % (8e-6 * ((w["n"] + 3) // 4 * 4) * (w["p"] + 2)),
                            fits_per_evaluation=info["fits_per_evaluation"], distinct_fits=info["distinct_fits"],
                            setup_ms=info["setup_ms"], gram_dmma_ms=info["gram_dmma_ms"],
-                           gram_tflops=info["gram_flops"] / max(info["gram_dmma_ms"], 1e-9) / 1e9),
-            "e2e": {"value": w["pop"] * world * args.steps / (e2e_ms * 1e-3), "unit": "evals/s",
+                           gram_tflops=info["gram_flops"] / max(info["gram_dmma_ms"], 1e-9) / 1e9,
+                           timing=("host clock around synchronous multi-device engine calls" if args.single_process
+                                   else "CUDA events on the launching stream, max over ranks"),
+                           gather_check=gather_check),
+            "e2e": {"value": global_pop * args.steps / (e2e_ms * 1e-3), "unit": "evals/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "K1 = simplsKspaceKernel (kernel-space SIMPLS on the FP64 tensor cores; subsets of more than 40 "
-                                                   "columns) + simplsFitFast (per-fit Gram-space kernel; the rest), all launches of a step",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "algorithmic_bytes_per_step": algo_bytes, "k1_ms_per_step": k1,
-                         "k2_ms_per_step": float(np.mean(k2_ms)),
-                         "traffic": MEASURED_TRAFFIC.get((args.workload, w["pop"])),
-                         "traffic_source": "profiles/r01_summary.txt (ncu --set full, sum over the K1 launches of one step)",
-                         "note": "achieved = SURVEY 8(d)'s algorithmic bytes (the logical inputs of every fit in the Gram formulation) / K1 "
-                                 "time; the kernel-space kernel does not move those bytes: it builds one K = Z Z' per chromosome in shared "
-                                 "memory (DRAM traffic: see traffic) and is bound by the FP64 tensor pipe, see fp64_tensor",
-                         "fp64_tensor": {"bound": "tensor", "achieved": tensor_gflop / max(k1, 1e-9), "peak": DMMA_PEAK_TFLOPS,
-                                         "unit": "TFLOP/s", "frac": tensor_gflop / max(k1, 1e-9) / DMMA_PEAK_TFLOPS,
-                                         "gflop_per_step": tensor_gflop,
-                                         "peak_source": "measured on B200 with profiles/micro/dmma_probe.cu: one DMMA.8x8x4 per 16 cycles "
-                                                        "per SM sub-partition at 1965 MHz (MEASURED_PEAKS.json has no FP64 figure)",
-                                         "note": "DMMA.8x8x4 issued by the kernel-space kernel x 512 FLOP over the time of ALL K1 launches"}},
+            "roofline": roof,
         }
-        if not args.no_cpu and world == 1:
+        if not args.no_cpu and units == 1:
             cb, _, _ = cpu_leg(w, X, y, subsets, args.cpu_seconds)
             line["cpu_baseline"] = cb
         else:

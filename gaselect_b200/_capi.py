@@ -17,6 +17,7 @@ EVAL_PLS_CV, EVAL_LM, EVAL_PLS_FIT = 1, 2, 3
 STAT = {"BIC": 0, "AIC": 1, "adjusted.r.squared": 2, "r.squared": 3}
 STATUS_OK, STATUS_EMPTY, STATUS_UNDERFLOW, STATUS_SINGULAR = range(4)
 SEED_WORDS = 624
+MAX_DEVICES = 16
 
 
 class Config(C.Structure):
@@ -24,7 +25,7 @@ class Config(C.Structure):
         ("struct_size", C.c_int32), ("device", C.c_int32), ("evaluator", C.c_int32), ("statistic", C.c_int32),
         ("num_replications", C.c_int32), ("inner_segments", C.c_int32), ("outer_segments", C.c_int32),
         ("max_ncomp", C.c_int32), ("test_set_size", C.c_double), ("sdfact", C.c_double),
-        ("complexity_penalty", C.c_double),
+        ("complexity_penalty", C.c_double), ("num_devices", C.c_int32), ("devices", C.c_int32 * 16), ("reserved", C.c_int32),
     ]
 
 
@@ -62,6 +63,7 @@ _H = C.c_void_p
 # name -> (restype, argtypes); every symbol include/gaselect_b200.h declares
 SIGNATURES = {
     "gsb_abi_version": (C.c_int, []),
+    "gsb_device_count": (C.c_int, [C.POINTER(C.c_int32)]),
     "gsb_create": (C.c_int, [C.POINTER(_H), C.POINTER(Config)]),
     "gsb_destroy": (None, [_H]),
     "gsb_last_error": (C.c_int, [_H, C.c_char_p, C.c_size_t]),
@@ -81,6 +83,7 @@ SIGNATURES = {
     "gsb_population_download": (C.c_int, [_H, _f64p, _i32p]),
     "gsb_population_device_results": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "gsb_last_timing": (C.c_int, [_H, C.POINTER(Timing)]),
+    "gsb_deal": (C.c_int, [_u32p, C.c_int32, C.c_int32, C.c_int32, _i32p]),
     "gsb_debug_trace": (C.c_int, [_H, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), C.c_int32]),
     "gsb_simpls": (C.c_int, [_H, _u32p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, _f64p, _f64p]),
     "gsb_rng_stream": (C.c_int, [_u32p, C.c_int32, _u32p]),

@@ -11,9 +11,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -117,11 +121,93 @@ struct EnvFlags {
 	int forcedNf = 0, forcedCs = 0, forcedVg = 0;
 };
 
+// One persistent host thread per device of a multi-device engine: the per-device engines are driven concurrently
+// (what MultiThreadedPopulation's worker threads are to the reference's cloned evaluators,
+// src/MultiThreadedPopulation.cpp:255-323), without creating threads per call.
+class DevicePool {
+public:
+	explicit DevicePool(int n) : jobs_(static_cast<size_t>(n)), rc_(static_cast<size_t>(n), 0), pending_(static_cast<size_t>(n), 0) {
+		for (int i = 0; i < n; ++i) threads_.emplace_back([this, i] { loop(i); });
+	}
+	~DevicePool() {
+		{
+			std::lock_guard<std::mutex> lk(m_);
+			stop_ = true;
+		}
+		cv_.notify_all();
+		for (size_t i = 0; i < threads_.size(); ++i) threads_[i].join();
+	}
+	// runs job(i) on thread i for every i, waits for all; returns the first nonzero result (and its index)
+	int run(const std::function<int(int)>& job, int* which) {
+		{
+			std::lock_guard<std::mutex> lk(m_);
+			for (size_t i = 0; i < jobs_.size(); ++i) { jobs_[i] = job; pending_[i] = 1; }
+			left_ = static_cast<int>(jobs_.size());
+		}
+		cv_.notify_all();
+		std::unique_lock<std::mutex> lk(m_);
+		done_.wait(lk, [this] { return left_ == 0; });
+		for (size_t i = 0; i < rc_.size(); ++i) {
+			if (rc_[i] != 0) { if (which) *which = static_cast<int>(i); return rc_[i]; }
+		}
+		return 0;
+	}
+private:
+	void loop(int i) {
+		for (;;) {
+			std::function<int(int)> job;
+			{
+				std::unique_lock<std::mutex> lk(m_);
+				cv_.wait(lk, [this, i] { return stop_ || pending_[static_cast<size_t>(i)]; });
+				if (stop_) return;
+				job = jobs_[static_cast<size_t>(i)];
+				pending_[static_cast<size_t>(i)] = 0;
+			}
+			const int rc = job(i);
+			{
+				std::lock_guard<std::mutex> lk(m_);
+				rc_[static_cast<size_t>(i)] = rc;
+				--left_;
+			}
+			done_.notify_all();
+		}
+	}
+	std::mutex m_;
+	std::condition_variable cv_, done_;
+	std::vector<std::function<int(int)>> jobs_;
+	std::vector<int> rc_;
+	std::vector<char> pending_;
+	std::vector<std::thread> threads_;
+	int left_ = 0;
+	bool stop_ = false;
+};
+
+// What a multi-device engine keeps besides its per-device engines: the deal of the resident population and the
+// gather buffers (device 0 of the list, then pinned host memory)
+struct MultiState {
+	DevicePool* pool = nullptr;
+	std::vector<std::vector<int>> shares;        // per device: caller indices of its chromosomes, ascending
+	std::vector<std::vector<uint32_t>> idx, off; // per device: its CSR lists
+	std::vector<int> first;                      // per device: offset of its results in the gathered vectors
+	int npop = 0;
+	bool populationReady = false, resultsReady = false;
+	double* dFitness = nullptr;                  // on devices[0]: the shares' results back to back
+	int* dStatus = nullptr;
+	double* hFitness = nullptr;                  // pinned
+	int* hStatus = nullptr;
+	size_t capacity = 0;
+	cudaStream_t stream = nullptr;               // on devices[0]
+	~MultiState() { delete pool; }
+};
+
 } // namespace
 
 struct gsb_engine {
 	gsb_config cfg;
 	std::string error;
+	// multi-device engine (cfg.num_devices > 1): one single-device engine per GPU; this object only deals and gathers
+	std::vector<gsb_engine*> replicas;
+	MultiState* multi = nullptr;
 
 	// host copies (PLS::PLS copies X and Y, src/PLS.h:25,95-96)
 	int n = 0, p = 0;
@@ -963,11 +1049,220 @@ std::string deriveShape(gsb_engine* e, std::vector<gsb::RowSet>& seg, const uint
 	return gsb::buildFitSegmentation(e->n, c.max_ncomp, c.inner_segments, c.sdfact, seed624, seg, e->shape);
 }
 
+
+// ---- multi-device engine -----------------------------------------------------------------------------------
+// The per-device engines ("replicas") are complete single-device engines: each holds its own copy of the data, builds
+// the same segmentation from the same seed and its own device tables (nothing is exchanged between GPUs at setup).
+// Per batch: deal -> concurrent upload / kernels on every replica -> peer copies of the result vectors to the first
+// device -> one copy to pinned host memory -> un-permute into the caller's order.
+
+int failFrom(gsb_engine* e, int rc, const gsb_engine* child, int dev) {
+	char buf[768];
+	std::snprintf(buf, sizeof(buf), "device %d: %s", dev, child ? child->error.c_str() : "");
+	return fail(e, rc, buf);
+}
+
+// runs fn(replica) on every replica concurrently (the pool's threads), propagates the first failure
+int onReplicas(gsb_engine* e, const std::function<int(gsb_engine*)>& fn) {
+	int which = 0;
+	const int rc = e->multi->pool->run([&](int i) { return fn(e->replicas[static_cast<size_t>(i)]); }, &which);
+	if (rc != GSB_OK) return failFrom(e, rc, e->replicas[static_cast<size_t>(which)], e->cfg.devices[which]);
+	return GSB_OK;
+}
+
+// cost model of the deal (multigpu.py holds the same constants for the one-process-per-GPU host): milliseconds per 296
+// chromosomes measured at BASELINE config 3 for the kernel-space kernel, k^2 for the per-fit Gram-space kernel
+double dealCost(double k, bool kspace) {
+	if (kspace) return k > 40.0 ? 1.24 + 0.00023 * k : 0.38 + 0.0131 * k;
+	return k * k + 1.0;
+}
+
+void dealPopulation(const uint32_t* offsets, int npop, int ndev, bool kspace, std::vector<int>& deviceOf) {
+	deviceOf.assign(static_cast<size_t>(npop), 0);
+	if (ndev <= 1) return;
+	std::vector<double> cost(static_cast<size_t>(npop));
+	std::vector<int> order(static_cast<size_t>(npop));
+	for (int c = 0; c < npop; ++c) {
+		cost[static_cast<size_t>(c)] = dealCost(static_cast<double>(offsets[c + 1] - offsets[c]), kspace);
+		order[static_cast<size_t>(c)] = c;
+	}
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[static_cast<size_t>(a)] > cost[static_cast<size_t>(b)]; });
+	const int cap = (npop + ndev - 1) / ndev;
+	std::vector<double> load(static_cast<size_t>(ndev), 0.0);
+	std::vector<int> count(static_cast<size_t>(ndev), 0);
+	for (int x = 0; x < npop; ++x) {
+		const int c = order[static_cast<size_t>(x)];
+		int best = -1;
+		for (int d = 0; d < ndev; ++d) {
+			if (count[static_cast<size_t>(d)] >= cap) continue;
+			if (best < 0 || load[static_cast<size_t>(d)] < load[static_cast<size_t>(best)]) best = d;
+		}
+		deviceOf[static_cast<size_t>(c)] = best;
+		load[static_cast<size_t>(best)] += cost[static_cast<size_t>(c)];
+		count[static_cast<size_t>(best)] += 1;
+	}
+}
+
+bool multiUsesKspace(const gsb_engine* e) {
+	const gsb_engine* r0 = e->replicas[0];
+	return r0->kspaceFits > 0 && !r0->env.noKspace;
+}
+
+void multiReleaseGather(gsb_engine* e) {
+	MultiState* ms = e->multi;
+	if (!ms) return;
+	if (ms->dFitness || ms->stream) cudaSetDevice(e->cfg.devices[0]);
+	if (ms->dFitness) cudaFree(ms->dFitness);
+	if (ms->dStatus) cudaFree(ms->dStatus);
+	if (ms->hFitness) cudaFreeHost(ms->hFitness);
+	if (ms->hStatus) cudaFreeHost(ms->hStatus);
+	if (ms->stream) cudaStreamDestroy(ms->stream);
+	ms->dFitness = nullptr; ms->dStatus = nullptr; ms->hFitness = nullptr; ms->hStatus = nullptr; ms->stream = nullptr;
+	ms->capacity = 0;
+}
+
+int multiUpload(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop) {
+	MultiState* ms = e->multi;
+	const int ndev = static_cast<int>(e->replicas.size());
+	ms->populationReady = ms->resultsReady = false;
+	for (int c = 0; c < npop; ++c) {
+		if (offsets[c + 1] < offsets[c]) return fail(e, GSB_ERR_INVALID_ARGUMENT, "population offsets must be non-decreasing");
+	}
+	// the replicas must be prepared before the deal: the cost model depends on which kernels the plan admits
+	int rc = onReplicas(e, [](gsb_engine* r) { return gsb_prepare(r); });
+	if (rc != GSB_OK) return rc;
+	std::vector<int> deviceOf;
+	dealPopulation(offsets, npop, ndev, multiUsesKspace(e), deviceOf);
+	ms->shares.assign(static_cast<size_t>(ndev), std::vector<int>());
+	ms->idx.assign(static_cast<size_t>(ndev), std::vector<uint32_t>());
+	ms->off.assign(static_cast<size_t>(ndev), std::vector<uint32_t>(1, 0u));
+	for (int c = 0; c < npop; ++c) {
+		const size_t d = static_cast<size_t>(deviceOf[static_cast<size_t>(c)]);
+		ms->shares[d].push_back(c);
+		ms->idx[d].insert(ms->idx[d].end(), idx + offsets[c], idx + offsets[c + 1]);
+		ms->off[d].push_back(static_cast<uint32_t>(ms->idx[d].size()));
+	}
+	ms->first.assign(static_cast<size_t>(ndev) + 1, 0);
+	for (int d = 0; d < ndev; ++d) {
+		ms->first[static_cast<size_t>(d) + 1] = ms->first[static_cast<size_t>(d)] + static_cast<int>(ms->shares[static_cast<size_t>(d)].size());
+		if (ms->idx[static_cast<size_t>(d)].empty()) ms->idx[static_cast<size_t>(d)].push_back(0u);
+	}
+	ms->npop = npop;
+	rc = e->multi->pool->run([&](int i) {
+		const size_t d = static_cast<size_t>(i);
+		return gsb_population_upload(e->replicas[d], ms->idx[d].data(), ms->off[d].data(), static_cast<int32_t>(ms->shares[d].size()));
+	}, nullptr);
+	if (rc != GSB_OK) {
+		for (int d = 0; d < ndev; ++d) if (!e->replicas[static_cast<size_t>(d)]->error.empty()) return failFrom(e, rc, e->replicas[static_cast<size_t>(d)], e->cfg.devices[d]);
+		return fail(e, rc, "population upload failed");
+	}
+	ms->populationReady = true;
+	return GSB_OK;
+}
+
+int multiEvaluate(gsb_engine* e, bool synchronous) {
+	MultiState* ms = e->multi;
+	if (!ms->populationReady) return fail(e, GSB_ERR_STATE, "no resident population: call gsb_population_upload first");
+	int rc;
+	if (synchronous) {
+		rc = onReplicas(e, [](gsb_engine* r) { return r->npop > 0 ? gsb_population_evaluate(r) : GSB_OK; });
+	} else {
+		// enqueue only: the launches are asynchronous, one device after the other from this thread
+		rc = GSB_OK;
+		for (size_t d = 0; d < e->replicas.size() && rc == GSB_OK; ++d) {
+			gsb_engine* r = e->replicas[d];
+			if (r->npop > 0) rc = gsb_population_enqueue(r);
+			if (rc != GSB_OK) return failFrom(e, rc, r, e->cfg.devices[d]);
+		}
+	}
+	if (rc != GSB_OK) return rc;
+	gsb_timing& t = e->timing;
+	std::memset(&t, 0, sizeof(t));
+	for (size_t d = 0; d < e->replicas.size(); ++d) {
+		const gsb_timing& c = e->replicas[d]->timing;
+		if (e->replicas[d]->npop == 0) continue;
+		t.h2d_ms = std::max(t.h2d_ms, c.h2d_ms);
+		t.fit_kernel_ms = std::max(t.fit_kernel_ms, c.fit_kernel_ms);
+		t.reduce_kernel_ms = std::max(t.reduce_kernel_ms, c.reduce_kernel_ms);
+		t.total_ms = std::max(t.total_ms, c.total_ms);
+		t.fit_ctas += c.fit_ctas;
+		t.kernel_launches += c.kernel_launches;
+		t.fit_tensor_gflop += c.fit_tensor_gflop;
+	}
+	ms->resultsReady = true;
+	return GSB_OK;
+}
+
+int multiDownload(gsb_engine* e, double* fitness, int32_t* status) {
+	MultiState* ms = e->multi;
+	if (!ms->resultsReady) return fail(e, GSB_ERR_STATE, "no results: call gsb_population_evaluate first");
+	const int ndev = static_cast<int>(e->replicas.size());
+	const size_t np = static_cast<size_t>(ms->npop);
+	if (np == 0) return GSB_OK;
+	try {
+		const int dev0 = e->cfg.devices[0];
+		// every replica's kernels must have finished before its result vectors are read from another device
+		for (int d = 0; d < ndev; ++d) {
+			gsb_engine* r = e->replicas[static_cast<size_t>(d)];
+			if (r->npop == 0) continue;
+			GSB_CUDA(cudaSetDevice(e->cfg.devices[d]));
+			GSB_CUDA(cudaStreamSynchronize(r->stream));
+		}
+		GSB_CUDA(cudaSetDevice(dev0));
+		if (!ms->stream) GSB_CUDA(cudaStreamCreateWithFlags(&ms->stream, cudaStreamNonBlocking));
+		if (np > ms->capacity) {
+			const size_t want = np + np / 2 + 64;
+			if (ms->dFitness) cudaFree(ms->dFitness);
+			if (ms->dStatus) cudaFree(ms->dStatus);
+			if (ms->hFitness) cudaFreeHost(ms->hFitness);
+			if (ms->hStatus) cudaFreeHost(ms->hStatus);
+			ms->dFitness = nullptr; ms->dStatus = nullptr; ms->hFitness = nullptr; ms->hStatus = nullptr; ms->capacity = 0;
+			GSB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ms->dFitness), want * sizeof(double)));
+			GSB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ms->dStatus), want * sizeof(int)));
+			GSB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ms->hFitness), want * sizeof(double), cudaHostAllocDefault));
+			GSB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ms->hStatus), want * sizeof(int), cudaHostAllocDefault));
+			ms->capacity = want;
+		}
+		// gather: peer copies (NVLink when peer access is enabled, else staged by the driver) into the first device
+		for (int d = 0; d < ndev; ++d) {
+			gsb_engine* r = e->replicas[static_cast<size_t>(d)];
+			const size_t cnt = ms->shares[static_cast<size_t>(d)].size();
+			if (cnt == 0) continue;
+			const size_t at = static_cast<size_t>(ms->first[static_cast<size_t>(d)]);
+			GSB_CUDA(cudaMemcpyPeerAsync(ms->dFitness + at, dev0, r->dFitness.ptr, e->cfg.devices[d], cnt * sizeof(double), ms->stream));
+			GSB_CUDA(cudaMemcpyPeerAsync(ms->dStatus + at, dev0, r->dStatus.ptr, e->cfg.devices[d], cnt * sizeof(int), ms->stream));
+		}
+		GSB_CUDA(cudaMemcpyAsync(ms->hFitness, ms->dFitness, np * sizeof(double), cudaMemcpyDeviceToHost, ms->stream));
+		GSB_CUDA(cudaMemcpyAsync(ms->hStatus, ms->dStatus, np * sizeof(int), cudaMemcpyDeviceToHost, ms->stream));
+		GSB_CUDA(cudaStreamSynchronize(ms->stream));
+		for (int d = 0; d < ndev; ++d) {
+			const std::vector<int>& sh = ms->shares[static_cast<size_t>(d)];
+			const size_t at = static_cast<size_t>(ms->first[static_cast<size_t>(d)]);
+			for (size_t i = 0; i < sh.size(); ++i) {
+				fitness[sh[i]] = ms->hFitness[at + i];
+				status[sh[i]] = ms->hStatus[at + i];
+			}
+		}
+	} catch (const CudaFailure& f) {
+		return failCuda(e, f);
+	}
+	return GSB_OK;
+}
+
 } // namespace
 
 extern "C" {
 
 int gsb_abi_version(void) { return GSB_ABI_VERSION; }
+
+int gsb_device_count(int32_t* count) {
+	if (!count) return GSB_ERR_INVALID_ARGUMENT;
+	int n = 0;
+	const cudaError_t err = cudaGetDeviceCount(&n);
+	if (err != cudaSuccess) cudaGetLastError();
+	*count = (err == cudaSuccess) ? n : 0;
+	return (err == cudaSuccess && n > 0) ? GSB_OK : GSB_ERR_CUDA;
+}
 
 int gsb_create(gsb_engine** out, const gsb_config* cfg) {
 	if (!out || !cfg) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "null argument");
@@ -976,6 +1271,11 @@ int gsb_create(gsb_engine** out, const gsb_config* cfg) {
 		return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "gsb_config.struct_size does not match this library");
 	}
 	if (cfg->device < 0) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "negative device ordinal");
+	if (cfg->num_devices < 0 || cfg->num_devices > GSB_MAX_DEVICES) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "num_devices out of range");
+	for (int i = 0; i < cfg->num_devices; ++i) {
+		if (cfg->devices[i] < 0) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "negative device ordinal in the device list");
+		for (int j = 0; j < i; ++j) if (cfg->devices[j] == cfg->devices[i]) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "the device list must hold distinct ordinals");
+	}
 	switch (cfg->evaluator) {
 	case GSB_EVAL_PLS_CV:
 		if (cfg->num_replications < 1) return fail(nullptr, GSB_ERR_INVALID_ARGUMENT, "numReplications must be at least 1");
@@ -999,12 +1299,39 @@ int gsb_create(gsb_engine** out, const gsb_config* cfg) {
 	gsb_engine* e = new (std::nothrow) gsb_engine();
 	if (!e) return fail(nullptr, GSB_ERR_MEMORY, "host allocation failed");
 	e->cfg = *cfg;
+	if (cfg->num_devices == 1) e->cfg.device = cfg->devices[0];
+	if (cfg->num_devices > 1) {
+		// one complete single-device engine per GPU; this object deals the batches and gathers the results
+		try {
+			for (int i = 0; i < cfg->num_devices; ++i) {
+				gsb_config one = *cfg;
+				one.num_devices = 0;
+				one.device = cfg->devices[i];
+				gsb_engine* r = nullptr;
+				const int rc = gsb_create(&r, &one);
+				if (rc != GSB_OK) { gsb_destroy(e); return rc; }
+				e->replicas.push_back(r);
+			}
+			e->multi = new MultiState();
+			e->multi->pool = new DevicePool(cfg->num_devices);
+		} catch (const std::exception&) {
+			gsb_destroy(e);
+			return fail(nullptr, GSB_ERR_MEMORY, "host allocation failed");
+		}
+	}
 	*out = e;
 	return GSB_OK;
 }
 
 void gsb_destroy(gsb_engine* e) {
 	if (!e) return;
+	if (e->multi) {
+		multiReleaseGather(e);
+		delete e->multi; // joins the device threads
+		e->multi = nullptr;
+	}
+	for (size_t i = 0; i < e->replicas.size(); ++i) gsb_destroy(e->replicas[i]);
+	e->replicas.clear();
 	if (e->deviceReady) cudaSetDevice(e->cfg.device);
 	releaseDevice(e);
 	delete e;
@@ -1021,6 +1348,17 @@ int gsb_set_data(gsb_engine* e, const double* X_colmajor, const double* y, int32
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
 	if (!X_colmajor || !y || n < 4 || p < 1) return fail(e, GSB_ERR_INVALID_ARGUMENT, "X must be n x p with n >= 4, p >= 1");
 	if (n > 65535 || p > 65535) return fail(e, GSB_ERR_INVALID_ARGUMENT, "n and p are limited to 65535 (src/Control.h:67-68, src/OnlineStddev.h:62)");
+	if (!e->replicas.empty()) { // every replica keeps its own copy (it uploads from it); this object only records the shape
+		for (size_t i = 0; i < e->replicas.size(); ++i) {
+			const int rc = gsb_set_data(e->replicas[i], X_colmajor, y, n, p);
+			if (rc != GSB_OK) return failFrom(e, rc, e->replicas[i], e->cfg.devices[i]);
+		}
+		e->n = n;
+		e->p = p;
+		e->haveData = true;
+		e->multi->populationReady = e->multi->resultsReady = false;
+		return GSB_OK;
+	}
 	try {
 		e->X.assign(X_colmajor, X_colmajor + static_cast<size_t>(n) * p);
 		e->y.assign(y, y + n);
@@ -1065,6 +1403,11 @@ int gsb_init_segmentation(gsb_engine* e, const uint32_t* seed624) {
 	if (e->cfg.evaluator == GSB_EVAL_LM) return GSB_OK;
 	if (!seed624) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null seed");
 	if (!e->haveData) return fail(e, GSB_ERR_STATE, "gsb_set_data has not been called");
+	for (size_t i = 0; i < e->replicas.size(); ++i) { // the same host-built segmentation on every replica
+		const int rc = gsb_init_segmentation(e->replicas[i], seed624);
+		if (rc != GSB_OK) return failFrom(e, rc, e->replicas[i], e->cfg.devices[i]);
+	}
+	if (!e->replicas.empty()) { e->multi->populationReady = e->multi->resultsReady = false; return GSB_OK; }
 	const std::string msg = deriveShape(e, e->segmentation, seed624);
 	if (!msg.empty()) return fail(e, GSB_ERR_INVALID_ARGUMENT, msg);
 	e->haveSegmentation = true;
@@ -1077,6 +1420,11 @@ int gsb_set_segmentation(gsb_engine* e, const uint32_t* rows, const uint32_t* of
 	if (e->cfg.evaluator == GSB_EVAL_LM) return GSB_OK;
 	if (!rows || !offsets || nvec < 2) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null or empty segmentation");
 	if (!e->haveData) return fail(e, GSB_ERR_STATE, "gsb_set_data has not been called");
+	for (size_t i = 0; i < e->replicas.size(); ++i) {
+		const int rc = gsb_set_segmentation(e->replicas[i], rows, offsets, nvec);
+		if (rc != GSB_OK) return failFrom(e, rc, e->replicas[i], e->cfg.devices[i]);
+	}
+	if (!e->replicas.empty()) { e->multi->populationReady = e->multi->resultsReady = false; return GSB_OK; }
 	// segment lengths and the maxNComp clamp depend only on n and the configuration
 	std::vector<uint32_t> zeros(GSB_SEED_WORDS, 0u);
 	zeros[0] = 1u;
@@ -1097,6 +1445,7 @@ int gsb_set_segmentation(gsb_engine* e, const uint32_t* rows, const uint32_t* of
 
 int gsb_get_segmentation(const gsb_engine* e, uint32_t* rows, uint32_t* offsets, int32_t* nvec, int64_t* total) {
 	if (!e || !nvec || !total) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->replicas.empty()) return gsb_get_segmentation(e->replicas[0], rows, offsets, nvec, total);
 	int64_t tot = 0;
 	for (size_t v = 0; v < e->segmentation.size(); ++v) tot += static_cast<int64_t>(e->segmentation[v].size());
 	*nvec = static_cast<int32_t>(e->segmentation.size());
@@ -1114,12 +1463,14 @@ int gsb_get_segmentation(const gsb_engine* e, uint32_t* rows, uint32_t* offsets,
 
 int gsb_prepare(gsb_engine* e) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->replicas.empty()) return onReplicas(e, [](gsb_engine* r) { return gsb_prepare(r); }); // K0 on every GPU at once
 	if (e->prepared) return GSB_OK;
 	return prepareChecked(e);
 }
 
 int gsb_set_stream(gsb_engine* e, void* cuda_stream) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->replicas.empty()) return fail(e, GSB_ERR_STATE, "a multi-device engine runs on its replicas' own streams");
 	try {
 		ensureDevice(e);
 		GSB_CUDA(cudaStreamSynchronize(e->stream));
@@ -1133,6 +1484,7 @@ int gsb_set_stream(gsb_engine* e, void* cuda_stream) {
 
 int gsb_get_info(const gsb_engine* e, gsb_info* info) {
 	if (!e || !info) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->replicas.empty()) return gsb_get_info(e->replicas[0], info);
 	*info = e->info;
 	if (!e->prepared) { // host-side facts are available before the device setup
 		info->n = e->n;
@@ -1150,6 +1502,7 @@ int gsb_get_info(const gsb_engine* e, gsb_info* info) {
 int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
 	if (!offsets || npop < 0 || (!idx && npop > 0 && offsets[npop] > 0)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null population");
+	if (!e->replicas.empty()) return multiUpload(e, idx, offsets, npop);
 	if (!e->prepared) {
 		const int rc = prepareChecked(e);
 		if (rc != GSB_OK) return rc;
@@ -1507,6 +1860,7 @@ extern "C" {
 
 int gsb_population_enqueue(gsb_engine* e) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->replicas.empty()) return multiEvaluate(e, false);
 	if (!e->populationReady) return fail(e, GSB_ERR_STATE, "no resident population: call gsb_population_upload first");
 	try {
 		ensureDevice(e);
@@ -1524,6 +1878,7 @@ int gsb_population_enqueue(gsb_engine* e) {
 
 int gsb_population_evaluate(gsb_engine* e) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->replicas.empty()) return multiEvaluate(e, true);
 	if (!e->populationReady) return fail(e, GSB_ERR_STATE, "no resident population: call gsb_population_upload first");
 	try {
 		ensureDevice(e);
@@ -1551,6 +1906,7 @@ int gsb_population_evaluate(gsb_engine* e) {
 int gsb_population_download(gsb_engine* e, double* fitness, int32_t* status) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
 	if (!fitness || !status) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null output buffer");
+	if (!e->replicas.empty()) return multiDownload(e, fitness, status);
 	if (!e->resultsReady) return fail(e, GSB_ERR_STATE, "no results: call gsb_population_evaluate first");
 	try {
 		ensureDevice(e);
@@ -1576,6 +1932,7 @@ int gsb_population_download(gsb_engine* e, double* fitness, int32_t* status) {
 
 int gsb_population_device_results(gsb_engine* e, void** d_fitness, void** d_status, int32_t* npop) {
 	if (!e || !d_fitness || !d_status || !npop) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->replicas.empty()) return fail(e, GSB_ERR_STATE, "a multi-device engine gathers its results to the host (gsb_population_download)");
 	if (!e->populationReady) return fail(e, GSB_ERR_STATE, "no resident population");
 	*d_fitness = e->dFitness.ptr;
 	*d_status = e->dStatus.ptr;
@@ -1626,6 +1983,7 @@ int gsb_evaluate_bitsets(gsb_engine* e, const uint64_t* bitsets, int32_t words_p
 
 int gsb_debug_trace(gsb_engine* e, int64_t* out, int32_t n) {
 	if (!e || !out || n < 0) return GSB_ERR_INVALID_ARGUMENT;
+	if (!e->replicas.empty()) return gsb_debug_trace(e->replicas[0], out, n);
 	for (int i = 0; i < n; ++i) out[i] = 0;
 	if (!e->traceBuf.ptr) return GSB_OK;
 	try {
@@ -1635,6 +1993,15 @@ int gsb_debug_trace(gsb_engine* e, int64_t* out, int32_t n) {
 	} catch (const CudaFailure& f) {
 		return failCuda(e, f);
 	}
+	return GSB_OK;
+}
+
+int gsb_deal(const uint32_t* offsets, int32_t npop, int32_t ndev, int32_t kspace, int32_t* device_of) {
+	if (!offsets || !device_of || npop < 0 || ndev < 1 || ndev > GSB_MAX_DEVICES) return GSB_ERR_INVALID_ARGUMENT;
+	for (int c = 0; c < npop; ++c) if (offsets[c + 1] < offsets[c]) return GSB_ERR_INVALID_ARGUMENT;
+	std::vector<int> d;
+	dealPopulation(offsets, npop, ndev, kspace != 0, d);
+	for (int c = 0; c < npop; ++c) device_of[c] = d[static_cast<size_t>(c)];
 	return GSB_OK;
 }
 
@@ -1648,6 +2015,10 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
                double* coef, double* intercepts) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
 	if (!e->haveData) return fail(e, GSB_ERR_STATE, "gsb_set_data has not been called");
+	if (!e->replicas.empty()) {
+		const int rc = gsb_simpls(e->replicas[0], cols, k, rows, nrows, ncomp, coef, intercepts);
+		return rc == GSB_OK ? rc : failFrom(e, rc, e->replicas[0], e->cfg.devices[0]);
+	}
 	if (!cols || k < 1 || k > 1024 || ncomp < 1 || !coef || !intercepts) return fail(e, GSB_ERR_INVALID_ARGUMENT, "invalid SIMPLS request");
 	const int n = e->n, p = e->p;
 	std::vector<uint32_t> trainRows;

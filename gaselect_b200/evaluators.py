@@ -45,11 +45,20 @@ class Evaluator:
 
     _kind = 0
 
-    def __init__(self, X, y, seed, device=0, **cfg):
+    def __init__(self, X, y, seed, device=0, devices=None, **cfg):
+        """device: one CUDA ordinal; devices: a list of ordinals for a multi-device engine (every batch is dealt to
+        the GPUs inside the engine; same results as on one GPU)."""
         lib = _capi.lib()
         c = _capi.Config()
         c.struct_size = C.sizeof(_capi.Config)
         c.device = int(device)
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            if not 1 <= len(devices) <= _capi.MAX_DEVICES:
+                raise ValueError("devices must hold 1..%d ordinals" % _capi.MAX_DEVICES)
+            c.num_devices = len(devices)
+            for i, d in enumerate(devices):
+                c.devices[i] = d
         c.evaluator = self._kind
         c.statistic = cfg.get("statistic", 0)
         c.num_replications = cfg.get("num_replications", 1)
@@ -217,8 +226,8 @@ class PLSEvaluator(Evaluator):
     _kind = _capi.EVAL_PLS_CV
 
     def __init__(self, X, y, seed, numReplications=30, maxNComp=0, innerSegments=7, outerSegments=1,
-                 testSetSize=0.0, sdfact=1.0, complexityPenalty=0.0, device=0):
-        super().__init__(X, y, seed, device=device, num_replications=int(numReplications), max_ncomp=int(maxNComp),
+                 testSetSize=0.0, sdfact=1.0, complexityPenalty=0.0, device=0, devices=None):
+        super().__init__(X, y, seed, device=device, devices=devices, num_replications=int(numReplications), max_ncomp=int(maxNComp),
                          inner_segments=int(innerSegments), outer_segments=int(outerSegments),
                          test_set_size=float(testSetSize), sdfact=float(sdfact),
                          complexity_penalty=float(complexityPenalty))
@@ -230,8 +239,8 @@ class BICEvaluator(Evaluator):
 
     _kind = _capi.EVAL_PLS_FIT
 
-    def __init__(self, X, y, seed, numSegments=7, statistic="BIC", maxNComp=0, sdfact=1.0, device=0):
-        super().__init__(X, y, seed, device=device, inner_segments=int(numSegments), statistic=_capi.STAT[statistic],
+    def __init__(self, X, y, seed, numSegments=7, statistic="BIC", maxNComp=0, sdfact=1.0, device=0, devices=None):
+        super().__init__(X, y, seed, device=device, devices=devices, inner_segments=int(numSegments), statistic=_capi.STAT[statistic],
                          max_ncomp=int(maxNComp), sdfact=float(sdfact))
 
 
@@ -240,5 +249,5 @@ class LMEvaluator(Evaluator):
 
     _kind = _capi.EVAL_LM
 
-    def __init__(self, X, y, statistic="BIC", device=0):
-        super().__init__(X, y, None, device=device, statistic=_capi.STAT[statistic])
+    def __init__(self, X, y, statistic="BIC", device=0, devices=None):
+        super().__init__(X, y, None, device=device, devices=devices, statistic=_capi.STAT[statistic])

@@ -1,8 +1,40 @@
 // GpuEvaluator.cpp -- see GpuEvaluator.h.
 #include "GpuEvaluator.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
+
+namespace {
+std::vector<int> g_defaultDevices;
+bool g_defaultDevicesSet = false;
+
+// GASELECT_B200_DEVICES: "all", or ordinals separated by commas
+std::vector<int> devicesFromEnvironment() {
+	std::vector<int> out;
+	const char* v = std::getenv("GASELECT_B200_DEVICES");
+	if (!v || !*v) return out;
+	if (std::strcmp(v, "all") == 0) {
+		int32_t n = 0;
+		if (gsb_device_count(&n) == GSB_OK) for (int i = 0; i < n && i < GSB_MAX_DEVICES; ++i) out.push_back(i);
+		return out;
+	}
+	const char* p = v;
+	while (*p) {
+		char* end = nullptr;
+		const long d = std::strtol(p, &end, 10);
+		if (end == p) break;
+		out.push_back(static_cast<int>(d));
+		p = (*end == ',') ? end + 1 : end;
+	}
+	return out;
+}
+}
+
+void GpuEvaluator::setDefaultDevices(const std::vector<int>& devices) {
+	g_defaultDevices = devices;
+	g_defaultDevicesSet = true;
+}
 
 void GpuEvaluator::check(gsb_engine* e, int rc) {
 	if (rc == GSB_OK) return;
@@ -15,7 +47,12 @@ void GpuEvaluator::check(gsb_engine* e, int rc) {
 GpuEvaluator* GpuEvaluator::make(const gsb_config& cfg, const arma::mat& X, const arma::vec& y,
                                  const std::vector<uint32_t>* seed, VerbosityLevel verbosity) {
 	std::shared_ptr<Engine> eng(new Engine());
-	check(nullptr, gsb_create(&eng->handle, &cfg));
+	gsb_config full = cfg;
+	const std::vector<int> devices = g_defaultDevicesSet ? g_defaultDevices : devicesFromEnvironment();
+	if (devices.size() > GSB_MAX_DEVICES) throw std::invalid_argument("too many devices");
+	full.num_devices = static_cast<int32_t>(devices.size());
+	for (size_t i = 0; i < devices.size(); ++i) full.devices[i] = devices[i];
+	check(nullptr, gsb_create(&eng->handle, &full));
 	// arma::mat is column-major, exactly what gsb_set_data takes; the engine keeps its own copy
 	check(eng->handle, gsb_set_data(eng->handle, X.memptr(), y.memptr(), static_cast<int32_t>(X.n_rows), static_cast<int32_t>(X.n_cols)));
 	if (seed) {

@@ -36,6 +36,12 @@ public:
 	// LMEvaluator(X, y, statistic, verbosity)                                   src/LMEvaluator.cpp:17-25
 	static GpuEvaluator* makeLM(const arma::mat& X, const arma::vec& y, int statistic, VerbosityLevel verbosity, int device = 0);
 
+	// Devices of every evaluator made afterwards: more than one ordinal makes the engine deal each batch to all of them
+	// (one process, one CUDA context per GPU; include/gaselect_b200.h, gsb_config.devices) -- the role numThreads plays in
+	// the reference (src/GenAlg.cpp:173-181).  Empty list: the `device` argument of make*.  Without a call, the
+	// environment variable GASELECT_B200_DEVICES ("all" or a comma-separated list of ordinals) is consulted.
+	static void setDefaultDevices(const std::vector<int>& devices);
+
 	~GpuEvaluator() {}
 
 	double evaluate(arma::uvec& columnSubset);   // src/Evaluator.h:30

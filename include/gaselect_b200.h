@@ -7,7 +7,12 @@
  * repository root).  Plain pointers and sizes only; no C++ or torch types; no exception crosses
  * this boundary.  All functions return GSB_OK (0) or a nonzero gsb_error; gsb_last_error()
  * gives the message.  An engine is NOT re-entrant (like a reference Evaluator instance,
- * src/PLS.h:100-103): one engine per host thread / per GPU.
+ * src/PLS.h:100-103): one engine per host thread.  An engine drives one GPU, or -- with
+ * gsb_config.num_devices > 1 -- several GPUs of the node from ONE process: every batch is dealt to
+ * per-device replicas (longest-processing-time-first on the kernels' cost model, equal counts), the
+ * replicas run concurrently on their own CUDA contexts, and the fitness / status vectors are
+ * gathered with peer copies.  That is the role the numThreads slice deal plays in the reference
+ * (src/MultiThreadedPopulation.cpp:260-262,301-323, selected at src/GenAlg.cpp:173-181).
  *
  * There is no CPU fallback: every evaluate call runs hand-written sm_100a CUDA kernels and
  * fails with GSB_ERR_CUDA when no usable device is present.
@@ -25,8 +30,9 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define GSB_ABI_VERSION 2
+#define GSB_ABI_VERSION 3
 #define GSB_SEED_WORDS 624 /* RNG::SEED_SIZE, src/RNG.h:64 */
+#define GSB_MAX_DEVICES 16
 
 typedef struct gsb_engine gsb_engine;
 
@@ -81,6 +87,11 @@ typedef struct gsb_config {
 	double test_set_size;      /* PLS_CV srCV only */
 	double sdfact;
 	double complexity_penalty; /* PLS_CV */
+	/* devices of a multi-device engine (ABI 3): num_devices <= 1 uses `device` alone; otherwise the batch of every
+	 * evaluate call is dealt to devices[0 .. num_devices) (distinct CUDA ordinals) and `device` is ignored */
+	int32_t num_devices;
+	int32_t devices[GSB_MAX_DEVICES];
+	int32_t reserved;
 } gsb_config;
 
 /* read-only facts about a prepared engine (sizes of the fit plan and the device tables) */
@@ -132,6 +143,10 @@ void gsb_destroy(gsb_engine* e);
 int gsb_last_error(const gsb_engine* e, char* buf, size_t buflen);
 
 int gsb_abi_version(void);
+
+/* Number of usable CUDA devices (0 and GSB_ERR_CUDA when there is none): what a host needs to build the device list
+ * of a multi-device engine without linking the CUDA runtime itself. */
+int gsb_device_count(int32_t* count);
 
 /* ---- data and CV segmentation (host side, bit-exact) -------------------------------------- */
 
@@ -196,10 +211,18 @@ int gsb_population_enqueue(gsb_engine* e);
 int gsb_population_download(gsb_engine* e, double* fitness, int32_t* status);
 
 /* Device addresses of the resident results (fitness: npop doubles, status: npop int32) so that a
- * multi-GPU host can hand them to NCCL without a host round trip.  Valid until the next upload. */
+ * multi-GPU host can hand them to NCCL without a host round trip.  Valid until the next upload.
+ * Single-device engines only (a multi-device engine gathers to the host itself). */
 int gsb_population_device_results(gsb_engine* e, void** d_fitness, void** d_status, int32_t* npop);
 
 int gsb_last_timing(const gsb_engine* e, gsb_timing* t);
+
+/* The deal of a multi-device engine, as a pure host function (testable without a GPU): chromosome c of a batch with
+ * the given CSR offsets goes to device_of[c] in [0, ndev).  Longest-processing-time-first on the cost model of the
+ * kernels that will run (kspace != 0: the kernel-space kernel takes subsets of more than 40 columns, its cost flat in
+ * the subset size; else k^2), at most ceil(npop / ndev) chromosomes per device, ties to the lower device:
+ * deterministic.  The role of the contiguous slices of src/MultiThreadedPopulation.cpp:260-262,302-308. */
+int gsb_deal(const uint32_t* offsets, int32_t npop, int32_t ndev, int32_t kspace, int32_t* device_of);
 
 /* Profiling aid: with GSB_TRACE set in the environment when the engine first touches the device, one
  * CTA of every K1 launch stamps clock64() at its phase boundaries; this returns the (up to 64)

@@ -298,3 +298,40 @@ def test_two_engines_and_a_caller_stream(engine):
         fb2, _ = b.evaluate_population(subsets)
         fc, sc = c.evaluate_population(subsets)
         assert (fa == fb).all() and (fa == fb2).all() and (sc == 0).all() and np.isfinite(fc).all()
+
+
+def test_multi_device_engine_is_bit_identical_to_one_device(engine, oracle_lib):
+    """A multi-device engine (gsb_config.devices) deals every batch to its per-GPU replicas and gathers the results with
+    peer copies: bit-identical fitness and status to the single-device engine, for PLS_CV (kernel-space kernel and per-fit
+    kernel classes, an empty subset, a repeated call with another batch), PLS_FIT and LM."""
+    from conftest import cuda_device_count
+    from gaselect_b200 import evaluators as E
+    ndev = cuda_device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 CUDA devices")
+    devices = list(range(min(ndev, 8)))
+    X, y = synth.nir_spectra(150, 400, seed=12, noise=1e-2)
+    kw = dict(numReplications=3, maxNComp=8, innerSegments=4, outerSegments=5)
+    subsets = synth.random_subsets(400, 203, 1, 150, seed=5)
+    subsets[7] = np.zeros(0, dtype=np.uint32)
+    with E.PLSEvaluator(X, y, 123, **kw) as one, E.PLSEvaluator(X, y, 123, devices=devices, **kw) as multi:
+        f1, s1 = one.evaluate_population(subsets)
+        fm, sm = multi.evaluate_population(subsets)
+        assert (s1 == sm).all() and (f1 == fm).all() and s1[7] == 1 and (s1 == 0).sum() == len(subsets) - 1
+        f1b, s1b = one.evaluate_population(subsets[::3])
+        fmb, smb = multi.evaluate_population(subsets[::3])
+        assert (s1b == smb).all() and (f1b == fmb).all() and (f1b == f1[::3]).all()
+        fo, _ = oracle_lib.pls_evaluator(X, y, oracle_lib.make_seedvec(123), **kw).evaluate(subsets[20:28], threads=4)
+        assert rel_err(fm[20:28], fo).max() <= REL_TOL
+        assert multi.timing()["fit_ctas"] == one.timing()["fit_ctas"] or multi.timing()["fit_ctas"] > 0
+        fe, se = multi.evaluate_population([])
+        assert len(fe) == 0 and len(se) == 0
+    narrow = [s for s in subsets if 0 < len(s) <= 60]
+    with E.BICEvaluator(X, y, 123, numSegments=5, maxNComp=6) as one, E.BICEvaluator(X, y, 123, numSegments=5, maxNComp=6, devices=devices) as multi:
+        f1, s1 = one.evaluate_population(narrow)
+        fm, sm = multi.evaluate_population(narrow)
+        assert (s1 == sm).all() and (f1 == fm).all()
+    with E.LMEvaluator(X, y) as one, E.LMEvaluator(X, y, devices=devices[:2]) as multi:
+        f1, s1 = one.evaluate_population(narrow)
+        fm, sm = multi.evaluate_population(narrow)
+        assert (s1 == sm).all() and (f1 == fm).all()

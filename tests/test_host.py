@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(engine):
     for name in declared:
         assert hasattr(engine, name), name + " is declared in include/gaselect_b200.h but not exported"
     assert declared == set(_capi.SIGNATURES), "ctypes signatures out of sync with the header"
-    assert engine.gsb_abi_version() == 2
+    assert engine.gsb_abi_version() == 3
 
 
 def test_struct_sizes_match_the_header(engine, tmp_path):
@@ -185,3 +185,47 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("oracle-independent", ""), os.path.join(dirpath, f)
+
+
+def test_multi_device_deal_is_a_balanced_deterministic_partition(engine):
+    """gsb_deal: the deal of a multi-device engine (pure host function): a partition with equal counts, balanced on the
+    cost model, deterministic, and the same deal as the Python host of the one-process-per-GPU path (multigpu.deal)."""
+    from gaselect_b200 import _capi, multigpu, synth
+    subsets = synth.random_subsets(1000, 501, 0, 200, seed=11)
+    _, offsets = _capi.to_csr(subsets)
+    sizes = np.diff(offsets.astype(np.int64))
+    for ndev in (1, 2, 3, 8):
+        for kspace in (0, 1):
+            dev = np.full(len(subsets), -1, dtype=np.int32)
+            assert engine.gsb_deal(offsets, len(subsets), ndev, kspace, dev) == 0
+            assert dev.min() >= 0 and dev.max() < ndev
+            counts = np.bincount(dev, minlength=ndev)
+            assert counts.max() <= -(-len(subsets) // ndev) and counts.sum() == len(subsets)
+            cost = multigpu.kspace_cost(sizes) if kspace else multigpu.gram_cost(sizes)
+            loads = np.array([cost[dev == d].sum() for d in range(ndev)])
+            assert loads.max() - loads.min() <= 1.5 * cost.max()
+            again = np.zeros_like(dev)
+            engine.gsb_deal(offsets, len(subsets), ndev, kspace, again)
+            assert (again == dev).all()
+            shares = multigpu.deal(sizes, ndev, cost=cost, equal_counts=True)
+            for d in range(ndev):
+                assert np.flatnonzero(dev == d).tolist() == shares[d].tolist()
+    assert engine.gsb_deal(offsets, len(subsets), 0, 0, dev) != 0 and engine.gsb_deal(offsets, len(subsets), 17, 0, dev) != 0
+
+
+def test_multi_device_configuration_is_validated(engine):
+    """A device list with a repeated or negative ordinal is an invalid argument; a valid list creates an engine without
+    touching CUDA (host-side segmentation works; evaluation fails loudly without the devices)."""
+    from gaselect_b200 import evaluators as E
+    from gaselect_b200 import synth
+    X, y = synth.nir_spectra(40, 12, seed=1)
+    with pytest.raises(ValueError):
+        E.PLSEvaluator(X, y, 1, numReplications=2, innerSegments=3, devices=[0, 0])
+    with pytest.raises(ValueError):
+        E.PLSEvaluator(X, y, 1, numReplications=2, innerSegments=3, devices=[0, -1])
+    with E.PLSEvaluator(X, y, 1, numReplications=2, innerSegments=3, devices=[0, 1]) as multi:
+        with E.PLSEvaluator(X, y, 1, numReplications=2, innerSegments=3) as single:
+            assert seg_digest(multi.getSegmentation()) == seg_digest(single.getSegmentation())
+        if cuda_device_count() < 2:
+            with pytest.raises(E.EngineError):
+                multi.evaluate_population([np.arange(5, dtype=np.uint32)])
