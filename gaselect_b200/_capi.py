@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libgaselect_b200.so")
 GSB_OK, GSB_ERR_INVALID_ARGUMENT, GSB_ERR_STATE, GSB_ERR_CUDA, GSB_ERR_MEMORY = range(5)
 EVAL_PLS_CV, EVAL_LM, EVAL_PLS_FIT = 1, 2, 3
 STAT = {"BIC": 0, "AIC": 1, "adjusted.r.squared": 2, "r.squared": 3}
-STATUS_OK, STATUS_EMPTY, STATUS_UNDERFLOW, STATUS_SINGULAR = range(4)
+STATUS_OK, STATUS_EMPTY, STATUS_UNDERFLOW, STATUS_SINGULAR, STATUS_FLAGGED = range(5)
 SEED_WORDS = 624
 MAX_DEVICES = 16
 
@@ -26,6 +26,7 @@ class Config(C.Structure):
         ("num_replications", C.c_int32), ("inner_segments", C.c_int32), ("outer_segments", C.c_int32),
         ("max_ncomp", C.c_int32), ("test_set_size", C.c_double), ("sdfact", C.c_double),
         ("complexity_penalty", C.c_double), ("num_devices", C.c_int32), ("devices", C.c_int32 * 16), ("reserved", C.c_int32),
+        ("tie_band", C.c_double),
     ]
 
 

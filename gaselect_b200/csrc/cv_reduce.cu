@@ -6,7 +6,9 @@
 //     (src/PLSEvaluator.cpp:284-308) -> optNComp;
 //   * residual statistics of the outer fit at optNComp, pooled over the outer folds of a
 //     replication; SEP = sample SD of the pooled residuals (:323-335);
-//   * fitness = -(1 + gamma k) * mean over replications (src/PLSEvaluator.cpp:87).
+//   * fitness = -(1 + gamma k) * mean over replications (src/PLSEvaluator.cpp:87);
+//   * status 4 (GSB_STATUS_FLAGGED) when a comparison of the rule was a near-tie (relative band gsb_config.tie_band):
+//     the fitness is valid for this engine, but a flipped optNComp moves it by O(1e-2), so the host may re-score.
 // and of BICEvaluator::getRSS / evaluate (src/BICEvaluator.cpp:191-226, :64-88): the same rule
 // over the K folds, RSS of the all-rows fit at optNComp, then BIC / AIC / adjusted R2 / R2.
 #include "kernels.cuh"
@@ -38,45 +40,22 @@ __global__ void __launch_bounds__(kReduceThreads) cvReduceKernel(const ReducePar
 
 	for (int g = threadIdx.x; g < prm.groups; g += kReduceThreads) {
 		const double* m = mseC + static_cast<size_t>(g) * I * prm.maxNComp;
-		bool bad = false;
-		// first minimum of the fold-mean MSEP (strict '<', :284-292)
-		int minIdx = 0;
-		double best = 0.0;
-		for (int a = 0; a < A; ++a) {
-			double s = 0.0;
-			for (int j = 0; j < I; ++j) s += m[j * prm.maxNComp + a];
-			s /= static_cast<double>(I);
-			if (isnan(s)) bad = true;
-			if (a == 0 || s < best) { best = s; minIdx = a; }
-		}
-		// sample SD over the folds at the minimum (I - 1 denominator; NaN when I == 1)
-		double ss = 0.0;
-		for (int j = 0; j < I; ++j) { const double d = m[j * prm.maxNComp + minIdx] - best; ss = fma(d, d, ss); }
-		const double cutoff = best + sqrt(ss / static_cast<double>(I - 1)) * prm.sdfact; // :296
-		int opt;
-		if (minIdx == 0) {
-			opt = 1; // :298-299
-		} else {
-			opt = 0; // :301-307
-			while (opt < minIdx) {
-				double s = 0.0;
-				for (int j = 0; j < I; ++j) s += m[j * prm.maxNComp + opt];
-				s /= static_cast<double>(I);
-				if (!(s > cutoff)) break;
-				++opt;
-			}
-			++opt;
-		}
+		const OneSe rule = oneSeRule(m, I, A, prm.maxNComp, prm.sdfact, prm.tieBand);
+		const bool bad = rule.bad;
+		const int opt = rule.opt;
 		const double* o = ostC + (static_cast<size_t>(g) * prm.maxNComp + (opt - 1)) * 2;
 		gE[g] = o[0];
 		gEE[g] = o[1];
-		gBad[g] = (bad || isnan(o[1])) ? 1 : 0;
+		gBad[g] = ((bad || isnan(o[1])) ? 1 : 0) | (rule.tie ? 2 : 0);
 	}
 	__syncthreads();
 	if (threadIdx.x != 0) return;
 
-	bool bad = false;
-	for (int g = 0; g < prm.groups; ++g) bad = bad || (gBad[g] != 0);
+	bool bad = false, tie = false;
+	for (int g = 0; g < prm.groups; ++g) {
+		bad = bad || (gBad[g] & 1) != 0;
+		tie = tie || (gBad[g] & 2) != 0;
+	}
 	if (bad) { // the reference throws: src/PLSEvaluator.cpp:337-340, src/BICEvaluator.cpp:227-230
 		prm.fitness[chrom] = 0.0;
 		prm.status[chrom] = 2;
@@ -110,12 +89,29 @@ __global__ void __launch_bounds__(kReduceThreads) cvReduceKernel(const ReducePar
 		} else fit = 1.0 - (RSS / prm.r2denom);                                        // :83
 	}
 	prm.fitness[chrom] = fit;
-	prm.status[chrom] = 0;
+	prm.status[chrom] = tie ? 4 : 0; // GSB_STATUS_FLAGGED: the fitness is this engine's, a near-tie decided optNComp
 }
 
 __global__ void markEmptyKernel(const uint32_t* offsets, int npop, double* fitness, int* status) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c < npop && offsets[c + 1] == offsets[c]) { fitness[c] = 0.0; status[c] = 1; }
+}
+
+// LMEvaluator does not refuse an empty subset (src/LMEvaluator.cpp:27-67): Xsub is the intercept column alone, the
+// solve returns the mean of y, RSS = sum (y - mean)^2 = r2denom, Xsub.n_cols = 1.
+__global__ void lmEmptyKernel(const uint32_t* offsets, int npop, int statistic, int n, double r2denom, double* fitness, int* status) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= npop || offsets[c + 1] != offsets[c]) return;
+	const double dn = static_cast<double>(n), dm = 1.0, RSS = r2denom;
+	double fit;
+	if (statistic == 0) fit = -(dn * log(RSS / dn) + dm * log(dn));   // :41
+	else if (statistic == 1) fit = -(dn * log(RSS / dn) + dm * 2.0);   // :45
+	else if (statistic == 2) {                                         // :49-50
+		const double r2 = 1.0 - (RSS / r2denom);
+		fit = 1.0 - (((dn - 1.0) * (1.0 - r2)) / (dn - dm - 1.0));
+	} else fit = 1.0 - (RSS / r2denom);                                // :54
+	fitness[c] = fit;
+	status[c] = 0;
 }
 
 } // namespace
@@ -129,6 +125,11 @@ void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream) {
 void launchMarkEmpty(const uint32_t* offsets, int npop, double* fitness, int* status, cudaStream_t stream) {
 	if (npop <= 0) return;
 	markEmptyKernel<<<(npop + 255) / 256, 256, 0, stream>>>(offsets, npop, fitness, status);
+}
+
+void launchLmEmpty(const uint32_t* offsets, int npop, int statistic, int n, double r2denom, double* fitness, int* status, cudaStream_t stream) {
+	if (npop <= 0) return;
+	lmEmptyKernel<<<(npop + 255) / 256, 256, 0, stream>>>(offsets, npop, statistic, n, r2denom, fitness, status);
 }
 
 } // namespace gsb

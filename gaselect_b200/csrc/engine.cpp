@@ -116,7 +116,7 @@ int bucketCeil(int k) {
 
 // profiling / experiment switches, read from the environment ONCE per engine (ensureDevice)
 struct EnvFlags {
-	bool serial = false, noScores = false, noKspace = false, trace = false, noPredict = false, noTmem = false;
+	bool serial = false, noScores = false, noKspace = false, trace = false, noPredict = false, noTmem = false, noEarlyStop = false;
 	int kspaceNf = 8, kspaceMinK = 40, kspaceSplit = 0, desync = 0;
 	int forcedNf = 0, forcedCs = 0, forcedVg = 0;
 };
@@ -284,6 +284,18 @@ struct gsb_engine {
 	DeviceArray<gsb::KFitDesc> kFits;
 	DeviceArray<gsb::KTaskDesc> kTasks;
 	int kspaceFits = 0; // 0: not available for this plan
+	// ... and the order its CTAs run the fits in (buildKspaceSchedule): fits that feed the MSEP table first, outer-only fits last
+	std::vector<int> kFitPhase, kFitComp; // per fit: 1 = outer-only; dependency component (fits and CV groups that share MSEP tables)
+	int kComponents = 0;
+	std::vector<int> hFitOrder;
+	std::vector<gsb::KPartDesc> hParts;
+	DeviceArray<int> kFitOrder;
+	DeviceArray<gsb::KPartDesc> kParts;
+	DeviceArray<uint32_t> kSched;
+	DeviceArray<unsigned long long> kProducts;
+	int kSchedSplit = -1, kSchedNf = -1, kSchedStride = 2;
+	bool kSchedEarly = false;
+	bool kProductsPending = false;
 	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
 
@@ -322,6 +334,8 @@ void releaseDevice(gsb_engine* e) {
 	e->coefScratch.release(); e->activeBlocks.release(); e->blockTaskOff.release(); e->predTasks.release();
 	e->xz.release(); e->scoreScratch.release(); e->xReps.release(); e->xGroups8.release(); e->xGroups16.release(); e->xFits.release(); e->xTasks.release();
 	e->kFits.release(); e->kTasks.release();
+	e->kFitOrder.release(); e->kParts.release(); e->kSched.release(); e->kProducts.release();
+	e->kSchedSplit = e->kSchedNf = -1;
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
@@ -371,6 +385,7 @@ void ensureDevice(gsb_engine* e) {
 	env.noScores = std::getenv("GSB_NO_SCORES") != nullptr;
 	env.noKspace = std::getenv("GSB_NO_KSPACE") != nullptr;
 	env.trace = std::getenv("GSB_TRACE") != nullptr;
+	env.noEarlyStop = std::getenv("GSB_NO_EARLYSTOP") != nullptr; // outer-only fits run every component (the arrangement before ABI 4)
 	env.noTmem = std::getenv("GSB_TMEM") == nullptr;          // opt-in experiment: the fit's Gram rows in tensor memory (simpls_tmem.cu; measured slower)
 	env.noPredict = std::getenv("GSB_NO_PREDICT") != nullptr; // per-fit kernel predicts in place (the previous arrangement)
 	if (const char* v = std::getenv("GSB_KSPACE_NF")) env.kspaceNf = std::atoi(v) == 16 ? 16 : 8;
@@ -897,6 +912,37 @@ void prepareDevice(gsb_engine* e) {
 		e->kTasks.upload(kt, e->stream);
 		GSB_CUDA(cudaStreamSynchronize(e->stream));
 		e->kspaceFits = nfits;
+		// outer-only fits, and the dependency components of (fits, CV groups): a fit belongs with every group whose MSEP
+		// table it feeds or whose optNComp it is fitted with (in a nested CV: one component per replication)
+		const int I = std::max(1, plan.innerPerGroup);
+		std::vector<int> parent(static_cast<size_t>(std::max(1, plan.groups)));
+		std::iota(parent.begin(), parent.end(), 0);
+		std::function<int(int)> find = [&](int x) { while (parent[static_cast<size_t>(x)] != x) x = parent[static_cast<size_t>(x)] = parent[static_cast<size_t>(parent[static_cast<size_t>(x)])]; return x; };
+		auto groupOf = [&](const gsb::PlanTask& pt) { return pt.kind == gsb::TASK_OUTER ? pt.dest : pt.dest / I; };
+		e->kFitPhase.assign(static_cast<size_t>(nfits), 1);
+		for (int f = 0; f < nfits; ++f) {
+			const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
+			if (pf.taskCount == 0) e->kFitPhase[static_cast<size_t>(f)] = 0;
+			for (int t = pf.taskBegin; t < pf.taskBegin + pf.taskCount; ++t) {
+				if (plan.tasks[static_cast<size_t>(t)].kind != gsb::TASK_OUTER) e->kFitPhase[static_cast<size_t>(f)] = 0;
+				const int a = find(groupOf(plan.tasks[static_cast<size_t>(pf.taskBegin)])), b = find(groupOf(plan.tasks[static_cast<size_t>(t)]));
+				if (a != b) parent[static_cast<size_t>(std::max(a, b))] = std::min(a, b);
+			}
+		}
+		std::vector<int> compId(parent.size(), -1);
+		e->kComponents = 0;
+		for (size_t g = 0; g < parent.size(); ++g) {
+			const int r = find(static_cast<int>(g));
+			if (compId[static_cast<size_t>(r)] < 0) compId[static_cast<size_t>(r)] = e->kComponents++;
+			compId[g] = compId[static_cast<size_t>(r)];
+		}
+		e->kFitComp.assign(static_cast<size_t>(nfits), 0);
+		for (int f = 0; f < nfits; ++f) {
+			const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
+			if (pf.taskCount > 0) e->kFitComp[static_cast<size_t>(f)] = compId[static_cast<size_t>(groupOf(plan.tasks[static_cast<size_t>(pf.taskBegin)]))];
+		}
+		e->kSchedSplit = e->kSchedNf = -1;
+		e->kProducts.reserve(1);
 	}
 
 
@@ -1602,12 +1648,64 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 
 namespace {
 
+// The order the CTAs of the kernel-space kernel run a chromosome's fits in, for `split` CTAs per chromosome and nf fits
+// per pass.  With early stopping every CTA takes whole dependency components (replications): their MSEP fits first,
+// then their outer-only fits, which the kernel stops at optNComp.  Without it (fewer components than CTAs, no
+// outer-only fits, GSB_NO_EARLYSTOP): plan order, equal numbers of passes.
+void buildKspaceSchedule(gsb_engine* e, int split, int nf, int grid) {
+	const int nfits = e->kspaceFits;
+	if (e->kSchedSplit != split || e->kSchedNf != nf) {
+		bool anyOuterOnly = false;
+		for (int f = 0; f < nfits; ++f) anyOuterOnly = anyOuterOnly || e->kFitPhase[static_cast<size_t>(f)] == 1;
+		const bool early = !e->env.noEarlyStop && anyOuterOnly && e->kComponents >= split && nfits < (1 << 24);
+		e->hFitOrder.clear();
+		e->hParts.assign(static_cast<size_t>(split), gsb::KPartDesc());
+		int stride = 2;
+		if (early) {
+			for (int part = 0; part < split; ++part) {
+				gsb::KPartDesc& pd = e->hParts[static_cast<size_t>(part)];
+				pd.begin = static_cast<int>(e->hFitOrder.size());
+				pd.n0 = pd.n1 = pd.pad = 0;
+				for (int phase = 0; phase < 2; ++phase) {
+					for (int f = 0; f < nfits; ++f) {
+						const int comp = e->kFitComp[static_cast<size_t>(f)];
+						if (static_cast<long long>(comp) * split / e->kComponents != part || e->kFitPhase[static_cast<size_t>(f)] != phase) continue;
+						e->hFitOrder.push_back(f);
+						(phase == 0 ? pd.n0 : pd.n1) += 1;
+					}
+				}
+			}
+		} else {
+			const int passes = (nfits + nf - 1) / nf, perPart = (passes + split - 1) / split;
+			for (int f = 0; f < nfits; ++f) e->hFitOrder.push_back(f);
+			for (int part = 0; part < split; ++part) {
+				gsb::KPartDesc& pd = e->hParts[static_cast<size_t>(part)];
+				pd.begin = std::min(nfits, part * perPart * nf);
+				pd.n0 = std::min(nfits, (part + 1) * perPart * nf) - pd.begin;
+				pd.n1 = pd.pad = 0;
+			}
+		}
+		// per CTA: one schedule word per fit of its part, and as many again to stage the sort
+		for (int part = 0; part < split; ++part) stride = std::max(stride, roundUp(e->hParts[static_cast<size_t>(part)].n0 + e->hParts[static_cast<size_t>(part)].n1, 2));
+		GSB_CUDA(cudaStreamSynchronize(e->stream)); // no launch in flight reads the previous schedule
+		e->kFitOrder.upload(e->hFitOrder, e->stream);
+		e->kParts.upload(e->hParts, e->stream);
+		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		e->kSchedSplit = split;
+		e->kSchedNf = nf;
+		e->kSchedStride = stride;
+		e->kSchedEarly = early;
+	}
+	e->kSched.reserve(static_cast<size_t>(grid) * 2 * static_cast<size_t>(e->kSchedStride));
+}
+
 // K1 per subset-size class, then K2 (or K3 for the LM evaluator); events ev[2..4] bracket them
 void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 		e->timing.fit_tensor_gflop = 0.0;
 		GSB_CUDA(cudaEventRecord(e->ev[2], e->stream));
 		if (e->cfg.evaluator == GSB_EVAL_LM) {
-			gsb::launchMarkEmpty(e->dOffsets.ptr, e->npop, e->dFitness.ptr, e->dStatus.ptr, e->stream);
+			// the reference's LMEvaluator scores an empty subset as the intercept-only model (src/LMEvaluator.cpp:27-67)
+			gsb::launchLmEmpty(e->dOffsets.ptr, e->npop, e->cfg.statistic, e->n, e->r2denom, e->dFitness.ptr, e->dStatus.ptr, e->stream);
 			++launches;
 			for (size_t b = 0; b < e->buckets.size(); ++b) {
 				gsb::OlsParams prm;
@@ -1697,16 +1795,25 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				kp.mse = e->dMse.ptr;
 				kp.ostat = e->dOstat.ptr;
 				kp.trace = e->traceBuf.ptr;
+				buildKspaceSchedule(e, kp.split, kp.nf, kp.bucketCount * kp.split);
+				kp.fitOrder = e->kFitOrder.ptr;
+				kp.parts = e->kParts.ptr;
+				kp.inner = std::max(1, e->plan.innerPerGroup);
+				kp.sdfact = e->shape.sdfact;
+				kp.sched = e->kSched.ptr;
+				kp.schedStride = e->kSchedStride;
+				kp.products = e->kProducts.ptr;
+				GSB_CUDA(cudaMemsetAsync(e->kProducts.ptr, 0, sizeof(unsigned long long), launchStream));
 				GSB_CUDA(gsb::launchKspaceKernel(kp, launchStream, &ctas));
 				++launches;
-				{ // tensor-core work of this launch: DMMA.8x8x4 = 512 FLOP
-					const double nt = kp.n8 / 8, steps = kp.n8 / 4, nb = (kp.n8 / 8 + 1) / 2;
+				e->kProductsPending = true;
+				{ // tensor-core work of the K = Z Z' builds (DMMA.8x8x4 = 512 FLOP); the products are counted by the kernel
+					const double nb = (kp.n8 / 8 + 1) / 2;
 					double dmma = 0.0;
 					for (int i = 0; i < kp.bucketCount; ++i) {
 						const int c = e->hBucket.ptr[e->buckets[kspaceFirst].begin + i];
 						const int k = static_cast<int>(e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c]);
-						dmma += static_cast<double>((e->kspaceFits + 7) / 8) * std::min(e->tableA, k) * nt * steps;  // products: column tiles of 8 fits
-						dmma += static_cast<double>(kp.split) * (nb * (nb + 1) / 2) * 4.0 * ((k + 3) / 4);        // K = Z Z'
+						dmma += static_cast<double>(kp.split) * (nb * (nb + 1) / 2) * 4.0 * ((k + 3) / 4);
 					}
 					e->timing.fit_tensor_gflop = dmma * 512.0 * 1e-9;
 				}
@@ -1845,6 +1952,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			rp.sdfact = e->shape.sdfact;
 			rp.gamma = e->cfg.evaluator == GSB_EVAL_PLS_CV ? e->cfg.complexity_penalty : 0.0;
 			rp.r2denom = e->r2denom;
+			rp.tieBand = e->cfg.tie_band == 0.0 ? 1e-9 : e->cfg.tie_band;
 			rp.fitness = e->dFitness.ptr;
 			rp.status = e->dStatus.ptr;
 			gsb::launchReduceKernel(rp, e->stream);
@@ -1884,8 +1992,15 @@ int gsb_population_evaluate(gsb_engine* e) {
 		ensureDevice(e);
 		long long ctas = 0;
 		int launches = 0;
+		e->kProductsPending = false;
 		enqueuePopulation(e, ctas, launches);
+		unsigned long long products = 0ull;
+		if (e->kProductsPending) GSB_CUDA(cudaMemcpyAsync(&products, e->kProducts.ptr, sizeof(products), cudaMemcpyDeviceToHost, e->stream));
 		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		if (e->kProductsPending) { // products the kernel-space kernel issued (column tiles of 8 fits): n8/8 row tiles x n8/4 steps of DMMA.8x8x4
+			const double n8 = roundUp(e->n, 8);
+			e->timing.fit_tensor_gflop += static_cast<double>(products) * (n8 / 8.0) * (n8 / 4.0) * 512.0 * 1e-9;
+		}
 		float msFit = 0.f, msRed = 0.f;
 		GSB_CUDA(cudaEventElapsedTime(&msFit, e->ev[2], e->ev[3]));
 		GSB_CUDA(cudaEventElapsedTime(&msRed, e->ev[3], e->ev[4]));

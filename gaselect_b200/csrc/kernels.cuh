@@ -116,6 +116,55 @@ struct PredictParams {
 	double* ostat;
 };
 
+// The "one-SE rule" of PLSEvaluator::estSEP (src/PLSEvaluator.cpp:284-308; BICEvaluator::getRSS, src/BICEvaluator.cpp:191-221)
+// for one (replication, outer fold): m[j * stride + a] = MSEP of inner fold j with a + 1 components.  ONE definition for
+// K2 (cv_reduce.cu) and for the kernel-space kernel, which stops its outer fits at optNComp: both take the same decisions
+// to the bit.  `tie`: a comparison the rule took was closer than tieBand (relative) -- another summation order, e.g. the
+// reference's own, may take it the other way (GSB_STATUS_FLAGGED).
+struct OneSe {
+	int opt;   // optNComp, 1-based
+	bool bad;  // a fold mean is NaN (the reference throws, :337-340)
+	bool tie;
+};
+
+#ifdef __CUDACC__
+__device__ inline OneSe oneSeRule(const double* m, int I, int A, int stride, double sdfact, double tieBand) {
+	OneSe r;
+	r.bad = false;
+	r.tie = false;
+	// first minimum of the fold-mean MSEP (strict '<', :284-292)
+	int minIdx = 0;
+	double best = 0.0;
+	for (int a = 0; a < A; ++a) {
+		double s = 0.0;
+		for (int j = 0; j < I; ++j) s += m[j * stride + a];
+		s /= static_cast<double>(I);
+		if (isnan(s)) r.bad = true;
+		if (a > 0 && fabs(s - best) <= tieBand * fabs(best)) r.tie = true;
+		if (a == 0 || s < best) { best = s; minIdx = a; }
+	}
+	// sample SD over the folds at the minimum (I - 1 denominator; NaN when I == 1)
+	double ss = 0.0;
+	for (int j = 0; j < I; ++j) { const double d = m[j * stride + minIdx] - best; ss = fma(d, d, ss); }
+	const double cutoff = best + sqrt(ss / static_cast<double>(I - 1)) * sdfact; // :296
+	if (minIdx == 0) {
+		r.opt = 1; // :298-299
+	} else {
+		int opt = 0; // :301-307
+		while (opt < minIdx) {
+			double s = 0.0;
+			for (int j = 0; j < I; ++j) s += m[j * stride + opt];
+			s /= static_cast<double>(I);
+			if (fabs(s - cutoff) <= tieBand * fabs(cutoff)) r.tie = true;
+			if (!(s > cutoff)) break;
+			++opt;
+		}
+		r.opt = opt + 1;
+	}
+	return r;
+}
+#endif
+
 struct ReduceParams {
 	const double* mse;
 	const double* ostat;
@@ -135,6 +184,7 @@ struct ReduceParams {
 	double sdfact;
 	double gamma;
 	double r2denom;
+	double tieBand; // relative band of the near-tie flag (GSB_STATUS_FLAGGED); negative: off
 	double* fitness;
 	int* status;
 };
@@ -242,6 +292,13 @@ struct KFitDesc {
 	KTaskDesc first[2];           // copies of the fit's first two tasks (kind -1 when absent)
 };
 
+// the fits one CTA of a chromosome runs: fitOrder[begin .. begin + n0 + n1); the first n0 need every component (they
+// feed the MSEP table), the last n1 only predict outer folds: once the first are done the CTA runs the one-SE rule
+// itself and stops each of those at its optNComp (src/PLSEvaluator.cpp:316-317 fits exactly optNComp components)
+struct KPartDesc {
+	int begin, n0, n1, pad;
+};
+
 struct KParams {
 	const double* zpool; // globally centred Z = [X y 1], column-major, leading dimension ldz, rows n..ldz-1 zero
 	const KFitDesc* kfits;
@@ -260,6 +317,13 @@ struct KParams {
 	double* mse;
 	double* ostat;
 	long long* trace; // optional (profiling): clock64() stamps of one CTA
+	const int* fitOrder;      // the order the fits are run in (indices into kfits), per part
+	const KPartDesc* parts;   // `split` entries
+	int inner;                // I: inner folds per (replication, outer fold) of the MSEP table
+	double sdfact;            // of the one-SE rule (after division by sqrt(I))
+	uint32_t* sched;          // per CTA 2 x schedStride words: (components << 24 | fit) per slot of its passes, and the sort's staging
+	int schedStride;
+	unsigned long long* products; // += column tiles x products this launch issued (FP64 tensor work actually done)
 };
 
 
@@ -320,6 +384,7 @@ void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream);
 cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream);
 int olsKernelMaxK(int smemLimit);
 void launchMarkEmpty(const uint32_t* offsets, int npop, double* fitness, int* status, cudaStream_t stream);
+void launchLmEmpty(const uint32_t* offsets, int npop, int statistic, int n, double r2denom, double* fitness, int* status, cudaStream_t stream);
 
 } // namespace gsb
 

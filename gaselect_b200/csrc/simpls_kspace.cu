@@ -432,6 +432,40 @@ __device__ __forceinline__ void kspaceDeflate(KFitState<NF>& fs, const KCtx& cx,
 	}
 }
 
+// The one-SE rule inside the kernel: called by every thread of the CTA once its fits that feed the MSEP table are done
+// (their global writes are visible CTA-wide after the barrier).  Slots [first, total) of the part's fit order are
+// outer-only fits: each gets the optNComp of its outer fold(s) (oneSeRule, the function K2 uses: the same decision to
+// the bit) and they are sorted, longest first, into sched[first ...) -- staged behind the schedule at sched + stride.
+__device__ __forceinline__ void kspaceRule(const KParams& prm, const KPartDesc& pd, uint32_t* sched, int first, int total, int chrom, int A,
+                                        int tid, int nthreads) {
+	__syncthreads();
+	uint32_t* raw = sched + prm.schedStride;
+	const int rem = total - first;
+	for (int j = tid; j < rem; j += nthreads) {
+		const int fj = prm.fitOrder[pd.begin + first + j];
+		const int tb = prm.kfits[fj].taskBegin, ntk = prm.kfits[fj].ntasks;
+		int nc = 1;
+		for (int tk = 0; tk < ntk; ++tk) {
+			const int grp = prm.ktasks[tb + tk].dest; // outer task: dest = (replication, outer fold)
+			const double* m = prm.mse + (static_cast<size_t>(chrom) * prm.innerDests + static_cast<size_t>(grp) * prm.inner) * prm.maxNComp;
+			const OneSe rule = oneSeRule(m, prm.inner, A, prm.maxNComp, prm.sdfact, -1.0);
+			nc = max(nc, rule.bad ? A : rule.opt);
+		}
+		raw[j] = (static_cast<uint32_t>(nc) << 24) | static_cast<uint32_t>(fj);
+	}
+	__syncthreads();
+	for (int j = tid; j < rem; j += nthreads) { // rank sort, longest first; ties keep their order
+		const uint32_t key = raw[j];
+		int rank = 0;
+		for (int i = 0; i < rem; ++i) {
+			const uint32_t ki = raw[i] >> 24;
+			rank += (ki > (key >> 24) || (ki == (key >> 24) && i < j)) ? 1 : 0;
+		}
+		sched[first + rank] = key;
+	}
+	__syncthreads();
+}
+
 // TRACE: the instance that stamps clock64() at its phase boundaries (launched only when prm.trace is set: the stamps
 // and the loads of their destination cost ~3 % in the component loop even when predicated off)
 template <int NF, bool TRACE>
@@ -458,6 +492,10 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
 	const int A = min(prm.maxNComp, k);
 	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+	// this CTA's fits: fitOrder[pd.begin ...), the first n0 with every component, then n1 that only predict outer folds
+	const KPartDesc pd = prm.parts[part];
+	const int total = pd.n0 + pd.n1;
+	if (total == 0) return;
 
 	const bool tracing = TRACE && prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
 	int stamp = 0;
@@ -567,17 +605,31 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	GSB_KSTAMP(); // 1: K done
 
 	// ---- passes of NF fits: one warp per fit ---------------------------------------------------------------------
-	const int passes = (prm.nfits + kKNF - 1) / kKNF;
-	const int perPart = (passes + prm.split - 1) / prm.split;
-	const int passEnd = min(passes, (part + 1) * perPart);
+	// The reference fits its outer models with exactly optNComp components (src/PLSEvaluator.cpp:316-317).  Once the
+	// passes holding the fits that feed the MSEP table are done, the CTA runs the one-SE rule itself (oneSeRule, the
+	// function K2 uses: same decision to the bit), sorts the remaining outer-only fits by their optNComp and runs each
+	// pass only as far as its longest fit needs.  (An outer-only fit sharing a pass with MSEP fits runs every component.)
+	const int passes = (total + kKNF - 1) / kKNF;
+	const int ruleAt = (pd.n1 > 0 && pd.n0 > 0) ? (pd.n0 + kKNF - 1) / kKNF : passes;
+	// the CTA's schedule: one word per slot, (components to run) << 24 | fit; the slots from ruleAt * NF on are written
+	// by kspaceRule below
+	uint32_t* sched = prm.sched + static_cast<size_t>(blockIdx.x) * 2 * prm.schedStride;
+	for (int j = tid; j < min(total, ruleAt * kKNF); j += kKThreads) {
+		sched[j] = (static_cast<uint32_t>(A) << 24) | static_cast<uint32_t>(prm.fitOrder[pd.begin + j]);
+	}
+	unsigned long long nprod = 0ull;
 	double* __restrict__ taW = TA + warp * ldk;
 	const double* __restrict__ tbW = TB + warp * ldk;
+	__syncthreads();
 #pragma unroll 1
-	for (int pass = part * perPart; pass < passEnd; ++pass) {
-		const int fi = pass * kKNF + warp;
-		const bool fitActive = fi < prm.nfits;
+	for (int pass = 0; pass < passes; ++pass) {
+		if (pass == ruleAt) kspaceRule(prm, pd, sched, ruleAt * kKNF, total, chrom, A, tid, kKThreads);
+		const int slot = min(pass * kKNF + warp, total - 1);
+		const bool fitActive = pass * kKNF + warp < total;
+		const int fi = static_cast<int>(sched[slot] & 0xffffffu);
+		const int Apass = min(A, static_cast<int>(sched[pass * kKNF] >> 24));
 		// one 128-byte record per fit: masks, centring constants and its first two tasks (no dependent loads)
-		const KFitDesc fd = prm.kfits[min(fi, prm.nfits - 1)];
+		const KFitDesc fd = prm.kfits[fi];
 		KFitState<NF> fs;
 		fs.tmemU = tmemBase + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(128 * (warp >> 2));
 		fs.trainBits = 0u; // bit u: the lane's row of slot u is a training row of the fit
@@ -611,7 +663,8 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 		for (int u = 0; u < kKNS; ++u) {
 			if ((fs.rowBits >> u) & 1u) taW[32 * u + lane] = ((fs.trainBits >> u) & 1u) ? fs.yc[u] : 0.0;
 		}
-		const int ct = (min(prm.nfits - pass * kKNF, kKNF) + 7) >> 3; // column tiles of 8 fits in use
+		const int ct = (min(total - pass * kKNF, kKNF) + 7) >> 3; // column tiles of 8 fits in use
+		nprod += static_cast<unsigned long long>(ct * Apass);
 		__syncthreads();
 		kernelProduct(Km, TA, TB, n8, ldk, warp, lane, ct);
 		__syncthreads();
@@ -622,12 +675,14 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 		cx.n8 = n8; cx.ldk = ldk; cx.warp = warp; cx.lane = lane; cx.A = A; cx.chrom = chrom;
 		cx.fd = &fd;
 		cx.fitActive = fitActive;
-		cx.tracing = tracing && pass == part * perPart;
+		cx.tracing = tracing && pass == 0;
 		if (cx.tracing) GSB_KSTAMP(); // 2: first scores
-		// the barriers below are uniform: A is a property of the chromosome
+		// the barriers below are uniform: Apass is a property of the pass.  (The loop bound is deliberately A, not Apass,
+		// and kspaceRule is force-inlined: with either of the other forms nvcc 12.9 emits the scores and deflation code
+		// twice -- 10.9 k instead of 7.7 k instructions -- and the instruction cache costs 4 % of the launch.)
 #pragma unroll 1
 		for (int comp = 0; comp < A; ++comp) {
-			const bool more = comp + 1 < A;
+			const bool more = comp + 1 < Apass;
 			double tc[kKNS], st[4];
 			kspaceScores<NF>(fs, cx, comp, more, tc, st);
 			if (!more) break;
@@ -654,6 +709,7 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 		}
 	}
 #undef GSB_KSTAMP
+	if (tid == 0 && prm.products != nullptr) atomicAdd(prm.products, nprod);
 	if (NF != 8) {
 		__syncthreads();
 		if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmemBase));

@@ -10,7 +10,10 @@ Same names, argument meaning and error behaviour as the reference's C++ evaluato
 src/Evaluator.h:30) and raises ``EvaluatorException`` where the reference throws
 ``Evaluator::EvaluatorException`` (src/Evaluator.h:21-25); ``evaluate_population`` is the batch
 loop of src/GenAlg.cpp:312-325 as ONE engine call and returns (fitness, status) so that a GA
-driver can re-draw failed slots itself (src/MultiThreadedPopulation.cpp:202-206).
+driver can re-draw failed slots itself (src/MultiThreadedPopulation.cpp:202-206).  Status 4
+(``STATUS_FLAGGED``) is not a failure: the fitness is valid, but a comparison of the one-SE rule
+(src/PLSEvaluator.cpp:284-308) was a near-tie within the relative band ``tieBand`` (default 1e-9), so
+the reference -- summing in another order -- may fit a different number of components.
 ``getSegmentation()`` is src/Evaluator.h:35-37.  Everything numerical happens in the sm_100a
 kernels behind include/gaselect_b200.h; nothing here computes a fit on the CPU.
 """
@@ -68,6 +71,7 @@ class Evaluator:
         c.test_set_size = cfg.get("test_set_size", 0.0)
         c.sdfact = cfg.get("sdfact", 1.0)
         c.complexity_penalty = cfg.get("complexity_penalty", 0.0)
+        c.tie_band = cfg.get("tie_band", 0.0)
         self._h = _capi._H()
         self._lib = lib
         rc = lib.gsb_create(C.byref(self._h), C.byref(c))
@@ -174,7 +178,7 @@ class Evaluator:
     def evaluate(self, columnSubset):
         """double Evaluator::evaluate(arma::uvec &columnSubset), src/Evaluator.h:30."""
         fitness, status = self.evaluate_population([np.asarray(columnSubset, dtype=np.uint32)])
-        if status[0] != _capi.STATUS_OK:
+        if status[0] not in (_capi.STATUS_OK, _capi.STATUS_FLAGGED):  # FLAGGED: valid fitness, near-tie in the one-SE rule
             raise EvaluatorException(_STATUS_MESSAGE.get(int(status[0]), "evaluation failed"))
         return float(fitness[0])
 
@@ -226,8 +230,8 @@ class PLSEvaluator(Evaluator):
     _kind = _capi.EVAL_PLS_CV
 
     def __init__(self, X, y, seed, numReplications=30, maxNComp=0, innerSegments=7, outerSegments=1,
-                 testSetSize=0.0, sdfact=1.0, complexityPenalty=0.0, device=0, devices=None):
-        super().__init__(X, y, seed, device=device, devices=devices, num_replications=int(numReplications), max_ncomp=int(maxNComp),
+                 testSetSize=0.0, sdfact=1.0, complexityPenalty=0.0, device=0, devices=None, tieBand=0.0):
+        super().__init__(X, y, seed, device=device, devices=devices, tie_band=float(tieBand), num_replications=int(numReplications), max_ncomp=int(maxNComp),
                          inner_segments=int(innerSegments), outer_segments=int(outerSegments),
                          test_set_size=float(testSetSize), sdfact=float(sdfact),
                          complexity_penalty=float(complexityPenalty))
@@ -239,8 +243,8 @@ class BICEvaluator(Evaluator):
 
     _kind = _capi.EVAL_PLS_FIT
 
-    def __init__(self, X, y, seed, numSegments=7, statistic="BIC", maxNComp=0, sdfact=1.0, device=0, devices=None):
-        super().__init__(X, y, seed, device=device, devices=devices, inner_segments=int(numSegments), statistic=_capi.STAT[statistic],
+    def __init__(self, X, y, seed, numSegments=7, statistic="BIC", maxNComp=0, sdfact=1.0, device=0, devices=None, tieBand=0.0):
+        super().__init__(X, y, seed, device=device, devices=devices, tie_band=float(tieBand), inner_segments=int(numSegments), statistic=_capi.STAT[statistic],
                          max_ncomp=int(maxNComp), sdfact=float(sdfact))
 
 

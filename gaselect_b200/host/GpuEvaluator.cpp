@@ -117,8 +117,17 @@ void GpuEvaluator::evaluateBatch(const std::vector<arma::uvec>& subsets, std::ve
 		std::lock_guard<std::mutex> guard(engine->lock);
 		check(engine->handle, gsb_evaluate_indices(engine->handle, idx.data(), offsets.data(), static_cast<int32_t>(n),
 		                                           fitness.data(), st.data()));
+		// GSB_STATUS_FLAGGED is not a failure (the fitness is valid; a near-tie decided optNComp): counted, reported as OK
+		for (size_t i = 0; i < n; ++i) {
+			if (st[i] == GSB_STATUS_FLAGGED) { st[i] = GSB_STATUS_OK; ++engine->flagged; }
+		}
 	}
 	status.assign(st.begin(), st.end());
+}
+
+size_t GpuEvaluator::flaggedCount() const {
+	std::lock_guard<std::mutex> guard(engine->lock);
+	return engine->flagged;
 }
 
 double GpuEvaluator::evaluate(arma::uvec& columnSubset) {

@@ -6,7 +6,8 @@
 // unchanged: construction sites src/GenAlg.cpp:119-127 (PLS), :131-141 (LM), :142-156 (FIT),
 // :262-303 (evaluate).  See INTEGRATION.md.
 //
-// Error convention: per-chromosome status != 0 -> Evaluator::EvaluatorException
+// Error convention: per-chromosome status 1..3 -> Evaluator::EvaluatorException; status 4
+// (GSB_STATUS_FLAGGED: valid fitness, near-tie in the one-SE rule) is counted (flaggedCount()), not thrown
 // (callers re-draw the slot, src/MultiThreadedPopulation.cpp:202-206); invalid constructor arguments
 // -> std::invalid_argument (src/PLSEvaluator.cpp:43,51); any other engine failure -> std::runtime_error.
 #ifndef GASELECT_B200_GPU_EVALUATOR_H
@@ -59,10 +60,15 @@ public:
 	// which the reference would have thrown EvaluatorException.
 	void evaluateBatch(const std::vector<arma::uvec>& subsets, std::vector<double>& fitness, std::vector<int>& status);
 
+	// Evaluations (over all clones) whose one-SE rule met a near-tie (GSB_STATUS_FLAGGED, relative band 1e-9): their
+	// fitness was returned as usual; the reference, summing in another order, may have fitted another optNComp there.
+	size_t flaggedCount() const;
+
 private:
 	struct Engine { // shared by clones: an engine is not re-entrant, calls are serialised
 		gsb_engine* handle = nullptr;
-		std::mutex lock;
+		mutable std::mutex lock;
+		size_t flagged = 0;
 		~Engine() { gsb_destroy(handle); }
 	};
 	GpuEvaluator(std::shared_ptr<Engine> engine, VerbosityLevel verbosity) : Evaluator(verbosity), engine(engine) {}

@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define GSB_ABI_VERSION 3
+#define GSB_ABI_VERSION 4
 #define GSB_SEED_WORDS 624 /* RNG::SEED_SIZE, src/RNG.h:64 */
 #define GSB_MAX_DEVICES 16
 
@@ -57,7 +57,13 @@ typedef enum gsb_status {
 	GSB_STATUS_OK = 0,
 	GSB_STATUS_EMPTY = 1,     /* empty subset: src/PLSEvaluator.cpp:72-75, src/BICEvaluator.cpp:55-58 */
 	GSB_STATUS_UNDERFLOW = 2, /* ||t|| < 1e-25: src/PLSSimpls.cpp:141-143 -> src/PLSEvaluator.cpp:337-340 */
-	GSB_STATUS_SINGULAR = 3   /* system could not be solved: src/LMEvaluator.cpp:60-61 */
+	GSB_STATUS_SINGULAR = 3,  /* system could not be solved: src/LMEvaluator.cpp:60-61 */
+	/* NOT an error: fitness is valid, but a comparison of the one-SE rule (src/PLSEvaluator.cpp:284-308: the first
+	 * minimum of the fold-mean MSEP, or a fold mean against the cutoff) was a near-tie within the relative band
+	 * gsb_config.tie_band.  The reference, summing in another order, may take that comparison the other way and fit a
+	 * different optNComp (moves the fitness by O(1e-2)); a host that needs the reference's exact choice re-scores the
+	 * flagged chromosomes there.  The wrappers return the fitness and count the flag; they do not throw. */
+	GSB_STATUS_FLAGGED = 4
 } gsb_status;
 
 typedef enum gsb_error {
@@ -92,6 +98,8 @@ typedef struct gsb_config {
 	int32_t num_devices;
 	int32_t devices[GSB_MAX_DEVICES];
 	int32_t reserved;
+	/* near-tie band of GSB_STATUS_FLAGGED, relative (ABI 4): 0 selects the default 1e-9, negative switches the flag off */
+	double tie_band;
 } gsb_config;
 
 /* read-only facts about a prepared engine (sizes of the fit plan and the device tables) */
@@ -187,7 +195,8 @@ int gsb_set_stream(gsb_engine* e, void* cuda_stream);
 
 /* Evaluator::evaluate(arma::uvec&) over a batch (the loop of src/GenAlg.cpp:312-325):
  * CSR lists of ascending 0-based column indices, HOST buffers.  fitness[npop], status[npop]
- * (gsb_status) are caller-allocated.  fitness is meaningful where status == 0. */
+ * (gsb_status) are caller-allocated.  fitness is meaningful where status == 0 or
+ * status == GSB_STATUS_FLAGGED. */
 int gsb_evaluate_indices(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop,
                          double* fitness, int32_t* status);
 

@@ -68,7 +68,19 @@ def test_virtual_interface_error_convention(dropin):
         f = C.c_double(0.0)
         assert dropin.dropin_evaluate_one(h, np.asarray([1, 2, 5, 8, 11, 13, 17, 19, 23, 29], dtype=np.uint32), 10, C.byref(f)) == 0
         assert f.value == pytest.approx(174.02302223845993, rel=1e-8)
+        # LMEvaluator does not refuse an empty subset: the intercept-only model (src/LMEvaluator.cpp:27-67)
+        assert dropin.dropin_evaluate_one(h, np.zeros(1, dtype=np.uint32), 0, C.byref(f)) == 0
+        assert f.value == pytest.approx(-37.56167949519022, rel=1e-8)  # the reference build's value for this data
+    finally:
+        dropin.dropin_destroy(h)
+    # PLSEvaluator throws on an empty subset (src/PLSEvaluator.cpp:72-75) -> EvaluatorException through the virtual interface
+    sv = np.ascontiguousarray(np.arange(1, 625, dtype=np.uint32))
+    h = dropin.dropin_pls_create(_colmajor(X), np.ascontiguousarray(y), 40, 30, 2, 5, sv, 4, 3, 0.0, 1.0, 0.0)
+    assert h
+    try:
+        f = C.c_double(0.0)
         assert dropin.dropin_evaluate_one(h, np.zeros(1, dtype=np.uint32), 0, C.byref(f)) == 1  # EvaluatorException
+        assert dropin.dropin_evaluate_one(h, np.asarray([1, 2, 5], dtype=np.uint32), 3, C.byref(f)) == 0 and f.value < 0.0
     finally:
         dropin.dropin_destroy(h)
 

@@ -150,3 +150,54 @@ def test_bic_evaluator_on_the_kernel_space_kernel(engine, oracle_lib, stat):
         with E.BICEvaluator(X, y, sv, numSegments=6, statistic=stat, maxNComp=7) as ev:
             fd, sd = ev.evaluate_population(subsets)
     assert (sd == so).all() and rel_err(fd[so == 0], fo[so == 0]).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("split", [1, 2, 5])
+def test_outer_fits_stop_at_optncomp(engine, oracle_lib, split):
+    """The reference fits its outer models with optNComp components only (src/PLSEvaluator.cpp:316-317).  K1k runs the
+    one-SE rule in the kernel once a CTA's MSEP fits are done and stops its outer-only fits there: bit-identical fitness
+    (a fit's first components do not depend on later ones), fewer tensor-core products."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.nir_spectra(150, 400, seed=5)
+    sv = oracle_lib.make_seedvec(9)
+    kw = dict(numReplications=5, maxNComp=10, innerSegments=4, outerSegments=5)
+    subsets = synth.random_subsets(400, 24, 41, 160, seed=2)
+    res = {}
+    for early in (True, False):
+        with forced(GSB_NO_KSPACE=None, GSB_KSPACE_SPLIT=str(split), GSB_NO_EARLYSTOP=None if early else "1"):
+            with E.PLSEvaluator(X, y, sv, **kw) as ev:
+                fit, status = ev.evaluate_population(subsets)
+                res[early] = (fit, status, ev.timing()["fit_tensor_gflop"], ev.timing()["fit_ctas"])
+    assert (res[True][0] == res[False][0]).all() and (res[True][1] == res[False][1]).all()
+    assert res[True][3] == res[False][3] == len(subsets) * split
+    if split < 5:
+        assert res[True][2] < 0.95 * res[False][2], (res[True][2], res[False][2])
+    else:  # one replication per CTA: its 5 outer fits share the pass of the last 2 MSEP fits and run every component
+        assert res[True][2] <= res[False][2]
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=8)
+    assert (res[True][1] == wstatus).all() and rel_err(res[True][0], want).max() <= REL_TOL
+
+
+def test_near_tie_flag(engine, oracle_lib):
+    """GSB_STATUS_FLAGGED (4): a comparison of the one-SE rule (src/PLSEvaluator.cpp:284-308) was closer than the
+    relative band; the fitness is the same valid number.  The default band (1e-9) flags nothing on this data; a band of
+    0.5 flags nearly everything; a negative band switches the flag off.  K1k and the per-fit kernel alike."""
+    from gaselect_b200 import evaluators as E, _capi
+    X, y = synth.nir_spectra(60, 120, seed=3)
+    sv = oracle_lib.make_seedvec(123)
+    kw = dict(numReplications=3, maxNComp=6, innerSegments=3, outerSegments=4)
+    subsets = synth.random_subsets(120, 40, 2, 100, seed=9)
+    out = {}
+    for band in (0.0, 0.5, -1.0):
+        with E.PLSEvaluator(X, y, sv, tieBand=band, **kw) as ev:
+            out[band] = ev.evaluate_population(subsets)
+            if band == 0.5:
+                assert ev.evaluate(subsets[0]) == out[band][0][0]  # the wrapper returns the fitness, it does not raise
+    assert (out[0.0][1] == 0).all() and (out[-1.0][1] == 0).all()
+    assert (out[0.5][1] == _capi.STATUS_FLAGGED).sum() > len(subsets) // 2 and set(out[0.5][1].tolist()) <= {0, 4}
+    assert (out[0.5][0] == out[0.0][0]).all() and (out[-1.0][0] == out[0.0][0]).all()
+    with E.BICEvaluator(X, y, sv, numSegments=5, maxNComp=6, tieBand=0.5) as ev:
+        fb, sb = ev.evaluate_population(subsets)
+    with E.BICEvaluator(X, y, sv, numSegments=5, maxNComp=6) as ev:
+        f0, s0 = ev.evaluate_population(subsets)
+    assert (fb == f0).all() and (s0 == 0).all() and (sb == 4).any()

@@ -140,9 +140,13 @@ def test_empty_ragged_and_unsorted_subsets(engine, oracle_lib):
             ev.evaluate([30])          # column out of range
         f0, s0 = ev.evaluate_population([])
         assert len(f0) == 0
-    with E.LMEvaluator(X, y) as ev:
-        fit, status = ev.evaluate_population(subsets)
-        assert status.tolist() == [1, 0, 0, 1, 0, 0]
+    # LMEvaluator does not refuse an empty subset: it scores the intercept-only model (src/LMEvaluator.cpp:27-67)
+    for stat in ("BIC", "AIC", "adjusted.r.squared", "r.squared"):
+        with E.LMEvaluator(X, y, stat) as ev:
+            fit, status = ev.evaluate_population(subsets)
+        fo, so = oracle_lib.lm_evaluator(X, y, stat).evaluate([sorted(s) for s in subsets])
+        assert status.tolist() == [0] * 6 and so.tolist() == [0] * 6
+        assert np.allclose(fit, fo, rtol=REL_TOL, atol=1e-12)
 
 
 def test_bitset_entry_matches_index_entry(engine):

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(engine):
     for name in declared:
         assert hasattr(engine, name), name + " is declared in include/gaselect_b200.h but not exported"
     assert declared == set(_capi.SIGNATURES), "ctypes signatures out of sync with the header"
-    assert engine.gsb_abi_version() == 3
+    assert engine.gsb_abi_version() == 4
 
 
 def test_struct_sizes_match_the_header(engine, tmp_path):
