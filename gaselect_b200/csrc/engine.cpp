@@ -116,7 +116,7 @@ int bucketCeil(int k) {
 
 // profiling / experiment switches, read from the environment ONCE per engine (ensureDevice)
 struct EnvFlags {
-	bool serial = false, noScores = false, noKspace = false, trace = false, noPredict = false, noTmem = false, noEarlyStop = false;
+	bool serial = false, noScores = false, noKspace = false, trace = false, noPredict = false, forcePredict = false, noTmem = false, noEarlyStop = false;
 	int kspaceNf = 8, kspaceMinK = 40, kspaceSplit = 0, desync = 0;
 	int forcedNf = 0, forcedCs = 0, forcedVg = 0;
 };
@@ -287,14 +287,17 @@ struct gsb_engine {
 	// ... and the order its CTAs run the fits in (buildKspaceSchedule): fits that feed the MSEP table first, outer-only fits last
 	std::vector<int> kFitPhase, kFitComp; // per fit: 1 = outer-only; dependency component (fits and CV groups that share MSEP tables)
 	int kComponents = 0;
-	std::vector<int> hFitOrder;
-	std::vector<gsb::KPartDesc> hParts;
-	DeviceArray<int> kFitOrder;
-	DeviceArray<gsb::KPartDesc> kParts;
+	struct KSchedule { // for one number of CTAs per chromosome (index) and kSchedNf fits per pass
+		bool ready = false, early = false;
+		int stride = 2; // schedule words a CTA needs
+		DeviceArray<int> fitOrder;
+		DeviceArray<gsb::KPartDesc> parts;
+	};
+	static constexpr int kMaxSplit = 8;
+	KSchedule kSchedules[kMaxSplit + 1];
+	int kSchedNf = -1;
 	DeviceArray<uint32_t> kSched;
 	DeviceArray<unsigned long long> kProducts;
-	int kSchedSplit = -1, kSchedNf = -1, kSchedStride = 2;
-	bool kSchedEarly = false;
 	bool kProductsPending = false;
 	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
@@ -334,8 +337,9 @@ void releaseDevice(gsb_engine* e) {
 	e->coefScratch.release(); e->activeBlocks.release(); e->blockTaskOff.release(); e->predTasks.release();
 	e->xz.release(); e->scoreScratch.release(); e->xReps.release(); e->xGroups8.release(); e->xGroups16.release(); e->xFits.release(); e->xTasks.release();
 	e->kFits.release(); e->kTasks.release();
-	e->kFitOrder.release(); e->kParts.release(); e->kSched.release(); e->kProducts.release();
-	e->kSchedSplit = e->kSchedNf = -1;
+	for (int i = 0; i <= gsb_engine::kMaxSplit; ++i) { e->kSchedules[i].fitOrder.release(); e->kSchedules[i].parts.release(); e->kSchedules[i].ready = false; }
+	e->kSched.release(); e->kProducts.release();
+	e->kSchedNf = -1;
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
 	e->hIdx.release(); e->hOffsets.release(); e->hBucket.release(); e->hStatus.release(); e->hFitness.release();
@@ -387,7 +391,8 @@ void ensureDevice(gsb_engine* e) {
 	env.trace = std::getenv("GSB_TRACE") != nullptr;
 	env.noEarlyStop = std::getenv("GSB_NO_EARLYSTOP") != nullptr; // outer-only fits run every component (the arrangement before ABI 4)
 	env.noTmem = std::getenv("GSB_TMEM") == nullptr;          // opt-in experiment: the fit's Gram rows in tensor memory (simpls_tmem.cu; measured slower)
-	env.noPredict = std::getenv("GSB_NO_PREDICT") != nullptr; // per-fit kernel predicts in place (the previous arrangement)
+	env.noPredict = std::getenv("GSB_NO_PREDICT") != nullptr; // per-fit kernel predicts in place whatever the block size
+	env.forcePredict = std::getenv("GSB_PREDICT") != nullptr; // fit-only kernel + predictBlocksKernel whatever the block size
 	if (const char* v = std::getenv("GSB_KSPACE_NF")) env.kspaceNf = std::atoi(v) == 16 ? 16 : 8;
 	if (const char* v = std::getenv("GSB_KSPACE_MINK")) env.kspaceMinK = std::atoi(v);
 	if (const char* v = std::getenv("GSB_KSPACE_SPLIT")) env.kspaceSplit = std::atoi(v);
@@ -941,7 +946,8 @@ void prepareDevice(gsb_engine* e) {
 			const gsb::PlanFit& pf = plan.fits[static_cast<size_t>(f)];
 			if (pf.taskCount > 0) e->kFitComp[static_cast<size_t>(f)] = compId[static_cast<size_t>(groupOf(plan.tasks[static_cast<size_t>(pf.taskBegin)]))];
 		}
-		e->kSchedSplit = e->kSchedNf = -1;
+		for (int i = 0; i <= gsb_engine::kMaxSplit; ++i) e->kSchedules[i].ready = false;
+		e->kSchedNf = -1;
 		e->kProducts.reserve(1);
 	}
 
@@ -1030,7 +1036,10 @@ void planBuckets(gsb_engine* e) {
 		Bucket& bk = e->buckets[b];
 		if (bk.kernel != BK_FIT) continue;
 		// fit-only kernel + one tensor-core prediction per (chromosome, held-out block) where the fast path serves the class
-		bk.split = !env.noPredict && e->nActiveBlocks > 0 && bk.kMax <= gsb::kPredMaxK && gsb::fitOnlyKernelServes(bk.kMax, e->tableA, e->smemLimit);
+		// (measured, profiles/pred_probe.py: the separate prediction wins by 20-30 % with the 100-row blocks of config 4 and
+		// loses 10-20 % with the 30-row blocks of config 3, whose tiles leave the tensor-core product mostly empty)
+		bk.split = !env.noPredict && e->nActiveBlocks > 0 && (e->maxBlockLd >= 64 || env.forcePredict) && bk.kMax <= gsb::kPredMaxK &&
+		           gsb::fitOnlyKernelServes(bk.kMax, e->tableA, e->smemLimit);
 		for (int i = 0; i < bk.count; ++i) {
 			const int c = e->hBucket.ptr[bk.begin + i];
 			const unsigned long long k = e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c];
@@ -1651,52 +1660,55 @@ namespace {
 // The order the CTAs of the kernel-space kernel run a chromosome's fits in, for `split` CTAs per chromosome and nf fits
 // per pass.  With early stopping every CTA takes whole dependency components (replications): their MSEP fits first,
 // then their outer-only fits, which the kernel stops at optNComp.  Without it (fewer components than CTAs, no
-// outer-only fits, GSB_NO_EARLYSTOP): plan order, equal numbers of passes.
-void buildKspaceSchedule(gsb_engine* e, int split, int nf, int grid) {
+// outer-only fits, GSB_NO_EARLYSTOP): plan order, equal numbers of passes.  Built once per (split, nf).
+gsb_engine::KSchedule& kspaceSchedule(gsb_engine* e, int split, int nf) {
 	const int nfits = e->kspaceFits;
-	if (e->kSchedSplit != split || e->kSchedNf != nf) {
-		bool anyOuterOnly = false;
-		for (int f = 0; f < nfits; ++f) anyOuterOnly = anyOuterOnly || e->kFitPhase[static_cast<size_t>(f)] == 1;
-		const bool early = !e->env.noEarlyStop && anyOuterOnly && e->kComponents >= split && nfits < (1 << 24);
-		e->hFitOrder.clear();
-		e->hParts.assign(static_cast<size_t>(split), gsb::KPartDesc());
-		int stride = 2;
-		if (early) {
-			for (int part = 0; part < split; ++part) {
-				gsb::KPartDesc& pd = e->hParts[static_cast<size_t>(part)];
-				pd.begin = static_cast<int>(e->hFitOrder.size());
-				pd.n0 = pd.n1 = pd.pad = 0;
-				for (int phase = 0; phase < 2; ++phase) {
-					for (int f = 0; f < nfits; ++f) {
-						const int comp = e->kFitComp[static_cast<size_t>(f)];
-						if (static_cast<long long>(comp) * split / e->kComponents != part || e->kFitPhase[static_cast<size_t>(f)] != phase) continue;
-						e->hFitOrder.push_back(f);
-						(phase == 0 ? pd.n0 : pd.n1) += 1;
-					}
+	if (e->kSchedNf != nf) {
+		for (int i = 0; i <= gsb_engine::kMaxSplit; ++i) e->kSchedules[i].ready = false;
+		e->kSchedNf = nf;
+	}
+	gsb_engine::KSchedule& sc = e->kSchedules[split];
+	if (sc.ready) return sc;
+	bool anyOuterOnly = false;
+	for (int f = 0; f < nfits; ++f) anyOuterOnly = anyOuterOnly || e->kFitPhase[static_cast<size_t>(f)] == 1;
+	// whole components per CTA only when they deal out evenly: an uneven deal costs more passes on the longest CTA than
+	// stopping the outer fits early saves (measured, profiles/split_probe.py: 10 replications over 4 CTAs)
+	sc.early = !e->env.noEarlyStop && anyOuterOnly && e->kComponents >= split && e->kComponents % split == 0 && nfits < (1 << 24);
+	std::vector<int> order;
+	std::vector<gsb::KPartDesc> parts(static_cast<size_t>(split), gsb::KPartDesc());
+	if (sc.early) {
+		for (int part = 0; part < split; ++part) {
+			gsb::KPartDesc& pd = parts[static_cast<size_t>(part)];
+			pd.begin = static_cast<int>(order.size());
+			pd.n0 = pd.n1 = pd.pad = 0;
+			for (int phase = 0; phase < 2; ++phase) {
+				for (int f = 0; f < nfits; ++f) {
+					const int comp = e->kFitComp[static_cast<size_t>(f)];
+					if (static_cast<long long>(comp) * split / e->kComponents != part || e->kFitPhase[static_cast<size_t>(f)] != phase) continue;
+					order.push_back(f);
+					(phase == 0 ? pd.n0 : pd.n1) += 1;
 				}
 			}
-		} else {
-			const int passes = (nfits + nf - 1) / nf, perPart = (passes + split - 1) / split;
-			for (int f = 0; f < nfits; ++f) e->hFitOrder.push_back(f);
-			for (int part = 0; part < split; ++part) {
-				gsb::KPartDesc& pd = e->hParts[static_cast<size_t>(part)];
-				pd.begin = std::min(nfits, part * perPart * nf);
-				pd.n0 = std::min(nfits, (part + 1) * perPart * nf) - pd.begin;
-				pd.n1 = pd.pad = 0;
-			}
 		}
-		// per CTA: one schedule word per fit of its part, and as many again to stage the sort
-		for (int part = 0; part < split; ++part) stride = std::max(stride, roundUp(e->hParts[static_cast<size_t>(part)].n0 + e->hParts[static_cast<size_t>(part)].n1, 2));
-		GSB_CUDA(cudaStreamSynchronize(e->stream)); // no launch in flight reads the previous schedule
-		e->kFitOrder.upload(e->hFitOrder, e->stream);
-		e->kParts.upload(e->hParts, e->stream);
-		GSB_CUDA(cudaStreamSynchronize(e->stream));
-		e->kSchedSplit = split;
-		e->kSchedNf = nf;
-		e->kSchedStride = stride;
-		e->kSchedEarly = early;
+	} else {
+		const int passes = (nfits + nf - 1) / nf, perPart = (passes + split - 1) / split;
+		for (int f = 0; f < nfits; ++f) order.push_back(f);
+		for (int part = 0; part < split; ++part) {
+			gsb::KPartDesc& pd = parts[static_cast<size_t>(part)];
+			pd.begin = std::min(nfits, part * perPart * nf);
+			pd.n0 = std::min(nfits, (part + 1) * perPart * nf) - pd.begin;
+			pd.n1 = pd.pad = 0;
+		}
 	}
-	e->kSched.reserve(static_cast<size_t>(grid) * 2 * static_cast<size_t>(e->kSchedStride));
+	// per CTA: one schedule word per fit of its part, and as many again to stage the sort
+	sc.stride = 2;
+	for (int part = 0; part < split; ++part) sc.stride = std::max(sc.stride, roundUp(parts[static_cast<size_t>(part)].n0 + parts[static_cast<size_t>(part)].n1, 2));
+	GSB_CUDA(cudaStreamSynchronize(e->stream)); // no launch in flight reads a previous schedule
+	sc.fitOrder.upload(order, e->stream);
+	sc.parts.upload(parts, e->stream);
+	GSB_CUDA(cudaStreamSynchronize(e->stream)); // the host vectors go out of scope
+	sc.ready = true;
+	return sc;
 }
 
 // K1 per subset-size class, then K2 (or K3 for the LM evaluator); events ev[2..4] bracket them
@@ -1762,29 +1774,42 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				kp.bucketCount = 0;
 				for (size_t b = kspaceFirst; b < e->buckets.size(); ++b) kp.bucketCount += e->buckets[b].count;
 				kp.nfits = e->kspaceFits;
-				// CTAs per chromosome: every CTA builds its own K, and CTAs run in waves of one per SM.  Pick the split
-				// that minimises waves x (passes per CTA x pass time + K build time); measured (k-cycles, B200): a
-				// component of a pass ~6, its first scores ~6, K = Z Z' ~0.37 per column
+				// CTAs per chromosome: every CTA builds its own K, and CTAs run in waves of one per SM.  Whole waves of
+				// chromosomes get one CTA each; the chromosomes of the last, partial wave (all of a small population) are
+				// split over the number of CTAs that minimises waves x (passes per CTA x pass time + K build time) and
+				// come last in the grid.  Measured (k-cycles, B200): a component of a pass ~6, its first scores ~6,
+				// K = Z Z' ~0.37 per column.  GSB_KSPACE_SPLIT forces one split for every chromosome.
 				const int passes = (e->kspaceFits + kspaceNf - 1) / kspaceNf;
 				kp.nf = kspaceNf;
-				int split = env.kspaceSplit;
-				if (split <= 0) {
-					double kbar = 0.0;
-					for (int i = 0; i < kp.bucketCount; ++i) {
+				const int maxSplit = std::min(gsb_engine::kMaxSplit, passes);
+				if (env.kspaceSplit > 0) {
+					kp.fullCount = 0;
+					kp.tailSplit = std::max(1, std::min(env.kspaceSplit, maxSplit));
+				} else {
+					const int S = std::max(1, e->smCount);
+					kp.fullCount = kp.bucketCount / S * S;
+					const int tail = kp.bucketCount - kp.fullCount;
+					double kbar = 0.0; // mean subset size of the tail (the smallest subsets of the launch)
+					for (int i = 0; i < tail; ++i) {
 						const int c = e->hBucket.ptr[e->buckets[kspaceFirst].begin + i];
 						kbar += static_cast<double>(e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c]);
 					}
-					kbar /= std::max(1, kp.bucketCount);
+					kbar /= std::max(1, tail);
 					const double passTime = (6.0 * e->tableA + 6.0) * (kspaceNf / 8), buildTime = 0.37 * kbar;
 					double best = 0.0;
-					split = 1;
-					for (int sp = 1; sp <= std::min(8, passes); ++sp) {
-						const long long waves = (static_cast<long long>(kp.bucketCount) * sp + e->smCount - 1) / std::max(1, e->smCount);
-						const double t = static_cast<double>(waves) * (((passes + sp - 1) / sp) * passTime + buildTime);
-						if (sp == 1 || t < best * 0.98) { best = t; split = sp; }
+					kp.tailSplit = 1;
+					for (int sp = 1; sp <= maxSplit && tail > 0; ++sp) {
+						const long long waves = (static_cast<long long>(tail) * sp + S - 1) / S;
+						// passes of the longest part: whole dependency components (replications) per CTA when there are enough
+						int partPasses = (passes + sp - 1) / sp;
+						if (e->kComponents >= sp && e->kComponents % sp == 0 && !env.noEarlyStop) {
+							const int comps = e->kComponents / sp;
+							partPasses = (comps * ((e->kspaceFits + e->kComponents - 1) / e->kComponents) + kspaceNf - 1) / kspaceNf;
+						}
+						const double t = static_cast<double>(waves) * (partPasses * passTime + buildTime);
+						if (sp == 1 || t < best * 0.98) { best = t; kp.tailSplit = sp; }
 					}
 				}
-				kp.split = std::max(1, std::min(split, passes));
 				kp.n = e->n;
 				kp.n8 = roundUp(e->n, 8);
 				kp.ldz = e->ldz;
@@ -1795,13 +1820,17 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				kp.mse = e->dMse.ptr;
 				kp.ostat = e->dOstat.ptr;
 				kp.trace = e->traceBuf.ptr;
-				buildKspaceSchedule(e, kp.split, kp.nf, kp.bucketCount * kp.split);
-				kp.fitOrder = e->kFitOrder.ptr;
-				kp.parts = e->kParts.ptr;
+				gsb_engine::KSchedule& scTail = kspaceSchedule(e, kp.tailSplit, kp.nf);
+				gsb_engine::KSchedule& scFull = kspaceSchedule(e, 1, kp.nf);
+				kp.fitOrder = scTail.fitOrder.ptr;
+				kp.parts = scTail.parts.ptr;
+				kp.fitOrderFull = scFull.fitOrder.ptr;
+				kp.partsFull = scFull.parts.ptr;
 				kp.inner = std::max(1, e->plan.innerPerGroup);
 				kp.sdfact = e->shape.sdfact;
+				kp.schedStride = std::max(scTail.stride, scFull.stride);
+				e->kSched.reserve((static_cast<size_t>(kp.fullCount) + static_cast<size_t>(kp.bucketCount - kp.fullCount) * kp.tailSplit) * 2 * static_cast<size_t>(kp.schedStride));
 				kp.sched = e->kSched.ptr;
-				kp.schedStride = e->kSchedStride;
 				kp.products = e->kProducts.ptr;
 				GSB_CUDA(cudaMemsetAsync(e->kProducts.ptr, 0, sizeof(unsigned long long), launchStream));
 				GSB_CUDA(gsb::launchKspaceKernel(kp, launchStream, &ctas));
@@ -1813,7 +1842,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 					for (int i = 0; i < kp.bucketCount; ++i) {
 						const int c = e->hBucket.ptr[e->buckets[kspaceFirst].begin + i];
 						const int k = static_cast<int>(e->hOffsets.ptr[c + 1] - e->hOffsets.ptr[c]);
-						dmma += static_cast<double>(kp.split) * (nb * (nb + 1) / 2) * 4.0 * ((k + 3) / 4);
+						dmma += static_cast<double>(i < kp.bucketCount - kp.fullCount ? kp.tailSplit : 1) * (nb * (nb + 1) / 2) * 4.0 * ((k + 3) / 4);
 					}
 					e->timing.fit_tensor_gflop = dmma * 512.0 * 1e-9;
 				}
@@ -2076,6 +2105,9 @@ int gsb_evaluate_bitsets(gsb_engine* e, const uint64_t* bitsets, int32_t words_p
 	const int unused = words * 64 - e->p;
 	std::vector<uint32_t> idx, offsets(static_cast<size_t>(npop) + 1, 0u);
 	try {
+		size_t total = 0;
+		for (size_t w = 0; w < static_cast<size_t>(npop) * words; ++w) total += static_cast<size_t>(__builtin_popcountll(bitsets[w]));
+		idx.reserve(total + 1);
 		for (int c = 0; c < npop; ++c) {
 			const uint64_t* w = bitsets + static_cast<size_t>(c) * words;
 			for (int part = 0; part < words; ++part) {

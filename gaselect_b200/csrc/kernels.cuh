@@ -308,7 +308,8 @@ struct KParams {
 	const int* bucket;
 	int bucketCount;
 	int nfits;
-	int split;  // CTAs per chromosome (each builds K and takes a share of the passes of nf fits)
+	int fullCount; // the first fullCount chromosomes (largest first) run on one CTA each ...
+	int tailSplit; // ... the others on tailSplit CTAs each (every CTA builds K and takes a share of the fits)
 	int nf;     // fits per pass = warps per CTA: 8, or 16 (stored vectors in tensor memory)
 	int n, n8, ldz, p;
 	int maxNComp;
@@ -317,8 +318,10 @@ struct KParams {
 	double* mse;
 	double* ostat;
 	long long* trace; // optional (profiling): clock64() stamps of one CTA
-	const int* fitOrder;      // the order the fits are run in (indices into kfits), per part
-	const KPartDesc* parts;   // `split` entries
+	const int* fitOrder;      // the order the fits are run in (indices into kfits), per part, for tailSplit CTAs per chromosome
+	const KPartDesc* parts;   // tailSplit entries
+	const int* fitOrderFull;  // the same for one CTA per chromosome
+	const KPartDesc* partsFull;
 	int inner;                // I: inner folds per (replication, outer fold) of the MSEP table
 	double sdfact;            // of the one-SE rule (after division by sqrt(I))
 	uint32_t* sched;          // per CTA 2 x schedStride words: (components << 24 | fit) per slot of its passes, and the sort's staging

@@ -436,13 +436,13 @@ __device__ __forceinline__ void kspaceDeflate(KFitState<NF>& fs, const KCtx& cx,
 // (their global writes are visible CTA-wide after the barrier).  Slots [first, total) of the part's fit order are
 // outer-only fits: each gets the optNComp of its outer fold(s) (oneSeRule, the function K2 uses: the same decision to
 // the bit) and they are sorted, longest first, into sched[first ...) -- staged behind the schedule at sched + stride.
-__device__ __forceinline__ void kspaceRule(const KParams& prm, const KPartDesc& pd, uint32_t* sched, int first, int total, int chrom, int A,
+__device__ __forceinline__ void kspaceRule(const KParams& prm, const int* fitOrder, const KPartDesc& pd, uint32_t* sched, int first, int total, int chrom, int A,
                                         int tid, int nthreads) {
 	__syncthreads();
 	uint32_t* raw = sched + prm.schedStride;
 	const int rem = total - first;
 	for (int j = tid; j < rem; j += nthreads) {
-		const int fj = prm.fitOrder[pd.begin + first + j];
+		const int fj = fitOrder[pd.begin + first + j];
 		const int tb = prm.kfits[fj].taskBegin, ntk = prm.kfits[fj].ntasks;
 		int nc = 1;
 		for (int tk = 0; tk < ntk; ++tk) {
@@ -484,16 +484,31 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	double* __restrict__ ys = smem + cv.ys;
 	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(TA);
 
-	// largest subsets first (the bucket list is ascending): their K costs the most
-	const int ci = prm.bucketCount - 1 - static_cast<int>(blockIdx.x % static_cast<unsigned>(prm.bucketCount));
-	const int part = static_cast<int>(blockIdx.x / static_cast<unsigned>(prm.bucketCount));
-	const int chrom = prm.bucket[ci];
+	// Largest subsets first (the bucket list is ascending): their K costs the most.  The first fullCount chromosomes get
+	// one CTA each (whole waves of one CTA per SM); the rest -- the last, partial wave, or all of a small population --
+	// are split over tailSplit CTAs each, which come last in the grid so that they fill the SMs as those run dry.
+	int cj, part;
+	const KPartDesc* partTab;
+	const int* fitOrder;
+	if (static_cast<int>(blockIdx.x) < prm.fullCount) {
+		cj = static_cast<int>(blockIdx.x);
+		part = 0;
+		partTab = prm.partsFull;
+		fitOrder = prm.fitOrderFull;
+	} else {
+		const int t = static_cast<int>(blockIdx.x) - prm.fullCount;
+		cj = prm.fullCount + t / prm.tailSplit;
+		part = t % prm.tailSplit;
+		partTab = prm.parts;
+		fitOrder = prm.fitOrder;
+	}
+	const int chrom = prm.bucket[prm.bucketCount - 1 - cj];
 	const uint32_t selBegin = prm.offsets[chrom];
 	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
 	const int A = min(prm.maxNComp, k);
 	const double nanv = __longlong_as_double(0x7ff8000000000000LL);
 	// this CTA's fits: fitOrder[pd.begin ...), the first n0 with every component, then n1 that only predict outer folds
-	const KPartDesc pd = prm.parts[part];
+	const KPartDesc pd = partTab[part];
 	const int total = pd.n0 + pd.n1;
 	if (total == 0) return;
 
@@ -615,7 +630,7 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	// by kspaceRule below
 	uint32_t* sched = prm.sched + static_cast<size_t>(blockIdx.x) * 2 * prm.schedStride;
 	for (int j = tid; j < min(total, ruleAt * kKNF); j += kKThreads) {
-		sched[j] = (static_cast<uint32_t>(A) << 24) | static_cast<uint32_t>(prm.fitOrder[pd.begin + j]);
+		sched[j] = (static_cast<uint32_t>(A) << 24) | static_cast<uint32_t>(fitOrder[pd.begin + j]);
 	}
 	unsigned long long nprod = 0ull;
 	double* __restrict__ taW = TA + warp * ldk;
@@ -623,7 +638,7 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	__syncthreads();
 #pragma unroll 1
 	for (int pass = 0; pass < passes; ++pass) {
-		if (pass == ruleAt) kspaceRule(prm, pd, sched, ruleAt * kKNF, total, chrom, A, tid, kKThreads);
+		if (pass == ruleAt) kspaceRule(prm, fitOrder, pd, sched, ruleAt * kKNF, total, chrom, A, tid, kKThreads);
 		const int slot = min(pass * kKNF + warp, total - 1);
 		const bool fitActive = pass * kKNF + warp < total;
 		const int fi = static_cast<int>(sched[slot] & 0xffffffu);
@@ -742,9 +757,9 @@ static cudaError_t launchKspaceOne(const KParams& prm, int bytes, long long grid
 
 cudaError_t launchKspaceKernel(const KParams& prm, cudaStream_t stream, long long* ctas) {
 	const int bytes = kspaceKernelSharedBytes(prm.n, prm.nf);
-	const long long grid = static_cast<long long>(prm.bucketCount) * prm.split;
-	if (grid <= 0) return cudaSuccess;
-	if (grid > 2147483647LL || prm.split < 1 || (prm.nf != 8 && prm.nf != 16)) return cudaErrorInvalidConfiguration;
+	const long long grid = static_cast<long long>(prm.fullCount) + static_cast<long long>(prm.bucketCount - prm.fullCount) * prm.tailSplit;
+	if (prm.bucketCount <= 0) return cudaSuccess;
+	if (grid > 2147483647LL || prm.tailSplit < 1 || prm.fullCount < 0 || prm.fullCount > prm.bucketCount || (prm.nf != 8 && prm.nf != 16)) return cudaErrorInvalidConfiguration;
 	const bool tr = prm.trace != nullptr;
 	const cudaError_t err = prm.nf == 8 ? (tr ? launchKspaceOne<8, true>(prm, bytes, grid, stream) : launchKspaceOne<8, false>(prm, bytes, grid, stream))
 	                                    : (tr ? launchKspaceOne<16, true>(prm, bytes, grid, stream) : launchKspaceOne<16, false>(prm, bytes, grid, stream));

@@ -4,17 +4,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <utility>
 
 namespace {
 
-std::string keyOf(const arma::uvec& cols) {
-	std::string key(cols.n_elem * sizeof(uint32_t), '\0');
-	for (arma::uword i = 0; i < cols.n_elem; ++i) {
-		const uint32_t v = static_cast<uint32_t>(cols[i]);
-		std::memcpy(&key[i * sizeof(uint32_t)], &v, sizeof(uint32_t));
-	}
-	return key;
+// exact key: the bytes of the chromosome's bit parts (equal parts <=> equal chromosomes, src/Chromosome.cpp:440-442)
+std::string keyOf(const std::vector<IntChromosome>& parts) {
+	return std::string(reinterpret_cast<const char*>(parts.data()), parts.size() * sizeof(IntChromosome));
 }
 
 } // namespace
@@ -37,9 +34,9 @@ BatchedPopulation::~BatchedPopulation() {
 	for (size_t i = 0; i < this->slots.size(); ++i) delete this->slots[i];
 }
 
-BatchedPopulation::Lookup BatchedPopulation::lookup(Chromosome& ch) {
-	const arma::uvec cols = ch.toColumnSubset();
-	const std::string key = keyOf(cols);
+BatchedPopulation::Lookup BatchedPopulation::lookup(Chromosome& ch, size_t* pendingIndex) {
+	const std::vector<IntChromosome>& parts = gsb_host::partsOf(ch);
+	std::string key = keyOf(parts);
 	std::unordered_map<std::string, Entry>::const_iterator hit = this->cache.find(key);
 	if (hit != this->cache.end()) {
 		++this->counters.cacheHits;
@@ -47,28 +44,64 @@ BatchedPopulation::Lookup BatchedPopulation::lookup(Chromosome& ch) {
 		ch.setFitness(hit->second.fitness);
 		return HIT_OK;
 	}
-	if (this->pendingSet.find(key) == this->pendingSet.end()) {
-		this->pendingSet.emplace(key, 1);
-		this->pendingKeys.push_back(key);
-		this->pending.push_back(cols);
+	std::unordered_map<std::string, size_t>::const_iterator known = this->pendingSet.find(key);
+	size_t index;
+	if (known == this->pendingSet.end()) {
+		index = this->pendingKeys.size();
+		this->words = parts.size();
+		this->pendingSet.emplace(key, index);
+		this->pendingKeys.push_back(std::move(key));
+		this->pendingParts.insert(this->pendingParts.end(), parts.begin(), parts.end());
+	} else {
+		index = known->second;
 	}
-	ch.setFitness(0.0); // provisional: this pass will be replayed
+	if (pendingIndex) *pendingIndex = index;
+	ch.setFitness(0.0); // provisional: confirmed or replayed after the engine call
 	return MISS;
 }
 
 void BatchedPopulation::flush() {
-	std::vector<double> fitness;
-	std::vector<int> status;
-	this->gpu.evaluateBatch(this->pending, fitness, status);
-	for (size_t i = 0; i < this->pending.size(); ++i) {
-		Entry e = {fitness[i], status[i]};
-		this->cache.emplace(this->pendingKeys[i], e);
+	const size_t count = this->pendingKeys.size();
+	this->gpu.evaluateBitsets(this->pendingParts.data(), static_cast<int>(this->words), count, this->lastFitness, this->lastStatus);
+	for (size_t i = 0; i < count; ++i) {
+		Entry e = {this->lastFitness[i], this->lastStatus[i]};
+		this->cache.emplace(std::move(this->pendingKeys[i]), e);
 	}
-	this->counters.engineEvaluations += this->pending.size();
+	this->counters.engineEvaluations += count;
 	++this->counters.engineCalls;
-	this->pending.clear();
+	this->pendingParts.clear();
 	this->pendingKeys.clear();
 	this->pendingSet.clear();
+}
+
+// After a flush: did every decision this pass took on a yet unknown fitness turn out right?  If so the chromosomes get
+// their fitness and the pass stands (the caller redoes the fitness-dependent bookkeeping); if not the caller replays.
+bool BatchedPopulation::confirmProvisional() {
+	for (size_t i = 0; i < this->provisional.size(); ++i) {
+		const Provisional& d = this->provisional[i];
+		if (this->lastStatus[d.pendingIndex] != 0) return false; // EvaluatorException: the slot would have been drawn again
+		if (!d.forced && !(this->lastFitness[d.pendingIndex] > d.cutoff)) return false; // the child would have been rejected
+	}
+	for (size_t i = 0; i < this->provisional.size(); ++i) {
+		this->provisional[i].ch->setFitness(this->lastFitness[this->provisional[i].pendingIndex]);
+	}
+	++this->counters.confirmed;
+	return true;
+}
+
+// snapshot of the generation being built, reusing the storage of the previous one (no allocation per chromosome)
+void BatchedPopulation::snapshotSlots() {
+	if (this->slotsBefore.size() != this->slots.size()) {
+		this->slotsBefore.clear();
+		this->slotsBefore.reserve(this->slots.size());
+		for (size_t i = 0; i < this->slots.size(); ++i) this->slotsBefore.push_back(*this->slots[i]);
+	} else {
+		for (size_t i = 0; i < this->slots.size(); ++i) this->slotsBefore[i] = *this->slots[i];
+	}
+}
+
+void BatchedPopulation::restoreSlots() {
+	for (size_t i = 0; i < this->slots.size(); ++i) *this->slots[i] = this->slotsBefore[i];
 }
 
 // One pass over the initial population (src/SingleThreadPopulation.cpp:73-104).
@@ -79,11 +112,17 @@ void BatchedPopulation::generateInitial(LoopState& st) {
 		for (size_t i = 0; i < this->slots.size() && !known; ++i) known = (*this->slots[i] == *candidate);
 		bool keep = false;
 		if (!known) {
-			const Lookup res = this->lookup(*candidate);
+			size_t pendingIndex = 0;
+			const Lookup res = this->lookup(*candidate, &pendingIndex);
 			keep = res != HIT_FAILED;
 			if (keep) {
+				if (res == MISS) {
+					const Provisional d = {candidate, pendingIndex, -std::numeric_limits<double>::infinity(), false};
+					this->provisional.push_back(d);
+				}
 				if (candidate->getFitness() < st.minFitness) st.minFitness = candidate->getFitness();
 				this->addChromosomeToElite(*candidate);
+				this->acceptedOrder.push_back(candidate);
 			}
 		}
 		if (keep) this->slots.push_back(candidate); else delete candidate;
@@ -120,12 +159,18 @@ void BatchedPopulation::mateGeneration(LoopState& st) {
 			if (dup && !(++tries > this->ctrl.maxDuplicateEliminationTries)) continue; // try this slot again
 			if (dup) child.randomlyReset(st.rng, st.shuffledSet); // too many duplicate tries: random restart
 			tries = 0;
-			const Lookup res = this->lookup(child);
+			size_t pendingIndex = 0;
+			const Lookup res = this->lookup(child, &pendingIndex);
 			if (res == HIT_FAILED) continue; // EvaluatorException: the slot is drawn again
 			const bool accepted = (res == MISS) || (child.getFitness() > cutoff) || (discarded > maxDiscarded);
 			if (accepted) {
+				if (res == MISS) {
+					const Provisional d = {&child, pendingIndex, cutoff, discarded > maxDiscarded};
+					this->provisional.push_back(d);
+				}
 				if (child.getFitness() < st.minFitness) st.minFitness = child.getFitness();
 				this->addChromosomeToElite(child);
+				this->acceptedOrder.push_back(&child);
 				if (which == 0) ++front; else ++back;
 				discarded = 0;
 			} else {
@@ -150,37 +195,54 @@ void BatchedPopulation::runSingle() {
 		const double minEliteBefore = this->minEliteFitness;
 		for (;;) {
 			++this->counters.passes;
+			this->provisional.clear();
+			this->acceptedOrder.clear();
 			this->generateInitial(st);
-			if (this->pending.empty()) break;
+			if (this->pendingKeys.empty()) break;
 			this->flush();
+			this->elite = eliteBefore;
+			this->minEliteFitness = minEliteBefore;
+			if (this->confirmProvisional()) { // the pass stands: redo what depended on the fitness, in the same order
+				st.minFitness = before.minFitness;
+				for (size_t i = 0; i < this->acceptedOrder.size(); ++i) {
+					if (this->acceptedOrder[i]->getFitness() < st.minFitness) st.minFitness = this->acceptedOrder[i]->getFitness();
+					this->addChromosomeToElite(*this->acceptedOrder[i]);
+				}
+				break;
+			}
 			for (size_t i = 0; i < this->slots.size(); ++i) delete this->slots[i];
 			this->slots.clear();
 			st = before;
-			this->elite = eliteBefore;
-			this->minEliteFitness = minEliteBefore;
 		}
 	}
 	this->initCurrentGeneration(st.shuffledSet, st.rng);
 	st.sumFitness = this->updateCurrentGeneration(this->slots, st.minFitness, true);
 
 	// ---- generations ------------------------------------------------------------------------------------
-	std::vector<Chromosome> slotsBefore;
 	for (int g = this->ctrl.numGenerations; g > 0 && !this->interrupted; --g) {
 		const LoopState before = st;
 		const SortedChromosomes eliteBefore = this->elite;
 		const double minEliteBefore = this->minEliteFitness;
-		slotsBefore.clear();
-		slotsBefore.reserve(this->slots.size());
-		for (size_t i = 0; i < this->slots.size(); ++i) slotsBefore.push_back(*this->slots[i]);
+		this->snapshotSlots();
 		for (;;) {
 			++this->counters.passes;
+			this->provisional.clear();
+			this->acceptedOrder.clear();
 			this->mateGeneration(st);
-			if (this->pending.empty()) break;
+			if (this->pendingKeys.empty()) break;
 			this->flush();
-			st = before;
 			this->elite = eliteBefore;
 			this->minEliteFitness = minEliteBefore;
-			for (size_t i = 0; i < this->slots.size(); ++i) *this->slots[i] = slotsBefore[i];
+			if (this->confirmProvisional()) { // the pass stands: redo what depended on the fitness, in the same order
+				st.minFitness = 0.0;
+				for (size_t i = 0; i < this->acceptedOrder.size(); ++i) {
+					if (this->acceptedOrder[i]->getFitness() < st.minFitness) st.minFitness = this->acceptedOrder[i]->getFitness();
+					this->addChromosomeToElite(*this->acceptedOrder[i]);
+				}
+				break;
+			}
+			st = before;
+			this->restoreSlots();
 		}
 		st.sumFitness = this->updateCurrentGeneration(this->slots, st.minFitness, false);
 	}
@@ -204,7 +266,13 @@ void BatchedPopulation::generateInitialSlice(Stream& w) {
 		Chromosome* candidate = new Chromosome(this->ctrl, w.shuffledSet, w.rng);
 		bool known = false;
 		for (uint16_t i = 0; i < filled && !known; ++i) known = (*this->slots[w.offset + i] == *candidate);
-		if (!known && this->lookup(*candidate) != HIT_FAILED) {
+		size_t pendingIndex = 0;
+		const Lookup res = known ? HIT_FAILED : this->lookup(*candidate, &pendingIndex);
+		if (!known && res != HIT_FAILED) {
+			if (res == MISS) {
+				const Provisional d = {candidate, pendingIndex, -std::numeric_limits<double>::infinity(), false};
+				this->provisional.push_back(d);
+			}
 			this->slots[w.offset + filled] = candidate;
 			++filled;
 		} else {
@@ -245,9 +313,14 @@ void BatchedPopulation::mateSlice(Stream& w, double sumFitness) {
 			if (dup && !(++tries[which] > this->ctrl.maxDuplicateEliminationTries)) continue;
 			if (dup) child.randomlyReset(w.rng, w.shuffledSet);
 			tries[which] = 0;
-			const Lookup res = this->lookup(child);
+			size_t pendingIndex = 0;
+			const Lookup res = this->lookup(child, &pendingIndex);
 			if (res == HIT_FAILED) continue; // EvaluatorException: the slot is drawn again
 			bool accepted = (res == MISS) || (child.getFitness() > cutoff);
+			if (res == MISS) { // stands iff fitness > cutoff (a rejection would also have moved the discarded counter)
+				const Provisional d = {&child, pendingIndex, cutoff, false};
+				this->provisional.push_back(d);
+			}
 			if (!accepted && ++discarded[which] > maxDiscarded) { // "the algorithm may be stuck": keep the child
 				discarded[which] = 0;
 				accepted = true;
@@ -298,9 +371,11 @@ void BatchedPopulation::runVirtualThreads() {
 		const std::vector<Stream> before = workers;
 		for (;;) {
 			++this->counters.passes;
+			this->provisional.clear();
 			for (size_t t = 0; t < workers.size(); ++t) this->generateInitialSlice(workers[t]);
-			if (this->pending.empty()) break;
+			if (this->pendingKeys.empty()) break;
 			this->flush();
+			if (this->confirmProvisional()) break; // nothing in a worker's loop depends on the fitness but these decisions
 			for (size_t i = 0; i < this->slots.size(); ++i) { delete this->slots[i]; this->slots[i] = nullptr; }
 			workers = before;
 		}
@@ -309,19 +384,18 @@ void BatchedPopulation::runVirtualThreads() {
 	double sumFitness = this->updateCurrentGeneration(this->slots, minFitnessOfSlots(), true, true);
 
 	// ---- generations ------------------------------------------------------------------------------------------
-	std::vector<Chromosome> slotsBefore;
 	for (int g = this->ctrl.numGenerations; g > 0 && !this->interrupted; --g) {
 		const std::vector<Stream> before = workers;
-		slotsBefore.clear();
-		slotsBefore.reserve(this->slots.size());
-		for (size_t i = 0; i < this->slots.size(); ++i) slotsBefore.push_back(*this->slots[i]);
+		this->snapshotSlots();
 		for (;;) {
 			++this->counters.passes;
+			this->provisional.clear();
 			for (size_t t = 0; t < workers.size(); ++t) this->mateSlice(workers[t], sumFitness);
-			if (this->pending.empty()) break;
+			if (this->pendingKeys.empty()) break;
 			this->flush();
+			if (this->confirmProvisional()) break;
 			workers = before;
-			for (size_t i = 0; i < this->slots.size(); ++i) *this->slots[i] = slotsBefore[i];
+			this->restoreSlots();
 		}
 		sumFitness = this->updateCurrentGeneration(this->slots, minFitnessOfSlots(), false, true);
 	}

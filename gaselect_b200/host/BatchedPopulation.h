@@ -14,9 +14,13 @@
 //   1. snapshot the generation's state (RNG, ShuffledSet, child slots, elite, counters);
 //   2. run the generation against the fitness cache; a chromosome that is not cached yet is recorded
 //      and provisionally treated as accepted;
-//   3. if anything was recorded: evaluate all of it in one engine call, restore the snapshot, go to 2;
+//   3. if anything was recorded: evaluate all of it in one engine call.  Every provisional decision is then checked
+//      against the real fitness (accepted iff fitness > cutoff, no EvaluatorException): when all of them stand, the
+//      speculative pass WAS the reference's generation up to the fitness-dependent bookkeeping (child fitness, the
+//      generation minimum, the elite insertions), which is redone in the recorded order -- no replay.  Otherwise the
+//      snapshot is restored and the pass runs again against the now larger cache (go to 2);
 //   4. a pass without a miss IS the reference's generation (fitness is a pure function of the subset).
-// At gaselect's defaults no child is rejected, so every generation costs one engine call.
+// At gaselect's defaults no child is rejected, so every generation costs one engine call and one host pass.
 //
 // Compiled inside the gaselect package next to the reference sources (it includes the package's own
 // Population.h); selected at src/GenAlg.cpp:173-181 in place of SingleThreadPopulation.  See INTEGRATION.md.
@@ -29,6 +33,7 @@
 
 #include "Population.h" // the reference's base class, on the package's include path
 
+#include "ChromosomeBits.h"
 #include "GpuEvaluator.h"
 
 class BatchedPopulation : public Population {
@@ -41,6 +46,7 @@ public:
 	// bookkeeping for benchmarks: chromosomes scored by the engine, engine calls, replayed passes
 	struct Stats {
 		unsigned long long engineEvaluations = 0, engineCalls = 0, passes = 0, cacheHits = 0;
+		unsigned long long confirmed = 0; // speculative passes whose every provisional decision stood (no replay)
 	};
 	const Stats& stats() const { return this->counters; }
 
@@ -53,8 +59,19 @@ private:
 	struct LoopState; // everything a generation mutates outside the base class
 	struct Stream;    // one (virtual) worker of the multi-threaded driver
 
-	Lookup lookup(Chromosome& ch);
+	// a decision taken on a chromosome whose fitness was not known yet
+	struct Provisional {
+		Chromosome* ch;
+		size_t pendingIndex; // into pending / lastFitness / lastStatus
+		double cutoff;       // the decision stands iff fitness > cutoff ...
+		bool forced;         // ... or the child was kept regardless (too many discarded)
+	};
+
+	Lookup lookup(Chromosome& ch, size_t* pendingIndex = nullptr);
 	void flush();
+	bool confirmProvisional();
+	void snapshotSlots();
+	void restoreSlots();
 	void generateInitial(LoopState& st);
 	void mateGeneration(LoopState& st);
 	void runSingle();
@@ -64,11 +81,18 @@ private:
 	bool pollInterrupt() { return this->interruptCheck != nullptr && this->interruptCheck(); }
 
 	GpuEvaluator& gpu;
+	// exact keys: the bytes of a chromosome's bit parts (ChromosomeBits.h); the parts also go to the engine as they are
 	std::unordered_map<std::string, Entry> cache;
-	std::vector<arma::uvec> pending;
+	std::vector<uint64_t> pendingParts;                 // `words` parts per pending chromosome
 	std::vector<std::string> pendingKeys;
-	std::unordered_map<std::string, char> pendingSet;
+	std::unordered_map<std::string, size_t> pendingSet; // key -> index into pendingKeys / pendingParts
+	size_t words = 0;                                   // parts per chromosome: ceil(chromosomeSize / 64)
+	std::vector<double> lastFitness;                    // results of the most recent flush, by pending index
+	std::vector<int> lastStatus;
+	std::vector<Provisional> provisional;               // this pass's decisions on unknown fitness
+	std::vector<Chromosome*> acceptedOrder;             // single-thread driver: children in the order they were accepted
 	std::vector<Chromosome*> slots; // the generation being built (owned)
+	std::vector<Chromosome> slotsBefore; // snapshot of the slots (storage kept across generations)
 	bool (*interruptCheck)() = nullptr;
 	Stats counters;
 };

@@ -125,6 +125,19 @@ void GpuEvaluator::evaluateBatch(const std::vector<arma::uvec>& subsets, std::ve
 	status.assign(st.begin(), st.end());
 }
 
+void GpuEvaluator::evaluateBitsets(const uint64_t* parts, int words, size_t count, std::vector<double>& fitness, std::vector<int>& status) {
+	fitness.assign(count, 0.0);
+	std::vector<int32_t> st(count, 0);
+	if (count > 0) {
+		std::lock_guard<std::mutex> guard(engine->lock);
+		check(engine->handle, gsb_evaluate_bitsets(engine->handle, parts, words, static_cast<int32_t>(count), fitness.data(), st.data()));
+		for (size_t i = 0; i < count; ++i) {
+			if (st[i] == GSB_STATUS_FLAGGED) { st[i] = GSB_STATUS_OK; ++engine->flagged; }
+		}
+	}
+	status.assign(st.begin(), st.end());
+}
+
 size_t GpuEvaluator::flaggedCount() const {
 	std::lock_guard<std::mutex> guard(engine->lock);
 	return engine->flagged;

@@ -59,6 +59,9 @@ public:
 	// driver and the loop of src/GenAlg.cpp:312-325 use).  status[i] != 0 marks the subsets for
 	// which the reference would have thrown EvaluatorException.
 	void evaluateBatch(const std::vector<arma::uvec>& subsets, std::vector<double>& fitness, std::vector<int>& status);
+	// The same for chromosomes as they are stored: `count` chromosomes of `words` 64-bit parts each, in the layout of
+	// src/Chromosome.cpp:55-77,419-438 (gsb_evaluate_bitsets decodes it on the engine's side).
+	void evaluateBitsets(const uint64_t* parts, int words, size_t count, std::vector<double>& fitness, std::vector<int>& status);
 
 	// Evaluations (over all clones) whose one-SE rule met a near-tie (GSB_STATUS_FLAGGED, relative band 1e-9): their
 	// fitness was returned as usual; the reference, summing in another order, may have fitted another optNComp there.

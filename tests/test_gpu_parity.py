@@ -202,19 +202,45 @@ def test_cfg3_full_size_population_against_reference_build(engine, ref_lib):
     assert rel_err(fg[:120], fr).max() <= REL_TOL
 
 
-def test_cfg4_shape_properties(engine, oracle_lib):
-    """BASELINE config 4 shape (n=500, p=5000): a sample against the oracle plus properties."""
+def test_cfg4_shape_against_reference_build(engine, ref_lib):
+    """BASELINE config 4 shape (n=500, p=5000, 10 x 5/4 CV, <= 10 components): 96 subsets of 20...400 columns (SURVEY 8(d)'s
+    range: the shared-memory path, the spill path above 212 columns and the in-place path above 384) against the
+    reference's own code (oracle/_ref), plus order independence."""
     from gaselect_b200 import evaluators as E
     X, y = synth.nir_spectra(500, 5000, seed=778, noise=1e-2)
-    sv = oracle_lib.make_seedvec(123)
-    subsets = synth.random_subsets(5000, 96, 20, 200, seed=43)
+    sv = ref_lib.make_seedvec(123)
+    subsets = synth.random_subsets(5000, 88, 20, 400, seed=43) + [synth.random_subsets(5000, 1, k, k, seed=k)[0] for k in (20, 212, 213, 256, 300, 384, 385, 400)]
     kw = dict(numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)
     with E.PLSEvaluator(X, y, sv, **kw) as ev:
         fg, sg = ev.evaluate_population(subsets)
         fg2, _ = ev.evaluate_population(subsets[::-1])
-    assert (sg == 0).all() and (fg2[::-1] == fg).all() and (fg < 0).all()
-    fo, so = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets[:12], threads=8)
-    assert rel_err(fg[:12], fo).max() <= REL_TOL
+    assert len(subsets) == 96 and (sg == 0).all() and (fg2[::-1] == fg).all() and (fg < 0).all()
+    fr, sr = ref_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=16)
+    assert (sr == 0).all() and rel_err(fg, fr).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("rows", [150, 400])
+def test_prediction_in_the_fit_kernel_and_in_its_own_kernel_agree(engine, oracle_lib, rows):
+    """The per-fit path predicts the held-out rows either in the fit kernel (default for blocks of fewer than 64 rows) or
+    with one tensor-core product per (chromosome, held-out block) in predictBlocksKernel (default for larger blocks):
+    both forced in turn, against each other and the oracle."""
+    from gaselect_b200 import evaluators as E
+    from test_gpu_scores import forced
+    X, y = synth.nir_spectra(rows, 600, seed=rows)
+    sv = oracle_lib.make_seedvec(31)
+    kw = dict(numReplications=3, maxNComp=8, innerSegments=4, outerSegments=5)
+    subsets = synth.random_subsets(600, 40, 1, 120, seed=5)
+    res = []
+    for env in (dict(GSB_PREDICT="1", GSB_NO_PREDICT=None), dict(GSB_PREDICT=None, GSB_NO_PREDICT="1"), dict(GSB_PREDICT=None, GSB_NO_PREDICT=None)):
+        with forced(GSB_NO_KSPACE="1", GSB_NO_SCORES="1", **env):
+            with E.PLSEvaluator(X, y, sv, **kw) as ev:
+                res.append(ev.evaluate_population(subsets) + (ev.timing()["kernel_launches"],))
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=8)
+    assert res[0][2] > res[1][2]  # the separate prediction is one more launch per subset-size class
+    assert res[2][2] == (res[0][2] if rows >= 320 else res[1][2])  # the default by block size (rows / 5 >= 64)
+    for fit, status, _ in res:
+        assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL
+    assert rel_err(res[0][0], res[1][0]).max() <= 1e-9
 
 
 def test_subsets_beyond_shared_memory_spill_to_l2(engine, oracle_lib):
