@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libgaselect_b200.so")
 GSB_OK, GSB_ERR_INVALID_ARGUMENT, GSB_ERR_STATE, GSB_ERR_CUDA, GSB_ERR_MEMORY = range(5)
 EVAL_PLS_CV, EVAL_LM, EVAL_PLS_FIT = 1, 2, 3
 STAT = {"BIC": 0, "AIC": 1, "adjusted.r.squared": 2, "r.squared": 3}
-STATUS_OK, STATUS_EMPTY, STATUS_UNDERFLOW, STATUS_SINGULAR, STATUS_FLAGGED = range(5)
+STATUS_OK, STATUS_EMPTY, STATUS_UNDERFLOW, STATUS_SINGULAR, STATUS_FLAGGED, STATUS_RETRY = range(6)
 SEED_WORDS = 624
 MAX_DEVICES = 16
 
@@ -48,7 +48,7 @@ class Timing(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_double), ("fit_kernel_ms", C.c_double), ("reduce_kernel_ms", C.c_double),
         ("d2h_ms", C.c_double), ("total_ms", C.c_double), ("fit_ctas", C.c_int64), ("kernel_launches", C.c_int32),
-        ("reserved", C.c_int32), ("fit_tensor_gflop", C.c_double),
+        ("retries", C.c_int32), ("fit_tensor_gflop", C.c_double),
     ]
 
     def as_dict(self):

@@ -28,6 +28,10 @@ __global__ void __launch_bounds__(kReduceThreads) cvReduceKernel(const ReducePar
 		if (threadIdx.x == 0) { prm.fitness[chrom] = 0.0; prm.status[chrom] = 1; }
 		return;
 	}
+	if (prm.refit != nullptr && prm.refit[chrom] != 0) { // the kernel-space kernel declined it: to be scored again (engine.cpp, resolveRetries)
+		if (threadIdx.x == 0) { prm.fitness[chrom] = 0.0; prm.status[chrom] = kStatusRetry; }
+		return;
+	}
 	extern __shared__ double sh[]; // per group: sum e, sum e^2, flag
 	double* gE = sh;
 	double* gEE = sh + prm.groups;

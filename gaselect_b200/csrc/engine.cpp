@@ -116,7 +116,7 @@ int bucketCeil(int k) {
 
 // profiling / experiment switches, read from the environment ONCE per engine (ensureDevice)
 struct EnvFlags {
-	bool serial = false, noScores = false, noKspace = false, trace = false, noPredict = false, forcePredict = false, noTmem = false, noEarlyStop = false;
+	bool serial = false, noScores = false, noKspace = false, trace = false, noPredict = false, forcePredict = false, noEarlyStop = false;
 	int kspaceNf = 8, kspaceMinK = 40, kspaceSplit = 0, desync = 0;
 	int forcedNf = 0, forcedCs = 0, forcedVg = 0;
 };
@@ -299,6 +299,12 @@ struct gsb_engine {
 	DeviceArray<uint32_t> kSched;
 	DeviceArray<unsigned long long> kProducts;
 	bool kProductsPending = false;
+	// chromosomes K1k declines (ill-conditioned: it takes |v|^2 by subtraction) are scored again on the Gram-space kernel by
+	// a child engine without K1k, created the first time it is needed (resolveRetries)
+	DeviceArray<int> dRefit;
+	bool refitArmed = false;       // the most recent enqueue ran K1k: its results may hold kStatusRetry
+	gsb_engine* retryEngine = nullptr;
+	bool forceNoKspace = false;    // this IS such a child engine
 	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
 
@@ -338,7 +344,7 @@ void releaseDevice(gsb_engine* e) {
 	e->xz.release(); e->scoreScratch.release(); e->xReps.release(); e->xGroups8.release(); e->xGroups16.release(); e->xFits.release(); e->xTasks.release();
 	e->kFits.release(); e->kTasks.release();
 	for (int i = 0; i <= gsb_engine::kMaxSplit; ++i) { e->kSchedules[i].fitOrder.release(); e->kSchedules[i].parts.release(); e->kSchedules[i].ready = false; }
-	e->kSched.release(); e->kProducts.release();
+	e->kSched.release(); e->kProducts.release(); e->dRefit.release();
 	e->kSchedNf = -1;
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
@@ -390,9 +396,9 @@ void ensureDevice(gsb_engine* e) {
 	env.noKspace = std::getenv("GSB_NO_KSPACE") != nullptr;
 	env.trace = std::getenv("GSB_TRACE") != nullptr;
 	env.noEarlyStop = std::getenv("GSB_NO_EARLYSTOP") != nullptr; // outer-only fits run every component (the arrangement before ABI 4)
-	env.noTmem = std::getenv("GSB_TMEM") == nullptr;          // opt-in experiment: the fit's Gram rows in tensor memory (simpls_tmem.cu; measured slower)
 	env.noPredict = std::getenv("GSB_NO_PREDICT") != nullptr; // per-fit kernel predicts in place whatever the block size
 	env.forcePredict = std::getenv("GSB_PREDICT") != nullptr; // fit-only kernel + predictBlocksKernel whatever the block size
+	env.noKspace = env.noKspace || e->forceNoKspace;
 	if (const char* v = std::getenv("GSB_KSPACE_NF")) env.kspaceNf = std::atoi(v) == 16 ? 16 : 8;
 	if (const char* v = std::getenv("GSB_KSPACE_MINK")) env.kspaceMinK = std::atoi(v);
 	if (const char* v = std::getenv("GSB_KSPACE_SPLIT")) env.kspaceSplit = std::atoi(v);
@@ -1111,6 +1117,8 @@ std::string deriveShape(gsb_engine* e, std::vector<gsb::RowSet>& seg, const uint
 // Per batch: deal -> concurrent upload / kernels on every replica -> peer copies of the result vectors to the first
 // device -> one copy to pinned host memory -> un-permute into the caller's order.
 
+int resolveRetries(gsb_engine* e); // below, next to the download
+
 int failFrom(gsb_engine* e, int rc, const gsb_engine* child, int dev) {
 	char buf[768];
 	std::snprintf(buf, sizeof(buf), "device %d: %s", dev, child ? child->error.c_str() : "");
@@ -1262,6 +1270,15 @@ int multiDownload(gsb_engine* e, double* fitness, int32_t* status) {
 			if (r->npop == 0) continue;
 			GSB_CUDA(cudaSetDevice(e->cfg.devices[d]));
 			GSB_CUDA(cudaStreamSynchronize(r->stream));
+			if (r->refitArmed) { // chromosomes its kernel-space kernel declined: re-scored on that device before the gather
+				r->hStatus.reserve(static_cast<size_t>(r->npop) + 1);
+				r->hFitness.reserve(static_cast<size_t>(r->npop) + 1);
+				GSB_CUDA(cudaMemcpyAsync(r->hStatus.ptr, r->dStatus.ptr, static_cast<size_t>(r->npop) * sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+				GSB_CUDA(cudaStreamSynchronize(r->stream));
+				const int rc = resolveRetries(r);
+				if (rc != GSB_OK) return failFrom(e, rc, r, e->cfg.devices[d]);
+				e->timing.retries += r->timing.retries;
+			}
 		}
 		GSB_CUDA(cudaSetDevice(dev0));
 		if (!ms->stream) GSB_CUDA(cudaStreamCreateWithFlags(&ms->stream, cudaStreamNonBlocking));
@@ -1387,6 +1404,8 @@ void gsb_destroy(gsb_engine* e) {
 	}
 	for (size_t i = 0; i < e->replicas.size(); ++i) gsb_destroy(e->replicas[i]);
 	e->replicas.clear();
+	if (e->retryEngine) gsb_destroy(e->retryEngine);
+	e->retryEngine = nullptr;
 	if (e->deviceReady) cudaSetDevice(e->cfg.device);
 	releaseDevice(e);
 	delete e;
@@ -1714,6 +1733,8 @@ gsb_engine::KSchedule& kspaceSchedule(gsb_engine* e, int split, int nf) {
 // K1 per subset-size class, then K2 (or K3 for the LM evaluator); events ev[2..4] bracket them
 void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 		e->timing.fit_tensor_gflop = 0.0;
+		e->timing.retries = 0;
+		e->refitArmed = false;
 		GSB_CUDA(cudaEventRecord(e->ev[2], e->stream));
 		if (e->cfg.evaluator == GSB_EVAL_LM) {
 			// the reference's LMEvaluator scores an empty subset as the intercept-only model (src/LMEvaluator.cpp:27-67)
@@ -1832,6 +1853,10 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				e->kSched.reserve((static_cast<size_t>(kp.fullCount) + static_cast<size_t>(kp.bucketCount - kp.fullCount) * kp.tailSplit) * 2 * static_cast<size_t>(kp.schedStride));
 				kp.sched = e->kSched.ptr;
 				kp.products = e->kProducts.ptr;
+				e->dRefit.reserve(static_cast<size_t>(e->npop));
+				kp.refit = e->dRefit.ptr;
+				e->refitArmed = true;
+				GSB_CUDA(cudaMemsetAsync(e->dRefit.ptr, 0, static_cast<size_t>(e->npop) * sizeof(int), launchStream));
 				GSB_CUDA(cudaMemsetAsync(e->kProducts.ptr, 0, sizeof(unsigned long long), launchStream));
 				GSB_CUDA(gsb::launchKspaceKernel(kp, launchStream, &ctas));
 				++launches;
@@ -1925,11 +1950,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.coefScratch = e->coefScratch.ptr;
 				prm.coefOff = e->dCoefOff.ptr;
 				if (bk.split) {
-					if (!env.noTmem && gsb::tmemKernelServes(bk.kMax, e->tableA, e->smemLimit)) {
-						GSB_CUDA(gsb::launchTmemKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas)); // Gram in tensor memory
-					} else {
-						GSB_CUDA(gsb::launchFitOnlyKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas));
-					}
+					GSB_CUDA(gsb::launchFitOnlyKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas));
 					gsb::PredictParams pr;
 					pr.zpool = e->zpool.ptr;
 					pr.blocks = e->blocks.ptr;
@@ -1982,6 +2003,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			rp.gamma = e->cfg.evaluator == GSB_EVAL_PLS_CV ? e->cfg.complexity_penalty : 0.0;
 			rp.r2denom = e->r2denom;
 			rp.tieBand = e->cfg.tie_band == 0.0 ? 1e-9 : e->cfg.tie_band;
+			rp.refit = e->refitArmed ? e->dRefit.ptr : nullptr;
 			rp.fitness = e->dFitness.ptr;
 			rp.status = e->dStatus.ptr;
 			gsb::launchReduceKernel(rp, e->stream);
@@ -1989,6 +2011,60 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			++launches;
 			GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
 		}
+}
+
+// Chromosomes the kernel-space kernel declined (kStatusRetry in hStatus[0 .. npop)): scored again by a child engine that
+// has no K1k (the Gram-space kernel takes its norms from explicit vectors, like the reference); host AND device copies
+// of the results are patched.  Returns GSB_OK or the child's error.
+int resolveRetries(gsb_engine* e) {
+	std::vector<int> ids;
+	for (int c = 0; c < e->npop; ++c) if (e->hStatus.ptr[c] == gsb::kStatusRetry) ids.push_back(c);
+	if (ids.empty()) return GSB_OK;
+	if (!e->retryEngine) {
+		gsb_config one = e->cfg;
+		one.num_devices = 0;
+		gsb_engine* r = nullptr;
+		int rc = gsb_create(&r, &one);
+		if (rc != GSB_OK) return fail(e, rc, "retry engine: " + g_createError);
+		r->forceNoKspace = true;
+		rc = gsb_set_data(r, e->X.data(), e->y.data(), e->n, e->p);
+		if (rc == GSB_OK) { // adopt the parent's segmentation as it is
+			std::vector<uint32_t> rows, offs(1, 0u);
+			for (size_t v = 0; v < e->segmentation.size(); ++v) {
+				rows.insert(rows.end(), e->segmentation[v].begin(), e->segmentation[v].end());
+				offs.push_back(static_cast<uint32_t>(rows.size()));
+			}
+			rc = gsb_set_segmentation(r, rows.data(), offs.data(), static_cast<int32_t>(e->segmentation.size()));
+		}
+		if (rc != GSB_OK) {
+			const std::string msg = "retry engine: " + r->error;
+			gsb_destroy(r);
+			return fail(e, rc, msg);
+		}
+		e->retryEngine = r;
+	}
+	std::vector<uint32_t> idx, off(1, 0u);
+	for (size_t i = 0; i < ids.size(); ++i) {
+		const int c = ids[i];
+		idx.insert(idx.end(), e->hIdx.ptr + e->hOffsets.ptr[c], e->hIdx.ptr + e->hOffsets.ptr[c + 1]);
+		off.push_back(static_cast<uint32_t>(idx.size()));
+	}
+	if (idx.empty()) idx.push_back(0u);
+	std::vector<double> fit(ids.size(), 0.0);
+	std::vector<int32_t> st(ids.size(), 0);
+	const int rc = gsb_evaluate_indices(e->retryEngine, idx.data(), off.data(), static_cast<int32_t>(ids.size()), fit.data(), st.data());
+	if (rc != GSB_OK) return fail(e, rc, "retry engine: " + e->retryEngine->error);
+	GSB_CUDA(cudaSetDevice(e->cfg.device));
+	for (size_t i = 0; i < ids.size(); ++i) {
+		const int c = ids[i];
+		e->hFitness.ptr[c] = fit[i];
+		e->hStatus.ptr[c] = st[i];
+		GSB_CUDA(cudaMemcpyAsync(e->dFitness.ptr + c, e->hFitness.ptr + c, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+		GSB_CUDA(cudaMemcpyAsync(e->dStatus.ptr + c, e->hStatus.ptr + c, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+	}
+	GSB_CUDA(cudaStreamSynchronize(e->stream));
+	e->timing.retries = static_cast<int32_t>(ids.size());
+	return GSB_OK;
 }
 
 } // namespace
@@ -2066,6 +2142,10 @@ int gsb_population_download(gsb_engine* e, double* fitness, int32_t* status) {
 		GSB_CUDA(cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]));
 		e->timing.d2h_ms = ms;
 		e->timing.total_ms = e->timing.h2d_ms + e->timing.fit_kernel_ms + e->timing.reduce_kernel_ms + ms;
+		if (e->refitArmed) {
+			const int rc = resolveRetries(e);
+			if (rc != GSB_OK) return rc;
+		}
 		std::memcpy(fitness, e->hFitness.ptr, np * sizeof(double));
 		for (size_t i = 0; i < np; ++i) status[i] = e->hStatus.ptr[i];
 	} catch (const CudaFailure& f) {

@@ -1,4 +1,4 @@
-// fit_common.cuh -- device helpers shared by the Gram-space fit kernels (simpls_fit.cu, simpls_tmem.cu): warp / CTA
+// fit_common.cuh -- device helpers shared by the Gram-space fit kernels (simpls_fit.cu; profiles/experiments/simpls_tmem.cu): warp / CTA
 // reductions with bitwise-identical totals in every thread, cp.async, TMA bulk copies on an mbarrier.
 #ifndef GASELECT_B200_FIT_COMMON_CUH
 #define GASELECT_B200_FIT_COMMON_CUH

@@ -185,6 +185,7 @@ struct ReduceParams {
 	double gamma;
 	double r2denom;
 	double tieBand; // relative band of the near-tie flag (GSB_STATUS_FLAGGED); negative: off
+	const int* refit; // optional: chromosomes the kernel-space kernel wants re-scored (status kStatusRetry)
 	double* fitness;
 	int* status;
 };
@@ -327,7 +328,12 @@ struct KParams {
 	uint32_t* sched;          // per CTA 2 x schedStride words: (components << 24 | fit) per slot of its passes, and the sort's staging
 	int schedStride;
 	unsigned long long* products; // += column tiles x products this launch issued (FP64 tensor work actually done)
+	int* refit;                   // per chromosome: set when a fit lost orthogonality (v'v by subtraction) or seemed to underflow
 };
+
+// status K2 gives a chromosome the kernel-space kernel marked in KParams::refit (GSB_STATUS_RETRY of the C ABI): the
+// engine scores it again on the Gram-space kernel when the results are downloaded
+constexpr int kStatusRetry = 5;
 
 
 __host__ __device__ inline unsigned long long tri(unsigned long long i) { return i * (i + 1ull) / 2ull; }
@@ -368,8 +374,6 @@ int fitKernelMaxK(int A, int smemLimit);
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
 bool fitOnlyKernelServes(int kMax, int A, int smemLimit);
 cudaError_t launchFitOnlyKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
-bool tmemKernelServes(int kMax, int A, int smemLimit);
-cudaError_t launchTmemKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);
 int predictKernelLda(int maxBlockLd);
 cudaError_t launchPredictKernel(const PredictParams& prm, cudaStream_t stream, long long* ctas);
 int scoreKernelMaxK(int nr, int nf, int clusterSize, int vGlobal, int smemLimit);

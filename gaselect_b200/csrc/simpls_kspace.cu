@@ -202,6 +202,7 @@ struct KFitState {
 	double rrA, rrB;              // 1 / rows of the task
 	double rntr, syc;
 	bool under;
+	bool ill; // the orthogonalised loading lost (nearly) all of its norm: v'v by subtraction is not trustworthy
 };
 
 // statistic of one prediction task for component COMP from its residual sums (src/PLSEvaluator.cpp:266-268, 323-325)
@@ -358,7 +359,8 @@ __device__ __forceinline__ void kspaceDeflate(KFitState<NF>& fs, const KCtx& cx,
 		}
 	}
 	double cj[kKA];
-	double vv = __shfl_sync(0xffffffffu, tot, (JHI + 1) * LP), vv2 = 0.0;
+	const double vvRaw = __shfl_sync(0xffffffffu, tot, (JHI + 1) * LP); // |X'tc|^2 before the projections are taken off
+	double vv = vvRaw, vv2 = 0.0;
 	const double vs = __shfl_sync(0xffffffffu, tot, JHI * LP);
 #pragma unroll
 	for (int j = 0; j < JHI; ++j) {
@@ -368,6 +370,9 @@ __device__ __forceinline__ void kspaceDeflate(KFitState<NF>& fs, const KCtx& cx,
 		else vv = fma(-cj[j], cj[j], vv);
 	}
 	vv -= vv2;
+	// v'v comes from a subtraction on K = Z Z' (squared conditioning); the reference takes the norm of the explicit
+	// vector (src/PLSSimpls.cpp:57-63).  When next to nothing is left the chromosome goes to the Gram-space kernel.
+	fs.ill = fs.ill || !(vv > 1e-8 * vvRaw);
 	const double rvn = rsqrt(vv);
 	const double dd = vs * rvn * rvn; // v'S / v'v
 	double dsum[kKNS]; // sum_j (V_j'v) U_j
@@ -650,6 +655,7 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 		fs.trainBits = 0u; // bit u: the lane's row of slot u is a training row of the fit
 		fs.rowBits = 0u;   // bit u: the lane's row of slot u exists in shared memory
 		fs.under = false;
+		fs.ill = false;
 		fs.taskBitsA = 0u; fs.taskBitsB = 0u;
 		fs.kindA = fitActive ? fd.first[0].kind : -1;
 		fs.kindB = fitActive ? fd.first[1].kind : -1;
@@ -722,6 +728,9 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 			}
 			if (cx.tracing) GSB_KSTAMP();
 		}
+		// ill-conditioned (or apparently underflowing) here: the engine scores the chromosome again on the Gram-space
+		// kernel, which takes its norms from explicit vectors, before anyone sees the result
+		if ((fs.ill || fs.under) && fitActive && lane == 0 && prm.refit != nullptr) prm.refit[chrom] = 1;
 	}
 #undef GSB_KSTAMP
 	if (tid == 0 && prm.products != nullptr) atomicAdd(prm.products, nprod);

@@ -63,7 +63,12 @@ typedef enum gsb_status {
 	 * gsb_config.tie_band.  The reference, summing in another order, may take that comparison the other way and fit a
 	 * different optNComp (moves the fitness by O(1e-2)); a host that needs the reference's exact choice re-scores the
 	 * flagged chromosomes there.  The wrappers return the fitness and count the flag; they do not throw. */
-	GSB_STATUS_FLAGGED = 4
+	GSB_STATUS_FLAGGED = 4,
+	/* Transient, never returned by gsb_evaluate_* / gsb_population_download: the kernel-space kernel found the chromosome
+	 * ill-conditioned (it takes |v|^2 by subtraction on K = Z Z') and left it to the Gram-space kernel; the download
+	 * re-scores such chromosomes before it returns (gsb_timing.retries counts them).  Only a caller that reads the
+	 * device buffers of gsb_population_device_results itself can see it. */
+	GSB_STATUS_RETRY = 5
 } gsb_status;
 
 typedef enum gsb_error {
@@ -132,7 +137,7 @@ typedef struct gsb_timing {
 	double total_ms;
 	int64_t fit_ctas;         /* CTAs launched by K1 */
 	int32_t kernel_launches;  /* kernels launched by the call */
-	int32_t reserved;
+	int32_t retries;          /* chromosomes the download re-scored on the Gram-space kernel (GSB_STATUS_RETRY) */
 	double fit_tensor_gflop;  /* FP64 tensor-core work of K1 (kernel-space kernel): DMMA.8x8x4 issued x 512 FLOP, from
 	                             the launch geometry (passes x products x tiles, plus the K = Z Z' builds) */
 } gsb_timing;

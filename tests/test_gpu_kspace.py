@@ -201,3 +201,34 @@ def test_near_tie_flag(engine, oracle_lib):
     with E.BICEvaluator(X, y, sv, numSegments=5, maxNComp=6) as ev:
         f0, s0 = ev.evaluate_population(subsets)
     assert (fb == f0).all() and (s0 == 0).all() and (sb == 4).any()
+
+
+def test_ill_conditioned_subsets_are_rescored_on_the_gram_space_kernel(engine, oracle_lib):
+    """K1k takes |v|^2 of an orthogonalised loading by subtraction on K = Z Z'; the reference takes the norm of the
+    explicit vector (src/PLSSimpls.cpp:57-63).  For nearly collinear columns the subtraction leaves nothing: the kernel
+    marks the chromosome (GSB_STATUS_RETRY), and the download has it scored again by the Gram-space kernel -- no
+    chromosome is reported as an underflow that the reference scores; the result is the per-fit path's to the bit."""
+    from gaselect_b200 import evaluators as E
+    rng = np.random.default_rng(4)
+    X, y = synth.nir_spectra(90, 300, seed=8)
+    X = X.copy()
+    for j in range(0, 96, 8):  # groups of eight columns that agree to 1e-7: a subset of 48 of them has rank 6 (+ 1e-7), ten components
+        for d in range(1, 8):
+            X[:, j + d] = X[:, j] * (1.0 + 1e-7 * rng.standard_normal(90))
+    sv = oracle_lib.make_seedvec(21)
+    kw = dict(numReplications=2, maxNComp=10, innerSegments=3, outerSegments=3)
+    subsets = [np.arange(0, 48, dtype=np.uint32), np.arange(48, 96, dtype=np.uint32)] + synth.random_subsets(300, 10, 45, 120, seed=6)
+    subsets = [s if i < 2 else s[s >= 96] for i, s in enumerate(subsets)]
+    with forced(GSB_NO_KSPACE=None, GSB_KSPACE_MINK=None):
+        with E.PLSEvaluator(X, y, sv, **kw) as ev:
+            f1, s1 = ev.evaluate_population(subsets)
+            retries = ev.timing()["retries"]
+            bits, _ = ev.evaluate_population(subsets)
+    with forced(GSB_NO_KSPACE="1", GSB_NO_SCORES="1"):
+        with E.PLSEvaluator(X, y, sv, **kw) as ev:
+            f0, s0 = ev.evaluate_population(subsets)
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=4)
+    assert retries == 2, retries                        # the collinear subsets were declined, the ordinary ones were not
+    assert (s1 == s0).all() and (s1[2:] == wstatus[2:]).all() and np.isfinite(f1).all() and (bits == f1).all()
+    assert (f1[:2] == f0[:2]).all()                      # re-scored by the same kernel that GSB_NO_KSPACE selects
+    assert rel_err(f1[2:], want[2:]).max() <= REL_TOL   # ordinary subsets: parity as everywhere
