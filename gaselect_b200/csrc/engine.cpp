@@ -305,6 +305,7 @@ struct gsb_engine {
 	bool refitArmed = false;       // the most recent enqueue ran K1k: its results may hold kStatusRetry
 	gsb_engine* retryEngine = nullptr;
 	bool forceNoKspace = false;    // this IS such a child engine
+	bool h2dPending = false;       // gsb_evaluate_indices: the upload's copies and the kernels are in flight, timed at the download
 	DeviceArray<long long> traceBuf; // allocated only when GSB_TRACE is set in the environment
 	double lastH2dMs = 0.0;
 
@@ -1573,10 +1574,17 @@ int gsb_get_info(const gsb_engine* e, gsb_info* info) {
 	return GSB_OK;
 }
 
+static int uploadPopulation(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop, bool sync);
+
 int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
 	if (!offsets || npop < 0 || (!idx && npop > 0 && offsets[npop] > 0)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null population");
 	if (!e->replicas.empty()) return multiUpload(e, idx, offsets, npop);
+	return uploadPopulation(e, idx, offsets, npop, true);
+}
+
+// sync = false (gsb_evaluate_indices): the copies are only enqueued; the call's one synchronisation is the download's
+static int uploadPopulation(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop, bool sync) {
 	if (!e->prepared) {
 		const int rc = prepareChecked(e);
 		if (rc != GSB_OK) return rc;
@@ -1595,6 +1603,10 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 	e->populationReady = e->resultsReady = false;
 	try {
 		ensureDevice(e);
+		if (e->h2dPending) { // a previous un-synchronised upload never reached its download: its copies may still read the pinned buffers
+			GSB_CUDA(cudaStreamSynchronize(e->stream));
+			e->h2dPending = false;
+		}
 		const size_t total = npop > 0 ? offsets[npop] : 0;
 		e->hIdx.reserve(total + 1);
 		e->hOffsets.reserve(static_cast<size_t>(npop) + 1);
@@ -1656,10 +1668,14 @@ int gsb_population_upload(gsb_engine* e, const uint32_t* idx, const uint32_t* of
 			e->dMse.reserve(static_cast<size_t>(npop) * innerDests * e->tableA);
 			e->dOstat.reserve(static_cast<size_t>(npop) * e->plan.groups * e->tableA * 2);
 		}
-		GSB_CUDA(cudaStreamSynchronize(e->stream));
-		float ms = 0.f;
-		GSB_CUDA(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
-		e->lastH2dMs = ms;
+		if (sync) {
+			GSB_CUDA(cudaStreamSynchronize(e->stream));
+			float ms = 0.f;
+			GSB_CUDA(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+			e->lastH2dMs = ms;
+		} else {
+			e->h2dPending = true;
+		}
 		e->populationReady = true;
 		e->resultsReady = false;
 	} catch (const CudaFailure& f) {
@@ -1740,7 +1756,16 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			// the reference's LMEvaluator scores an empty subset as the intercept-only model (src/LMEvaluator.cpp:27-67)
 			gsb::launchLmEmpty(e->dOffsets.ptr, e->npop, e->cfg.statistic, e->n, e->r2denom, e->dFitness.ptr, e->dStatus.ptr, e->stream);
 			++launches;
-			for (size_t b = 0; b < e->buckets.size(); ++b) {
+			// size classes whose shared memory stays small go out as ONE launch (a launch of a few dozen single-CTA
+			// Choleskys is latency-bound: six of them in a row were 0.4 of the 0.5 ms of a 200-chromosome generation)
+			for (size_t b = 0; b < e->buckets.size();) {
+				size_t last = b;
+				int kMax = e->buckets[b].kMax, count = e->buckets[b].count;
+				while (last + 1 < e->buckets.size() && e->buckets[last + 1].kMax <= 96) {
+					++last;
+					kMax = std::max(kMax, e->buckets[last].kMax);
+					count += e->buckets[last].count;
+				}
 				gsb::OlsParams prm;
 				prm.gram = e->gram.ptr;
 				prm.s0 = e->s0.ptr;
@@ -1753,14 +1778,15 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.idx = e->dIdx.ptr;
 				prm.offsets = e->dOffsets.ptr;
 				prm.bucket = e->dBucket.ptr + e->buckets[b].begin;
-				prm.bucketCount = e->buckets[b].count;
+				prm.bucketCount = count;
 				prm.statistic = e->cfg.statistic;
 				prm.r2denom = e->r2denom;
 				prm.fitness = e->dFitness.ptr;
 				prm.status = e->dStatus.ptr;
-				GSB_CUDA(gsb::launchOlsKernel(prm, e->buckets[b].kMax, e->smemLimit, e->stream));
+				GSB_CUDA(gsb::launchOlsKernel(prm, kMax, e->smemLimit, e->stream));
 				ctas += prm.bucketCount;
 				++launches;
+				b = last + 1;
 			}
 			GSB_CUDA(cudaEventRecord(e->ev[3], e->stream));
 			GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
@@ -2123,22 +2149,47 @@ int gsb_population_evaluate(gsb_engine* e) {
 	return GSB_OK;
 }
 
+static int downloadResults(gsb_engine* e, double* fitness, int32_t* status, bool fused);
+
 int gsb_population_download(gsb_engine* e, double* fitness, int32_t* status) {
 	if (!e) return GSB_ERR_INVALID_ARGUMENT;
 	if (!fitness || !status) return fail(e, GSB_ERR_INVALID_ARGUMENT, "null output buffer");
 	if (!e->replicas.empty()) return multiDownload(e, fitness, status);
 	if (!e->resultsReady) return fail(e, GSB_ERR_STATE, "no results: call gsb_population_evaluate first");
+	return downloadResults(e, fitness, status, false);
+}
+
+// fused = true (gsb_evaluate_indices): upload, kernels and these copies were enqueued back to back; this is the call's ONE
+// synchronisation and every stage is timed from its events afterwards
+static int downloadResults(gsb_engine* e, double* fitness, int32_t* status, bool fused) {
 	try {
 		ensureDevice(e);
 		const size_t np = static_cast<size_t>(e->npop);
 		e->hFitness.reserve(np + 1);
 		e->hStatus.reserve(np + 1);
-		GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
+		if (!fused) GSB_CUDA(cudaEventRecord(e->ev[4], e->stream)); // fused: ev[4] is the end of K2, where these copies start
 		GSB_CUDA(cudaMemcpyAsync(e->hFitness.ptr, e->dFitness.ptr, np * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
 		GSB_CUDA(cudaMemcpyAsync(e->hStatus.ptr, e->dStatus.ptr, np * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
 		GSB_CUDA(cudaEventRecord(e->ev[5], e->stream));
+		unsigned long long products = 0ull;
+		if (fused && e->kProductsPending) GSB_CUDA(cudaMemcpyAsync(&products, e->kProducts.ptr, sizeof(products), cudaMemcpyDeviceToHost, e->stream));
 		GSB_CUDA(cudaStreamSynchronize(e->stream));
+		e->h2dPending = false;
 		float ms = 0.f;
+		if (fused) {
+			float msH2d = 0.f, msFit = 0.f, msRed = 0.f;
+			GSB_CUDA(cudaEventElapsedTime(&msH2d, e->ev[0], e->ev[1]));
+			GSB_CUDA(cudaEventElapsedTime(&msFit, e->ev[2], e->ev[3]));
+			GSB_CUDA(cudaEventElapsedTime(&msRed, e->ev[3], e->ev[4]));
+			e->lastH2dMs = msH2d;
+			e->timing.h2d_ms = msH2d;
+			e->timing.fit_kernel_ms = msFit;
+			e->timing.reduce_kernel_ms = msRed;
+			if (e->kProductsPending) {
+				const double n8 = roundUp(e->n, 8);
+				e->timing.fit_tensor_gflop += static_cast<double>(products) * (n8 / 8.0) * (n8 / 4.0) * 512.0 * 1e-9;
+			}
+		}
 		GSB_CUDA(cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]));
 		e->timing.d2h_ms = ms;
 		e->timing.total_ms = e->timing.h2d_ms + e->timing.fit_kernel_ms + e->timing.reduce_kernel_ms + ms;
@@ -2166,6 +2217,24 @@ int gsb_population_device_results(gsb_engine* e, void** d_fitness, void** d_stat
 
 int gsb_evaluate_indices(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop, double* fitness,
                          int32_t* status) {
+	if (e && e->replicas.empty() && offsets && npop > 0 && idx && fitness && status) {
+		// one device: upload, kernels and download enqueued back to back, ONE synchronisation (three, and their event
+		// queries, cost 0.05 ms of a 2 ms call)
+		int rc = uploadPopulation(e, idx, offsets, npop, false);
+		if (rc != GSB_OK) return rc;
+		try {
+			long long ctas = 0;
+			int launches = 0;
+			e->kProductsPending = false;
+			enqueuePopulation(e, ctas, launches);
+			e->timing.fit_ctas = ctas;
+			e->timing.kernel_launches = launches;
+			e->resultsReady = true;
+		} catch (const CudaFailure& f) {
+			return failCuda(e, f);
+		}
+		return downloadResults(e, fitness, status, true);
+	}
 	int rc = gsb_population_upload(e, idx, offsets, npop);
 	if (rc != GSB_OK) return rc;
 	if (npop == 0) return GSB_OK;

@@ -1,9 +1,9 @@
 // ols_fit.cu -- K3: ordinary least squares with intercept + BIC/AIC/R2 epilogue, one CTA per
 // chromosome.  Replaces LMEvaluator::evaluate (src/LMEvaluator.cpp:27-67):
 //   Xsub = [1 | X[:, sel]]; beta = arma::solve(Xsub, y); RSS = sum (y - Xsub beta)^2; statistic.
-// The reference solves by LAPACK least squares (QR); here the slope coefficients come from a
-// Cholesky factorisation of the centred Gram sub-matrix (gathered from the all-rows Gram
-// table into shared memory, packed lower triangle), and -- as SURVEY.md Appendix B.1 shows is
+// The reference solves by LAPACK least squares (QR); here the slope coefficients come from an
+// LDL' factorisation (Cholesky's pivots, no square roots) of the centred Gram sub-matrix (gathered from
+// the all-rows Gram table into shared memory, packed lower triangle), and -- as SURVEY.md Appendix B.1 shows is
 // necessary for 1e-8 parity when R^2 -> 1 -- the RSS is accumulated from EXPLICIT residuals
 // over coalesced column segments of X[:, sel], not from the quadratic form.
 // A pivot that is not safely positive marks the subset GSB_STATUS_SINGULAR (the reference
@@ -65,7 +65,11 @@ __global__ void __launch_bounds__(kOlsThreads) olsFitKernel(const OlsParams prm)
 	}
 	__syncthreads();
 
-	// right-looking Cholesky on the packed triangle
+	// Right-looking LDL' (the Cholesky pivots without the square roots) of the packed triangle, the right-hand side
+	// carried as one more row (row k): after column j every entry (r, c > j) has lost A[r][j] A[c][j] / d_j, so the
+	// last row ends as M^-1 s0 scaled by D -- the forward substitution is done -- and column j is never written again
+	// after step j - 1: ONE barrier per column (the scaled-column form needed three, and two more per column for the
+	// substitutions: a 50-column subset paid 350 barriers).
 	for (int j = 0; j < k; ++j) {
 		const int tj = j * (j + 1) / 2;
 		const double piv = L[tj + j];
@@ -73,18 +77,12 @@ __global__ void __launch_bounds__(kOlsThreads) olsFitKernel(const OlsParams prm)
 			if (tid == 0) singular = 1;
 			break;
 		}
-		const double ljj = sqrt(piv);
-		__syncthreads();
-		for (int r = j + tid; r < k; r += kOlsThreads) {
-			const int trr = r * (r + 1) / 2;
-			L[trr + j] = (r == j) ? ljj : L[trr + j] / ljj;
-		}
-		__syncthreads();
-		// trailing update: L[r][c] -= L[r][j] * L[c][j] for j < c <= r
-		for (int r = j + 1 + tid; r < k; r += kOlsThreads) {
-			const int trr = r * (r + 1) / 2;
-			const double lrj = L[trr + j];
-			for (int c = j + 1; c <= r; ++c) L[trr + c] = fma(-lrj, L[c * (c + 1) / 2 + j], L[trr + c]);
+		const double rp = 1.0 / piv;
+		for (int r = j + 1 + tid; r <= k; r += kOlsThreads) {
+			double* __restrict__ row = (r < k) ? L + r * (r + 1) / 2 : rhs;
+			const double f = row[j] * rp;
+			const int cend = (r < k) ? r : k - 1;
+			for (int c = j + 1; c <= cend; ++c) row[c] = fma(-f, L[c * (c + 1) / 2 + j], row[c]);
 		}
 		__syncthreads();
 	}
@@ -93,22 +91,18 @@ __global__ void __launch_bounds__(kOlsThreads) olsFitKernel(const OlsParams prm)
 		if (tid == 0) { prm.fitness[chrom] = 0.0; prm.status[chrom] = 3; }
 		return;
 	}
-	// forward substitution L z = s0 (column oriented), then backward L' beta = z
-	for (int j = 0; j < k; ++j) {
-		const double zj = rhs[j] / L[j * (j + 1) / 2 + j];
-		__syncthreads();
-		if (tid == 0) rhs[j] = zj;
-		for (int r = j + 1 + tid; r < k; r += kOlsThreads) rhs[r] = fma(-L[r * (r + 1) / 2 + j], zj, rhs[r]);
-		__syncthreads();
+	// backward substitution M' beta = D^-1 (last row), column oriented, by ONE warp: lane c mod 32 owns entry c, beta_j
+	// travels by shuffle, no CTA barrier: beta_j = acc[j] / d_j; acc[c] -= A[j][c] beta_j for c < j (row j is contiguous)
+	if (tid < 32) {
+		for (int j = k - 1; j >= 0; --j) {
+			const int tj = j * (j + 1) / 2;
+			double bj = 0.0;
+			if ((j & 31) == tid) { bj = rhs[j] / L[tj + j]; rhs[j] = bj; }
+			bj = __shfl_sync(0xffffffffu, bj, j & 31);
+			for (int c = tid; c < j; c += 32) rhs[c] = fma(-L[tj + c], bj, rhs[c]);
+		}
 	}
-	for (int j = k - 1; j >= 0; --j) {
-		const int tj = j * (j + 1) / 2;
-		const double bj = rhs[j] / L[tj + j];
-		__syncthreads();
-		if (tid == 0) rhs[j] = bj;
-		for (int c = tid; c < j; c += kOlsThreads) rhs[c] = fma(-L[tj + c], bj, rhs[c]);
-		__syncthreads();
-	}
+	__syncthreads();
 	// intercept on the (globally centred) data: b0 = ym - xm'beta
 	double part = 0.0;
 	for (int i = tid; i < k; i += kOlsThreads) part = fma(xms[i], rhs[i], part);

@@ -1,12 +1,13 @@
 """Turn the ncu outputs of a round (gpurun_out/) into the small, committed summaries under profiles/.
 
-usage: python profiles/summarize.py r01
+usage: python profiles/summarize.py r01 ["the profiled command"]      (round 2: r02_cfg3, r02_cfg4 -- profiles/r02_capture.sh)
   gpurun_out/<round>_launches.csv      (ncu --metrics gpu__time_duration.sum ... python bench.py ...)
   gpurun_out/<round>_k1_full.ncu-rep   (ncu --set full ... -k regex:simpls ... python bench.py ...)
 """
 import collections, csv, io, os, subprocess, sys
 
 rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+command = sys.argv[2] if len(sys.argv) > 2 else "python bench.py --steps 3 --warmup 3 --no-cpu"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = []
 
@@ -24,15 +25,17 @@ if os.path.exists(path):
         agg[name][1] += v
     tot = sum(v[1] for v in agg.values())
     out.append("== launch list (ncu --metrics gpu__time_duration.sum, cold-cache serialised launches; compare SHARES) ==")
-    out.append("command: python bench.py --steps 3 --warmup 3 --no-cpu   (first 400 launches)")
+    out.append("command: %s" % command)
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append("%-44s launches=%4d  total=%9.3f ms  share=%5.1f%%" % (k[:44], v[0], v[1], 100 * v[1] / tot))
     with open(os.path.join(root, "profiles", rnd + "_launches.csv"), "w") as fh:
         fh.write("\n".join(lines) + "\n")
 
 rep = os.path.join(root, "gpurun_out", rnd + "_k1_full.ncu-rep")
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rawcsv = os.path.join(root, "gpurun_out", rnd + "_k1_raw.csv")  # exported on the GPU box (the report itself stays there)
+if os.path.exists(rep) or os.path.exists(rawcsv):
+    raw = open(rawcsv).read() if os.path.exists(rawcsv) else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = "\n".join(l for l in raw.splitlines() if l.startswith('"'))
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = rows[0]
     want = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -49,7 +52,7 @@ if os.path.exists(rep):
         for r in rows[2:]:
             w.writerow([r[i].replace("void gsb::<unnamed>::", "") for _, i in idx])
     out.append("")
-    out.append("== K1 (simplsKspaceKernel + simplsFitFast per size class), ncu --set full --clock-control none (one generation) ==")
+    out.append("== K1 launches of one generation (kernel-space kernel, per-fit path per size class), ncu --set full --clock-control none ==")
     out.append("%-34s %-10s %-8s %9s %10s %10s %6s %7s %7s %7s %7s %7s %7s" % ("kernel", "block", "grid", "time ms", "dram rd MB", "dram wr MB", "regs", "smem KB", "warps%", "issue%", "fp64%", "lds%", "dmma%"))
     g = dict(idx)
     tot_t = tot_rd = tot_wr = 0.0
