@@ -47,7 +47,7 @@ namespace {
 constexpr int kChunk = 10;  // components per prediction pass (accumulators held in registers)
 constexpr int kDots = 6;    // loadings projected in the same reduction round as S'w and s0'S
 constexpr int kRedMax = 20; // widest reduction (values per thread)
-constexpr int kMaxWarps = 12; // 384 threads: subsets up to k = 384 on the spill path
+constexpr int kMaxWarps = 13; // 416 threads: subsets up to k = 416 on the spill path
 
 // Sum NV values over the CTA (nw warps); every thread receives bitwise-identical totals.
 template <int NV>
@@ -441,8 +441,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 // Reductions: ONE round per component for {S'w, s0'S, V_j'w for every stored loading} and one for
 // {v'v, v'S}.  A round over 16 values costs 16 shuffle-adds (the lanes halve the value set at every
 // butterfly step) instead of 80, and 1/tn, 1/|v| come from rsqrt (no division, no sqrt).
+// shared memory of the spill path beside the packed rows: the spilled rows' own products (k - rs) and, per warp, its share
+// of the column products of the spilled entries (k each)
+__host__ __device__ inline int spillScratchDoubles(int k, int rs) {
+	if (rs >= k) return 0;
+	return roundUp(k - rs, 2) + (roundUp(k, 32) / 32) * roundUp(k, 2);
+}
+
 struct FastCarve {
 	int P, S, red, sel, total;
+	int spill;                        // spill path: wrow[k - rs], then part[warp][k]
 	int coef, part, stage, stageCols; // inside the P area, after the fit
 	int xt;                           // > 0: whole held-out blocks are staged at P + xt ...
 	int xtTasks;                      // ... this many per pass (1 or 2)
@@ -482,6 +490,7 @@ __host__ __device__ inline FastCarve fastCarve(int k, int A, int nw, int maxTask
 	c.S = o; o += roundUp(k, 2);
 	c.red = o; o += 2 * nw * 16; // double-buffered partial sums, 16 values per warp
 	c.sel = o; o += roundUp(k, 2) / 2 + 1;
+	c.spill = o; o += spillScratchDoubles(k, rs);
 	c.total = o;
 	c.coef = 0;
 	c.part = coefD;
@@ -501,6 +510,7 @@ __host__ __device__ inline FastCarve fitOnlyCarve(int k, int nw, int rowsInSmem)
 	c.S = o; o += roundUp(k, 2);
 	c.red = o; o += 2 * nw * 16;
 	c.sel = o;
+	c.spill = o; o += spillScratchDoubles(k, rs);
 	c.total = o;
 	c.coef = c.part = c.stage = c.stageCols = c.xt = c.xtTasks = 0;
 	return c;
@@ -568,81 +578,76 @@ __device__ __forceinline__ double symvRow(const double* __restrict__ P, const do
 	return (a0 + a1) + (a2 + a3);
 }
 
-// The same row when only the packed rows [0, rs) are in shared memory (rs is a multiple of 32 or k, so a warp's rows
-// are all on one side): the rows [rs, k) are read in place from the fit's packed slab gp in global memory (L2).
-__device__ __forceinline__ double symvRowSpill(const double* __restrict__ P, const double* __restrict__ S, const double* __restrict__ gp,
-                                               int k, int rs, int r, int rlo, int rhi) {
-	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-	int c = 0;
-	if (rlo < rs) {
-		// this warp's rows are in shared memory: as symvRow up to the first spilled row ...
-		const double* __restrict__ pr = P + r * (r + 1) / 2;
-		const double* __restrict__ pc = P + r;
-		for (; c + 3 < rlo; c += 4) {
-			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
-			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
-			a0 = fma(pr[c], s01.x, a0);
-			a1 = fma(pr[c + 1], s01.y, a1);
-			a2 = fma(pr[c + 2], s23.x, a2);
-			a3 = fma(pr[c + 3], s23.y, a3);
+// w = G S when only the packed rows [0, rs) are in shared memory (rs is a multiple of 32 below k, so a warp's rows are
+// all on one side); the rows [rs, k) stay in the fit's packed slab gp in global memory (L2-resident while the CTA runs).
+//   * warps whose rows are in shared memory: symvRow on the rs x rs triangle;
+//   * then EVERY warp takes its share of the spilled rows (row rs + warp, rs + warp + warps, ...), one row at a time with
+//     the lanes across its columns: coalesced 256-byte reads, every spilled entry fetched ONCE and used for both of its
+//     products (row c: summed over the lanes; column j: a per-lane accumulator, colacc[m] for j = lane + 32 m).  All
+//     warps, because a row costs an L2 round trip: with the spilled rows left to the few warps that own them a
+//     256-column subset (one such warp) took twice as long as with per-thread runs;
+//   * one barrier; every row then adds the warps' column shares (fixed order: bitwise reproducible) and, if it is a
+//     spilled row, its own product.
+// (The first form read the spilled rows as per-thread runs -- a 32-byte sector per 8 useful bytes -- and every spilled
+// entry twice; at k = 384 the step took 3.9 x what the k^2 trend of the shared-memory path predicts.)
+constexpr int kSpillCols = kMaxWarps; // column slots of 32 per lane
+__device__ __forceinline__ double symvSpill(const double* __restrict__ P, const double* __restrict__ S, const double* __restrict__ gp,
+                                            int k, int rs, int r, int rlo, int rhi, int warp, int lane, double* __restrict__ wrow,
+                                            double* __restrict__ part) {
+	const int kp = roundUp(k, 2);
+	const int nsw = roundUp(k, 32) / 32; // warps of this subset (a class of subsets shares one multiple of 32)
+	double wa = 0.0;
+	if (rlo < rs) wa = symvRow(P, S, rs, r, rlo, rhi);
+	{
+		const int sw = warp;
+		const int cFirst = sw < nsw ? rs + sw : k;
+		double colacc[kSpillCols];
+#pragma unroll
+		for (int m = 0; m < kSpillCols; ++m) colacc[m] = 0.0;
+		// two rows per iteration: their loads are in flight together (a row is one L2 round trip)
+		for (int c = cFirst; c < k; c += 2 * nsw) {
+			const int c2 = c + nsw;
+			const bool two = c2 < k;
+			const double* __restrict__ row = gp + static_cast<size_t>(c) * (c + 1) / 2;
+			const double* __restrict__ row2 = gp + static_cast<size_t>(two ? c2 : c) * ((two ? c2 : c) + 1) / 2;
+			double g[kSpillCols], h[kSpillCols];
+#pragma unroll
+			for (int m = 0; m < kSpillCols; ++m) {
+				const int j = lane + 32 * m;
+				g[m] = (j <= c) ? __ldcg(row + j) : 0.0;
+				h[m] = (two && j <= c2) ? __ldcg(row2 + j) : 0.0;
+			}
+			const double sc = S[c], sc2 = S[two ? c2 : c];
+			double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+			for (int m = 0; m < kSpillCols; ++m) {
+				const int j = lane + 32 * m;
+				if (32 * m <= (two ? c2 : c)) { // warp-uniform
+					const double sj = S[min(j, k - 1)];
+					acc = fma(g[m], sj, acc);
+					acc2 = fma(h[m], sj, acc2);
+					if (j < c) colacc[m] = fma(g[m], sc, colacc[m]);
+					if (two && j < c2) colacc[m] = fma(h[m], sc2, colacc[m]);
+				}
+			}
+#pragma unroll
+			for (int m = 16; m >= 1; m >>= 1) { acc += shflXor(acc, m); acc2 += shflXor(acc2, m); }
+			if (lane == 0) {
+				wrow[c - rs] = acc;
+				if (two) wrow[c2 - rs] = acc2;
+			}
 		}
-		for (; c < rlo; ++c) a0 = fma(pr[c], S[c], a0);
-		int tc = rlo * (rlo + 1) / 2;
-		for (; c <= rhi; ++c) {
-			const double g = (c <= r) ? pr[c] : pc[tc];
-			a1 = fma(g, S[c], a1);
-			tc += c + 1;
-		}
-		for (; c + 3 < rs; c += 4) {
-			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
-			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
-			const int t1 = tc + c + 1, t2 = t1 + c + 2, t3 = t2 + c + 3;
-			a0 = fma(pc[tc], s01.x, a0);
-			a1 = fma(pc[t1], s01.y, a1);
-			a2 = fma(pc[t2], s23.x, a2);
-			a3 = fma(pc[t3], s23.y, a3);
-			tc = t3 + c + 4;
-		}
-		for (; c < rs; ++c) {
-			a2 = fma(pc[tc], S[c], a2);
-			tc += c + 1;
-		}
-	} else {
-		// ... this warp's rows are spilled: own packed row, per-thread runs from L2
-		const double* __restrict__ gr = gp + static_cast<size_t>(r) * (r + 1) / 2;
-		for (; c + 3 < rlo; c += 4) {
-			const double2 s01 = *reinterpret_cast<const double2*>(S + c);
-			const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
-			a0 = fma(__ldcg(gr + c), s01.x, a0);
-			a1 = fma(__ldcg(gr + c + 1), s01.y, a1);
-			a2 = fma(__ldcg(gr + c + 2), s23.x, a2);
-			a3 = fma(__ldcg(gr + c + 3), s23.y, a3);
-		}
-		for (; c < rlo; ++c) a0 = fma(__ldcg(gr + c), S[c], a0);
-		for (; c <= rhi; ++c) { // the band: (r, c) for c <= r, else (c, r) of another spilled row
-			const double g = (c <= r) ? __ldcg(gr + c) : __ldcg(gp + static_cast<size_t>(c) * (c + 1) / 2 + r);
-			a1 = fma(g, S[c], a1);
+#pragma unroll
+		for (int m = 0; m < kSpillCols; ++m) {
+			const int j = lane + 32 * m;
+			if (j < k && sw < nsw) part[sw * kp + j] = colacc[m];
 		}
 	}
-	// below the band / beyond the shared rows: column r of the spilled rows c (coalesced over the lanes)
-	c = max(c, rs);
-	const double* __restrict__ gc = gp + r;
-	size_t tc = static_cast<size_t>(c) * (c + 1) / 2;
-	for (; c + 3 < k; c += 4) {
-		const double2 s01 = *reinterpret_cast<const double2*>(S + c);
-		const double2 s23 = *reinterpret_cast<const double2*>(S + c + 2);
-		const size_t t1 = tc + c + 1, t2 = t1 + c + 2, t3 = t2 + c + 3;
-		a0 = fma(__ldcg(gc + tc), s01.x, a0);
-		a1 = fma(__ldcg(gc + t1), s01.y, a1);
-		a2 = fma(__ldcg(gc + t2), s23.x, a2);
-		a3 = fma(__ldcg(gc + t3), s23.y, a3);
-		tc = t3 + c + 4;
-	}
-	for (; c < k; ++c) {
-		a3 = fma(__ldcg(gc + tc), S[c], a3);
-		tc += c + 1;
-	}
-	return (a0 + a1) + (a2 + a3);
+	__syncthreads();
+	double w = wa;
+	for (int s2 = 0; s2 < nsw; ++s2) w += part[s2 * kp + r];
+	if (r >= rs) w += wrow[r - rs];
+	return w;
 }
 
 // SPILL: packed Gram rows >= rSplit (a multiple of 32) do not fit in shared memory; every matrix-vector product reads
@@ -734,7 +739,8 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	double cum = 0.0;
 #pragma unroll 1
 	for (int comp = 0; comp < A; ++comp) {
-		const double w = SPILL ? symvRowSpill(P, S, gsrc, k, rs, r, rlo, rhi) : symvRow(P, S, k, r, rlo, rhi);
+		const double w = SPILL ? symvSpill(P, S, gsrc, k, rs, r, rlo, rhi, warp, lane, smem + cv.spill, smem + cv.spill + roundUp(k - rs, 2))
+		                       : symvRow(P, S, k, r, rlo, rhi);
 
 		// ONE round: tn^2 = S'GS (:138), q*tn = s0'S (:148), projections V_j'w on every stored loading
 		double r1[2 + AREG];

@@ -55,6 +55,12 @@ if os.path.exists(rep) or os.path.exists(rawcsv):
     out.append("== K1 launches of one generation (kernel-space kernel, per-fit path per size class), ncu --set full --clock-control none ==")
     out.append("%-34s %-10s %-8s %9s %10s %10s %6s %7s %7s %7s %7s %7s %7s" % ("kernel", "block", "grid", "time ms", "dram rd MB", "dram wr MB", "regs", "smem KB", "warps%", "issue%", "fp64%", "lds%", "dmma%"))
     g = dict(idx)
+    unit_of = {n: rows[1][i] for n, i in idx}
+    t_ms = {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}.get(unit_of.get("gpu__time_duration.sum", "ms"), 1.0)
+    b_mb = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+    rd_mb = b_mb.get(unit_of.get("dram__bytes_read.sum", "Mbyte"), 1.0)
+    wr_mb = b_mb.get(unit_of.get("dram__bytes_write.sum", "Mbyte"), 1.0)
+    sm_kb = {"byte": 1e-3, "Kbyte": 1.0, "Mbyte": 1e3}.get(unit_of.get("launch__shared_mem_per_block_dynamic", "Kbyte"), 1.0)
     tot_t = tot_rd = tot_wr = 0.0
     for r in rows[2:]:
         def f(name, d=0.0):
@@ -62,17 +68,15 @@ if os.path.exists(rep) or os.path.exists(rawcsv):
                 return float(r[g[name]].replace(",", ""))
             except (KeyError, ValueError):
                 return d
-        tot_t += f("gpu__time_duration.sum"); tot_rd += f("dram__bytes_read.sum"); tot_wr += f("dram__bytes_write.sum")
+        tot_t += f("gpu__time_duration.sum") * t_ms; tot_rd += f("dram__bytes_read.sum") * rd_mb; tot_wr += f("dram__bytes_write.sum") * wr_mb
         out.append("%-34s %-10s %-8s %9.3f %10.1f %10.1f %6.0f %7.1f %7.1f %7.1f %7.1f %7.1f %7.1f" % (
-            r[g["Kernel Name"]].replace("void gsb::<unnamed>::", "").split("(")[0][:34], r[g["Block Size"]].replace(" ", ""), r[g["Grid Size"]].split(",")[0].strip("("), f("gpu__time_duration.sum"),
-            f("dram__bytes_read.sum"), f("dram__bytes_write.sum"), f("launch__registers_per_thread"),
-            f("launch__shared_mem_per_block_dynamic"), f("sm__warps_active.avg.pct_of_peak_sustained_active"),
+            r[g["Kernel Name"]].replace("void gsb::<unnamed>::", "").split("(")[0][:34], r[g["Block Size"]].replace(" ", ""), r[g["Grid Size"]].split(",")[0].strip("("), f("gpu__time_duration.sum") * t_ms,
+            f("dram__bytes_read.sum") * rd_mb, f("dram__bytes_write.sum") * wr_mb, f("launch__registers_per_thread"),
+            f("launch__shared_mem_per_block_dynamic") * sm_kb, f("sm__warps_active.avg.pct_of_peak_sustained_active"),
             f("smsp__issue_active.avg.pct_of_peak_sustained_active"), f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
             f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
             f("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")))
-    units = {n: rows[1][i] for n, i in idx}
-    out.append("sum over the generation: time %.3f %s (serialised under ncu), dram read %.1f %s, dram write %.1f %s" % (
-        tot_t, units.get("gpu__time_duration.sum", ""), tot_rd, units.get("dram__bytes_read.sum", ""), tot_wr, units.get("dram__bytes_write.sum", "")))
+    out.append("sum over the captured launches: time %.3f ms (serialised under ncu), dram read %.1f MB, dram write %.1f MB" % (tot_t, tot_rd, tot_wr))
 
 text = "\n".join(out) + "\n"
 with open(os.path.join(root, "profiles", rnd + "_summary.txt"), "w") as fh:
