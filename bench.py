@@ -378,6 +378,12 @@ def main():
         step_resident()
     barrier()
     gather_check = None
+    if world > 1:
+        # chromosomes the kernel-space kernel declined (GSB_STATUS_RETRY; none on the bench populations) are re-scored
+        # and patched into the device buffers by the download: gather once more so that the check below sees them
+        ev.download_results(fitness, status)
+        all_gather()
+        barrier()
     if world > 1 and rank == 0:
         # the gathered vector, un-permuted, against this GPU's own evaluation of the WHOLE generation: bit for bit
         got = np.zeros(len(generation), dtype=np.float64)
