@@ -102,6 +102,7 @@ struct Bucket {
 	int kMax;
 	int kernel;        // BucketKernel, decided when the population is uploaded
 	bool split;        // BK_FIT: fit-only kernel + predictBlocksKernel (else the per-fit kernel predicts in place)
+	unsigned long long genPerCta; // BK_FIT: doubles of global scratch per CTA (many components on wide subsets), 0: none
 	int nf, cs, vg;    // K1x configuration (fits per CTA, cluster size, loadings in the global scratch)
 	long long vPerCta, vOffset;
 	int vSlots;
@@ -257,6 +258,7 @@ struct gsb_engine {
 	PinnedArray<unsigned long long> hPackOff, hVecOff, hCoefOff;
 	// ... and the fits' coefficient rows for the prediction kernel, whose task lists are per held-out block
 	DeviceArray<double> coefScratch;
+	DeviceArray<double> genScratch; // stored loadings + coefficients of the generic kernel when they outgrow shared memory
 	DeviceArray<int> activeBlocks, blockTaskOff;
 	DeviceArray<gsb::PredTask> predTasks;
 	int nActiveBlocks = 0;
@@ -341,7 +343,7 @@ void releaseDevice(gsb_engine* e) {
 	e->unitTab.release(); e->unitSum.release(); e->unitXy.release(); e->packFits.release();
 	e->gpack.release(); e->pvec.release(); e->dPackOff.release(); e->dVecOff.release(); e->dCoefOff.release();
 	e->hPackOff.release(); e->hVecOff.release(); e->hCoefOff.release();
-	e->coefScratch.release(); e->activeBlocks.release(); e->blockTaskOff.release(); e->predTasks.release();
+	e->coefScratch.release(); e->genScratch.release(); e->activeBlocks.release(); e->blockTaskOff.release(); e->predTasks.release();
 	e->xz.release(); e->scoreScratch.release(); e->xReps.release(); e->xGroups8.release(); e->xGroups16.release(); e->xFits.release(); e->xTasks.release();
 	e->kFits.release(); e->kTasks.release();
 	for (int i = 0; i <= gsb_engine::kMaxSplit; ++i) { e->kSchedules[i].fitOrder.release(); e->kSchedules[i].parts.release(); e->kSchedules[i].ready = false; }
@@ -1060,6 +1062,29 @@ void planBuckets(gsb_engine* e) {
 				coefTotal += ((k + 2ull) * A * static_cast<unsigned long long>(nfits) + 1ull) & ~1ull;
 			}
 		}
+	}
+	// generic kernel (more than ten components): when the stored loadings and coefficients of a class outgrow shared
+	// memory they live in a global scratch, one region per CTA of a launch; the class is then walked in chunks of
+	// chromosomes (launchFitKernel).  One region for all such classes: they are launched on one stream.
+	unsigned long long genWant = 0, genMin = 0;
+	for (size_t b = 0; b < e->buckets.size(); ++b) {
+		Bucket& bk = e->buckets[b];
+		bk.genPerCta = 0;
+		if (bk.kernel != BK_FIT || bk.split) continue;
+		bk.genPerCta = gsb::fitKernelScratchPerCta(bk.kMax, e->tableA, e->maxTasks, e->maxBlockLd, e->smemLimit);
+		const unsigned long long perChrom = bk.genPerCta * static_cast<unsigned long long>(nfits);
+		genMin = std::max(genMin, perChrom);
+		genWant = std::max(genWant, perChrom * static_cast<unsigned long long>(std::min(bk.count, 2 * std::max(1, e->smCount))));
+	}
+	if (genWant > e->genScratch.capacity) {
+		size_t freeB = 0, totalB = 0;
+		GSB_CUDA(cudaMemGetInfo(&freeB, &totalB));
+		const unsigned long long room = static_cast<unsigned long long>(0.25 * static_cast<double>(freeB)) / 8ull;
+		const unsigned long long take = std::max(genMin, std::min(genWant, room));
+		if (8.0 * static_cast<double>(take) > 0.9 * static_cast<double>(freeB)) {
+			throw std::string("the stored loadings of this many components on subsets this wide do not fit in device memory");
+		}
+		e->genScratch.reserve(static_cast<size_t>(take));
 	}
 	if (packTotal + vecTotal + coefTotal > e->gpack.capacity + e->pvec.capacity + e->coefScratch.capacity) {
 		size_t freeB = 0, totalB = 0;
@@ -1901,6 +1926,7 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			for (size_t bi = kspaceFirst; bi-- > 0; ++slot) {
 				const Bucket& bk = e->buckets[bi];
 				cudaStream_t launchStream = nside ? e->side[slot % nside] : e->stream;
+				if (nside && bk.kernel == BK_FIT && bk.genPerCta > 0) launchStream = e->side[0]; // the classes that share the global scratch run in order
 				if (bk.kernel == BK_SCORES) {
 					gsb::XParams xp;
 					xp.zpool = e->xz.ptr;
@@ -1975,6 +2001,9 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.maxBlockLd = e->maxBlockLd;
 				prm.coefScratch = e->coefScratch.ptr;
 				prm.coefOff = e->dCoefOff.ptr;
+				prm.genScratch = e->genScratch.ptr;
+				prm.genCapacity = e->genScratch.capacity;
+				prm.genStride = 0;
 				if (bk.split) {
 					GSB_CUDA(gsb::launchFitOnlyKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas));
 					gsb::PredictParams pr;
@@ -2403,6 +2432,10 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
 		prm.p = k; prm.maxNComp = A; prm.innerDests = 0; prm.outerDests = 0;
 		prm.mse = dDummy.ptr; prm.ostat = dDummy.ptr; prm.coefOut = dOut.ptr; prm.trace = nullptr; prm.maxTasks = 0; prm.maxBlockLd = 0;
 		prm.coefScratch = nullptr; prm.coefOff = nullptr;
+		DeviceArray<double> dGen; // many components on a wide subset: stored loadings and coefficients outside shared memory
+		const unsigned long long genPer = gsb::fitKernelScratchPerCta(k, A, 0, 0, e->smemLimit);
+		if (genPer > 0) dGen.reserve(static_cast<size_t>(genPer));
+		prm.genScratch = dGen.ptr; prm.genCapacity = dGen.capacity; prm.genStride = 0;
 		GSB_CUDA(gsb::launchFitKernel(prm, k, A, e->smemLimit, e->stream, nullptr));
 		std::vector<double> out(static_cast<size_t>(k) * A + A);
 		GSB_CUDA(cudaMemcpyAsync(out.data(), dOut.ptr, out.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));

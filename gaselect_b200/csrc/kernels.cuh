@@ -81,6 +81,10 @@ struct FitParams {
 	// [coef (k x A); -1 (A); intercepts (A)] go to coefScratch for predictBlocksKernel (predict_blocks.cu)
 	double* coefScratch;
 	const unsigned long long* coefOff; // per chromosome: offset (doubles) of its first fit's rows
+	// generic kernel, many components on wide subsets: stored loadings and coefficients in a global scratch, one region of
+	// genStride doubles per CTA of a launch (launchFitKernel walks the class in chunks of chromosomes that fit genCapacity)
+	double* genScratch;
+	unsigned long long genCapacity, genStride;
 };
 
 // ---- K1p (predict_blocks.cu): held-out prediction of the per-fit path, one CTA per (held-out block, chromosome) ----
@@ -369,6 +373,7 @@ void launchUnitInterleave(const double* const* mUnits, int unitBegin, int unitCo
 cudaError_t launchGramPack(const PackParams& prm, int kMax, cudaStream_t stream);
 void launchBlockGather(const double* z, int ldz, int ncols, const uint32_t* cols, const uint32_t* rows, int nrows,
                        double* dst, int ld, cudaStream_t stream);
+unsigned long long fitKernelScratchPerCta(int kMax, int A, int maxTasks, int maxBlockLd, int smemLimit);
 int fitKernelSharedBytes(int k, int A);
 int fitKernelMaxK(int A, int smemLimit);
 cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit, cudaStream_t stream, long long* ctas);

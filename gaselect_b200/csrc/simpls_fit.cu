@@ -85,7 +85,10 @@ struct Carve {
 // staging area of the generic path after the fit: the warps' partial sums + at least min(k, 32) column tiles
 __host__ __device__ inline int stageMin(int k, int nw) { return nw * 32 * kChunk + 32 * min(k, 32); }
 
-__host__ __device__ inline Carve carve(int k, int A, bool gramInSmem, int nw) {
+// vGlobal: the stored loadings V (A x k) and the cumulative coefficients (k x Apad) live in a global scratch (one region
+// per CTA of the launch, L2-resident while it runs) instead of shared memory: unconstrained component counts on wide
+// subsets (evaluatorPLS defaults on spectra: A = min(k, n_tr - 1) ~ 100 components of 200 columns = 320 KB)
+__host__ __device__ inline Carve carve(int k, int A, bool gramInSmem, int nw, bool vGlobal = false) {
 	Carve c;
 	const int Apad = roundUp(A, kChunk);
 	int o = 0;
@@ -94,8 +97,8 @@ __host__ __device__ inline Carve carve(int k, int A, bool gramInSmem, int nw) {
 	c.S = o; o += roundUp(k, 2);
 	c.s0 = o; o += roundUp(k, 2);
 	c.xm = o; o += roundUp(k, 2);
-	c.V = o; o += roundUp(A * k, 2);
-	c.coef = o; o += k * Apad;
+	c.V = o; o += vGlobal ? 0 : roundUp(A * k, 2);
+	c.coef = o; o += vGlobal ? 0 : k * Apad;
 	c.b0 = o; o += Apad;
 	c.red = o; o += 2 * nw * kRedMax;  // double-buffered
 	c.sel = o; o += roundUp(k, 2) / 2 + 1;    // uint32 column ids
@@ -104,7 +107,7 @@ __host__ __device__ inline Carve carve(int k, int A, bool gramInSmem, int nw) {
 }
 
 // RPT rows of the k x k system per thread (1 on the shared-memory path: blockDim.x >= k)
-template <int RPT, bool GSMEM>
+template <int RPT, bool GSMEM, bool VGLOB = false>
 __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParams prm) {
 	extern __shared__ __align__(16) double smem[];
 	const int NT = blockDim.x, NW = NT >> 5;
@@ -119,13 +122,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 	const FitDesc fd = prm.fits[fi];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-	const Carve cv = carve(k, A, GSMEM, NW);
+	const Carve cv = carve(k, A, GSMEM, NW, VGLOB);
 	double* __restrict__ P = smem + cv.P;
 	double* __restrict__ S = smem + cv.S;
 	double* __restrict__ s0s = smem + cv.s0;
 	double* __restrict__ xms = smem + cv.xm;
-	double* __restrict__ V = smem + cv.V;
-	double* __restrict__ coef = smem + cv.coef;
+	double* __restrict__ V = VGLOB ? prm.genScratch + static_cast<size_t>(blockIdx.x) * prm.genStride : smem + cv.V;
+	double* __restrict__ coef = VGLOB ? V + roundUp(A * k, 2) : smem + cv.coef;
 	double* __restrict__ b0 = smem + cv.b0;
 	double* red = smem + cv.red;
 	uint32_t* __restrict__ sel = reinterpret_cast<uint32_t*>(smem + cv.sel);
@@ -1111,22 +1114,55 @@ cudaError_t launchFast(const FitParams& prm, int kMax, int A, int smemLimit, cud
 
 constexpr int kFastComponents = 10;
 
-template <int RPT, bool GSMEM>
+template <int RPT, bool GSMEM, bool VGLOB = false>
 cudaError_t launchOne(const FitParams& prm, int kMax, int A, int threads, cudaStream_t stream, long long* ctas) {
-	const Carve cv = carve(kMax, A, GSMEM, threads / 32);
+	const Carve cv = carve(kMax, A, GSMEM, threads / 32, VGLOB);
 	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double);
-	cudaError_t err = cudaFuncSetAttribute(simplsFitKernel<RPT, GSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	cudaError_t err = cudaFuncSetAttribute(simplsFitKernel<RPT, GSMEM, VGLOB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	                                       static_cast<int>(bytes));
 	if (err != cudaSuccess) return err;
 	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
 	if (grid <= 0) return cudaSuccess;
 	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-	simplsFitKernel<RPT, GSMEM><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm);
+	simplsFitKernel<RPT, GSMEM, VGLOB><<<static_cast<unsigned>(grid), threads, bytes, stream>>>(prm);
 	if (ctas) *ctas += grid;
 	return cudaGetLastError();
 }
 
+// doubles of global scratch one CTA of the vGlobal instances needs for a subset of k columns and A components
+inline unsigned long long genScratchPerCta(int k, int A) {
+	return static_cast<unsigned long long>(roundUp(A * k, 2)) + static_cast<unsigned long long>(k) * roundUp(A, kChunk) + 2ull;
+}
+
+// the vGlobal instances, the chromosomes of the class walked in chunks that fit the scratch the engine provides
+template <int RPT, bool GSMEM>
+cudaError_t launchGlobalV(const FitParams& prm, int kMax, int A, int threads, cudaStream_t stream, long long* ctas) {
+	const unsigned long long per = genScratchPerCta(kMax, A);
+	if (prm.genScratch == nullptr || prm.genCapacity < per * static_cast<unsigned long long>(prm.nfits)) return cudaErrorMemoryAllocation;
+	const int chunk = static_cast<int>(std::min<unsigned long long>(static_cast<unsigned long long>(prm.bucketCount),
+	                                                                   prm.genCapacity / (per * static_cast<unsigned long long>(prm.nfits))));
+	for (int c0 = 0; c0 < prm.bucketCount; c0 += chunk) {
+		FitParams sub = prm;
+		sub.bucket = prm.bucket + c0;
+		sub.bucketCount = std::min(chunk, prm.bucketCount - c0);
+		sub.genStride = per;
+		const cudaError_t err = launchOne<RPT, GSMEM, true>(sub, kMax, A, threads, stream, ctas); // same stream: the chunks reuse the scratch in order
+		if (err != cudaSuccess) return err;
+	}
+	return cudaSuccess;
+}
+
 } // namespace
+
+// doubles of global scratch per CTA the per-fit kernel needs for a class of subsets up to kMax columns with A components
+// (0: everything fits in shared memory)
+unsigned long long fitKernelScratchPerCta(int kMax, int A, int maxTasks, int maxBlockLd, int smemLimit) {
+	const int Ak = (A < kMax) ? A : kMax;
+	if (Ak <= kFastComponents && kMax <= kMaxWarps * 32 && fastRowsInSmem(kMax, Ak, maxTasks, maxBlockLd, smemLimit) > 0) return 0ull;
+	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true, roundUp(kMax, 32) / 32).total * 8 <= smemLimit) return 0ull;
+	if (kMax <= 4 * kMaxWarps * 32 && carve(kMax, Ak, false, kMaxWarps).total * 8 <= smemLimit) return 0ull;
+	return genScratchPerCta(kMax, Ak);
+}
 
 int fitKernelSharedBytes(int k, int A) { return carve(k, A, true, roundUp(k, 32) / 32).total * static_cast<int>(sizeof(double)); }
 
@@ -1146,8 +1182,15 @@ cudaError_t launchFitKernel(const FitParams& prm, int kMax, int A, int smemLimit
 	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true, roundUp(kMax, 32) / 32).total * 8 <= smemLimit) {
 		return launchOne<1, true>(prm, kMax, Ak, roundUp(kMax, 32), stream, ctas); // one thread per row
 	}
-	if (kMax > 4 * kMaxWarps * 32 || carve(kMax, Ak, false, kMaxWarps).total * 8 > smemLimit) return cudaErrorInvalidValue;
-	return launchOne<4, false>(prm, kMax, Ak, kMaxWarps * 32, stream, ctas);         // Gram read in place (L2)
+	if (kMax <= 4 * kMaxWarps * 32 && carve(kMax, Ak, false, kMaxWarps).total * 8 <= smemLimit) {
+		return launchOne<4, false>(prm, kMax, Ak, kMaxWarps * 32, stream, ctas);     // Gram read in place (L2)
+	}
+	// many components on a wide subset: the stored loadings and coefficients no longer fit beside the Gram (or at all)
+	if (kMax <= kMaxWarps * 32 && carve(kMax, Ak, true, roundUp(kMax, 32) / 32, true).total * 8 <= smemLimit) {
+		return launchGlobalV<1, true>(prm, kMax, Ak, roundUp(kMax, 32), stream, ctas);
+	}
+	if (kMax > 4 * kMaxWarps * 32 || carve(kMax, Ak, false, kMaxWarps, true).total * 8 > smemLimit) return cudaErrorInvalidValue;
+	return launchGlobalV<4, false>(prm, kMax, Ak, kMaxWarps * 32, stream, ctas);
 }
 
 // The fit-only instance of the fast path (A <= 10 components, k <= 384) serves this class: its coefficients go to

@@ -365,3 +365,23 @@ def test_multi_device_engine_is_bit_identical_to_one_device(engine, oracle_lib):
         f1, s1 = one.evaluate_population(narrow)
         fm, sm = multi.evaluate_population(narrow)
         assert (s1 == sm).all() and (f1 == fm).all()
+
+
+def test_unconstrained_components_on_wide_subsets(engine, oracle_lib):
+    """evaluatorPLS defaults (maxNComp = 0: as many components as the training sets allow, src/PLSEvaluator.cpp:135-138)
+    on subsets of up to 200 columns: 88 components per fit.  The stored loadings and cumulative coefficients (2 k A
+    doubles = 320 KB) no longer fit in shared memory: the generic kernel keeps them in a global scratch and the class is
+    walked in chunks of chromosomes.  Well-conditioned Gaussian data, as SURVEY 8(d) prescribes for unconstrained
+    component counts; against the plain-C oracle (the reference build's stand-in crashes at maxNComp = 0 with n = 150)."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.gaussian(150, 400, seed=21)
+    sv = oracle_lib.make_seedvec(17)
+    subsets = [synth.random_subsets(400, 1, k, k, seed=k)[0] for k in (12, 60, 105, 106, 130, 200)] + synth.random_subsets(400, 6, 20, 200, seed=4)
+    kw = dict(numReplications=2, innerSegments=5)
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=8)
+    with E.PLSEvaluator(X, y, sv, **kw) as ev:
+        assert ev.prepare()["max_ncomp"] > 80  # 88 components: 2 x 200 x 88 doubles = 282 KB of loadings and coefficients
+        fit, status = ev.evaluate_population(subsets)
+        again, _ = ev.evaluate_population(subsets[::-1])
+    assert (status == wstatus).all() and (again[::-1] == fit).all()
+    assert rel_err(fit[wstatus == 0], want[wstatus == 0]).max() <= REL_TOL
