@@ -1039,7 +1039,17 @@ void planBuckets(gsb_engine* e) {
 	e->hCoefOff.reserve(static_cast<size_t>(e->npop) + 1);
 	for (int c = 0; c <= e->npop; ++c) e->hPackOff.ptr[c] = e->hVecOff.ptr[c] = e->hCoefOff.ptr[c] = 0ull;
 	if (!wantFit) return;
-	buildUnitTables(e);
+	try {
+		buildUnitTables(e);
+	} catch (const std::string&) {
+		// the moment tables of the Gram-space path do not fit in device memory (p in the tens of thousands): when the
+		// kernel-space kernel can serve the plan it takes the small subsets too (it needs no tables at all)
+		bool allKspace = kspaceOn && !e->unitsReady;
+		for (size_t b = 0; b < e->buckets.size() && allKspace; ++b) allKspace = e->buckets[b].kernel == BK_KSPACE || e->buckets[b].kernel == BK_FIT;
+		if (!allKspace) throw;
+		for (size_t b = 0; b < e->buckets.size(); ++b) e->buckets[b].kernel = BK_KSPACE;
+		return;
+	}
 	unsigned long long packTotal = 0, vecTotal = 0, coefTotal = 0;
 	for (size_t b = 0; b < e->buckets.size(); ++b) {
 		Bucket& bk = e->buckets[b];

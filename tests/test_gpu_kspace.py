@@ -232,3 +232,21 @@ def test_ill_conditioned_subsets_are_rescored_on_the_gram_space_kernel(engine, o
     assert (s1 == s0).all() and (s1[2:] == wstatus[2:]).all() and np.isfinite(f1).all() and (bits == f1).all()
     assert (f1[:2] == f0[:2]).all()                      # re-scored by the same kernel that GSB_NO_KSPACE selects
     assert rel_err(f1[2:], want[2:]).max() <= REL_TOL   # ordinary subsets: parity as everywhere
+
+
+def test_tables_that_do_not_fit_leave_everything_to_the_kernel_space_kernel(engine, oracle_lib):
+    """p = 60 000 columns, 5 x 3-fold CV: the unit moment tables of the Gram-space path (p (p + 1) / 2 entries x 16 units
+    = 230 GB) do not fit in device memory.  The reference handles any p up to 65535 (src/Control.h:67-68);
+    K1k needs no tables, so it takes the subsets of <= 40 columns as well instead of the call failing with GSB_ERR_MEMORY."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.gaussian(48, 60000, seed=5)
+    sv = oracle_lib.make_seedvec(3)
+    kw = dict(numReplications=5, maxNComp=6, innerSegments=3, outerSegments=3)
+    subsets = synth.random_subsets(60000, 12, 2, 40, seed=8) + synth.random_subsets(60000, 6, 41, 150, seed=9)
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=8)
+    with forced(GSB_NO_KSPACE=None, GSB_KSPACE_MINK=None, GSB_KSPACE_SPLIT=None):
+        with E.PLSEvaluator(X, y, sv, **kw) as ev:
+            fit, status = ev.evaluate_population(subsets)
+            assert ev.info()["gram_bytes"] == 0               # no tables were built
+            assert ev.timing()["kernel_launches"] == 2        # one K1k launch + K2
+    assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL
