@@ -1632,7 +1632,7 @@ static int uploadPopulation(gsb_engine* e, const uint32_t* idx, const uint32_t* 
 		for (uint32_t i = offsets[c]; i < offsets[c + 1]; ++i) {
 			if (idx[i] >= static_cast<uint32_t>(e->p)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "column index out of range");
 		}
-		if (e->cfg.evaluator == GSB_EVAL_LM && k > lmMaxK) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the OLS kernel (k <= min(n - 2, shared-memory limit))");
+		if (e->cfg.evaluator == GSB_EVAL_LM && k > lmMaxK) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the OLS kernel (k <= n - 2)");
 		if (e->cfg.evaluator != GSB_EVAL_LM && k > 1024) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the SIMPLS kernel (k <= 1024)");
 	}
 	e->populationReady = e->resultsReady = false;
@@ -1818,6 +1818,12 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.r2denom = e->r2denom;
 				prm.fitness = e->dFitness.ptr;
 				prm.status = e->dStatus.ptr;
+				// subsets too wide for shared memory (k > ~230): the packed triangle is factorised in a global scratch
+				const unsigned long long per = gsb::olsKernelScratchPerCta(kMax, e->smemLimit);
+				if (per > 0) e->genScratch.reserve(static_cast<size_t>(per * static_cast<unsigned long long>(std::min(count, 2 * std::max(1, e->smCount)))));
+				prm.scratch = e->genScratch.ptr;
+				prm.scratchCapacity = e->genScratch.capacity;
+				prm.scratchStride = 0;
 				GSB_CUDA(gsb::launchOlsKernel(prm, kMax, e->smemLimit, e->stream));
 				ctas += prm.bucketCount;
 				++launches;

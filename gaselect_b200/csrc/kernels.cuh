@@ -211,6 +211,8 @@ struct OlsParams {
 	double r2denom;
 	double* fitness;
 	int* status;
+	double* scratch;                 // subsets too wide for shared memory: the packed triangle is factorised here
+	unsigned long long scratchCapacity, scratchStride;
 };
 
 
@@ -395,6 +397,7 @@ cudaError_t launchKspaceKernel(const KParams& prm, cudaStream_t stream, long lon
 void launchReduceKernel(const ReduceParams& prm, cudaStream_t stream);
 cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream);
 int olsKernelMaxK(int smemLimit);
+unsigned long long olsKernelScratchPerCta(int kMax, int smemLimit);
 void launchMarkEmpty(const uint32_t* offsets, int npop, double* fitness, int* status, cudaStream_t stream);
 void launchLmEmpty(const uint32_t* offsets, int npop, int statistic, int n, double r2denom, double* fitness, int* status, cudaStream_t stream);
 

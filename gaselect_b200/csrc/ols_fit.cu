@@ -10,6 +10,7 @@
 // reports "system could not be solved", src/LMEvaluator.cpp:60-61).
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 
 namespace gsb {
@@ -32,6 +33,9 @@ __device__ __forceinline__ double blockSum1(double v, double* red) {
 	return s;
 }
 
+// GLOB: the packed triangle of a subset too wide for shared memory (k > ~230) is factorised in a global scratch, one region
+// per CTA of the launch (L2-resident while it runs); everything else stays in shared memory
+template <bool GLOB>
 __global__ void __launch_bounds__(kOlsThreads) olsFitKernel(const OlsParams prm) {
 	extern __shared__ __align__(16) double smem[];
 	const int chrom = prm.bucket[blockIdx.x];
@@ -39,8 +43,9 @@ __global__ void __launch_bounds__(kOlsThreads) olsFitKernel(const OlsParams prm)
 	const int k = static_cast<int>(prm.offsets[chrom + 1] - selBegin);
 	const int tid = threadIdx.x;
 	const int ntri = k * (k + 1) / 2;
-	double* __restrict__ L = smem;                         // packed lower triangle, row-major
-	double* __restrict__ rhs = smem + ntri + (ntri & 1);   // s0 -> z -> beta
+	const int ntriS = GLOB ? 0 : ntri;
+	double* __restrict__ L = GLOB ? prm.scratch + static_cast<size_t>(blockIdx.x) * prm.scratchStride : smem; // packed lower triangle, row-major
+	double* __restrict__ rhs = smem + ntriS + (ntriS & 1); // s0 -> z -> beta
 	double* __restrict__ diag0 = rhs + k + (k & 1);
 	double* __restrict__ xms = diag0 + k + (k & 1);
 	double* red = xms + k + (k & 1);
@@ -132,8 +137,8 @@ __global__ void __launch_bounds__(kOlsThreads) olsFitKernel(const OlsParams prm)
 	}
 }
 
-int olsSharedDoubles(int k) {
-	const int ntri = k * (k + 1) / 2;
+int olsSharedDoubles(int k, bool glob = false) {
+	const int ntri = glob ? 0 : k * (k + 1) / 2;
 	return ntri + (ntri & 1) + 3 * (k + (k & 1)) + 8 + (k + 1) / 2 + 1;
 }
 
@@ -141,18 +146,42 @@ int olsSharedDoubles(int k) {
 
 int olsKernelMaxK(int smemLimit) {
 	int k = 1;
-	while (k < 4096 && olsSharedDoubles(k + 1) * 8 <= smemLimit) ++k;
+	while (k < 65535 && olsSharedDoubles(k + 1, true) * 8 <= smemLimit) ++k; // with the triangle in the global scratch
 	return k;
+}
+
+// doubles of global scratch per chromosome for subsets up to kMax columns (0: the triangle fits in shared memory)
+unsigned long long olsKernelScratchPerCta(int kMax, int smemLimit) {
+	if (olsSharedDoubles(kMax) * 8 <= smemLimit) return 0ull;
+	return (static_cast<unsigned long long>(kMax) * (kMax + 1) / 2 + 1ull) & ~1ull;
 }
 
 cudaError_t launchOlsKernel(const OlsParams& prm, int kMax, int smemLimit, cudaStream_t stream) {
 	if (prm.bucketCount <= 0) return cudaSuccess;
-	const size_t bytes = static_cast<size_t>(olsSharedDoubles(kMax)) * sizeof(double);
-	if (static_cast<int>(bytes) > smemLimit) return cudaErrorInvalidValue;
-	cudaError_t err = cudaFuncSetAttribute(olsFitKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+	const unsigned long long per = olsKernelScratchPerCta(kMax, smemLimit);
+	if (per == 0) {
+		const size_t bytes = static_cast<size_t>(olsSharedDoubles(kMax)) * sizeof(double);
+		cudaError_t err = cudaFuncSetAttribute(olsFitKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+		if (err != cudaSuccess) return err;
+		olsFitKernel<false><<<static_cast<unsigned>(prm.bucketCount), kOlsThreads, bytes, stream>>>(prm);
+		return cudaGetLastError();
+	}
+	// the chromosomes of the class in chunks that fit the scratch the engine provides (same stream: reused in order)
+	const size_t bytes = static_cast<size_t>(olsSharedDoubles(kMax, true)) * sizeof(double);
+	if (static_cast<int>(bytes) > smemLimit || prm.scratch == nullptr || prm.scratchCapacity < per) return cudaErrorInvalidValue;
+	cudaError_t err = cudaFuncSetAttribute(olsFitKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 	if (err != cudaSuccess) return err;
-	olsFitKernel<<<static_cast<unsigned>(prm.bucketCount), kOlsThreads, bytes, stream>>>(prm);
-	return cudaGetLastError();
+	const int chunk = static_cast<int>(std::min<unsigned long long>(static_cast<unsigned long long>(prm.bucketCount), prm.scratchCapacity / per));
+	for (int c0 = 0; c0 < prm.bucketCount; c0 += chunk) {
+		OlsParams sub = prm;
+		sub.bucket = prm.bucket + c0;
+		sub.bucketCount = std::min(chunk, prm.bucketCount - c0);
+		sub.scratchStride = per;
+		olsFitKernel<true><<<static_cast<unsigned>(sub.bucketCount), kOlsThreads, bytes, stream>>>(sub);
+		err = cudaGetLastError();
+		if (err != cudaSuccess) return err;
+	}
+	return cudaSuccess;
 }
 
 } // namespace gsb

@@ -385,3 +385,16 @@ def test_unconstrained_components_on_wide_subsets(engine, oracle_lib):
         again, _ = ev.evaluate_population(subsets[::-1])
     assert (status == wstatus).all() and (again[::-1] == fit).all()
     assert rel_err(fit[wstatus == 0], want[wstatus == 0]).max() <= REL_TOL
+
+
+def test_lm_subsets_wider_than_shared_memory(engine, oracle_lib):
+    """LMEvaluator with subsets of up to n - 2 = 298 columns (the reference takes any k <= n - 1, R/validData.R:30-36): above
+    ~230 columns the packed Gram triangle no longer fits in shared memory and K3 factorises it in a global scratch."""
+    from gaselect_b200 import evaluators as E
+    X, y = synth.gaussian(300, 400, seed=12)
+    subsets = [synth.random_subsets(400, 1, k, k, seed=k)[0] for k in (1, 40, 230, 240, 298)] + synth.random_subsets(400, 8, 100, 298, seed=2)
+    for stat in ("BIC", "r.squared"):
+        want, wstatus = oracle_lib.lm_evaluator(X, y, stat).evaluate(subsets, threads=8)
+        with E.LMEvaluator(X, y, stat) as ev:
+            fit, status = ev.evaluate_population(subsets)
+        assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL
