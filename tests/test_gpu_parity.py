@@ -356,6 +356,24 @@ def test_multi_device_engine_is_bit_identical_to_one_device(engine, oracle_lib):
         assert multi.timing()["fit_ctas"] == one.timing()["fit_ctas"] or multi.timing()["fit_ctas"] > 0
         fe, se = multi.evaluate_population([])
         assert len(fe) == 0 and len(se) == 0
+        few = subsets[100:100 + max(1, len(devices) - 1)]  # fewer chromosomes than devices: some replicas get nothing
+        f1c, s1c = one.evaluate_population(few)
+        fmc, smc = multi.evaluate_population(few)
+        assert (s1c == smc).all() and (f1c == fmc).all()
+    # chromosomes the kernel-space kernel declines (rank-deficient: 48 near-copies of 6 columns, 8 components) are re-scored
+    # on the Gram-space kernel of the replica that holds them before the gather
+    rng = np.random.default_rng(4)
+    Xc = X.copy()
+    for j in range(0, 96, 8):
+        for d in range(1, 8):
+            Xc[:, j + d] = Xc[:, j] * (1.0 + 1e-7 * rng.standard_normal(Xc.shape[0]))
+    hard = [np.arange(0, 48, dtype=np.uint32), np.arange(48, 96, dtype=np.uint32)] + [s[s >= 96] for s in subsets[30:60] if (s >= 96).sum() > 45]
+    with E.PLSEvaluator(Xc, y, 123, **kw) as one, E.PLSEvaluator(Xc, y, 123, devices=devices, **kw) as multi:
+        f1, s1 = one.evaluate_population(hard)
+        r1 = one.timing()["retries"]
+        fm, sm = multi.evaluate_population(hard)
+        assert r1 == 2 and multi.timing()["retries"] == 2
+        assert (s1 == sm).all() and (f1 == fm).all() and np.isfinite(fm).all() and not (sm == 5).any()
     narrow = [s for s in subsets if 0 < len(s) <= 60]
     with E.BICEvaluator(X, y, 123, numSegments=5, maxNComp=6) as one, E.BICEvaluator(X, y, 123, numSegments=5, maxNComp=6, devices=devices) as multi:
         f1, s1 = one.evaluate_population(narrow)
