@@ -1626,12 +1626,17 @@ static int uploadPopulation(gsb_engine* e, const uint32_t* idx, const uint32_t* 
 	}
 	// validate the whole CSR before any resident state is touched
 	const int lmMaxK = std::min(gsb::olsKernelMaxK(e->smemLimit), e->n - 2);
+	std::vector<unsigned char> unsortedFlag(static_cast<size_t>(npop), 0);
 	for (int c = 0; c < npop; ++c) {
 		if (offsets[c + 1] < offsets[c]) return fail(e, GSB_ERR_INVALID_ARGUMENT, "population offsets must be non-decreasing");
 		const int k = static_cast<int>(offsets[c + 1] - offsets[c]);
-		for (uint32_t i = offsets[c]; i < offsets[c + 1]; ++i) {
-			if (idx[i] >= static_cast<uint32_t>(e->p)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "column index out of range");
-		}
+		// largest index and sortedness of the list in one branch-free pass (this loop runs over every index of every call)
+		const uint32_t* list = idx + offsets[c];
+		uint32_t largest = 0, descents = 0;
+		for (int i = 0; i < k; ++i) largest = std::max(largest, list[i]);
+		for (int i = 1; i < k; ++i) descents |= static_cast<uint32_t>(list[i] < list[i - 1]);
+		if (k > 0 && largest >= static_cast<uint32_t>(e->p)) return fail(e, GSB_ERR_INVALID_ARGUMENT, "column index out of range");
+		unsortedFlag[static_cast<size_t>(c)] = static_cast<unsigned char>(descents);
 		if (e->cfg.evaluator == GSB_EVAL_LM && k > lmMaxK) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the OLS kernel (k <= n - 2)");
 		if (e->cfg.evaluator != GSB_EVAL_LM && k > 1024) return fail(e, GSB_ERR_INVALID_ARGUMENT, "subset too large for the SIMPLS kernel (k <= 1024)");
 	}
@@ -1647,27 +1652,39 @@ static int uploadPopulation(gsb_engine* e, const uint32_t* idx, const uint32_t* 
 		e->hOffsets.reserve(static_cast<size_t>(npop) + 1);
 		e->hBucket.reserve(static_cast<size_t>(npop) + 1);
 		int kMaxPop = 0;
+		if (total > 0) std::memcpy(e->hIdx.ptr, idx, total * sizeof(uint32_t));
 		for (int c = 0; c < npop; ++c) {
 			const uint32_t b = offsets[c], en = offsets[c + 1];
-			bool sorted = true;
-			for (uint32_t i = b; i < en; ++i) {
-				const uint32_t v = idx[i];
-				if (i > b && v < idx[i - 1]) sorted = false;
-				e->hIdx.ptr[i] = v;
-			}
-			if (!sorted) std::sort(e->hIdx.ptr + b, e->hIdx.ptr + en); // the fit does not depend on the column order
+			if (unsortedFlag[static_cast<size_t>(c)]) std::sort(e->hIdx.ptr + b, e->hIdx.ptr + en); // the fit does not depend on the column order
 			e->hOffsets.ptr[c] = b;
 			kMaxPop = std::max(kMaxPop, static_cast<int>(en - b));
 		}
 		e->hOffsets.ptr[npop] = static_cast<uint32_t>(total);
 
-		// counting sort of the non-empty chromosomes into subset-size classes
+		// counting sort of the non-empty chromosomes into subset-size classes (stable: caller order inside a class)
 		std::vector<int> order;
-		order.reserve(static_cast<size_t>(npop));
-		for (int c = 0; c < npop; ++c) if (offsets[c + 1] > offsets[c]) order.push_back(c);
-		std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-			return bucketCeil(static_cast<int>(offsets[a + 1] - offsets[a])) < bucketCeil(static_cast<int>(offsets[b + 1] - offsets[b]));
-		});
+		if (kMaxPop > 1024) { // (LM subsets may be wider than the SIMPLS kernels take: no table of classes for those)
+			order.reserve(static_cast<size_t>(npop));
+			for (int c = 0; c < npop; ++c) if (offsets[c + 1] > offsets[c]) order.push_back(c);
+			std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+				return bucketCeil(static_cast<int>(offsets[a + 1] - offsets[a])) < bucketCeil(static_cast<int>(offsets[b + 1] - offsets[b]));
+			});
+		} else {
+			int classCount[80] = {0}; // classes: multiples of 8 up to 64, of 16 up to 256, of 32 up to 1024
+			auto classOf = [](int k) { return k <= 64 ? (k + 7) / 8 : (k <= 256 ? 8 + (k - 64 + 15) / 16 : 20 + (k - 256 + 31) / 32); };
+			int live = 0;
+			for (int c = 0; c < npop; ++c) {
+				const int k = static_cast<int>(offsets[c + 1] - offsets[c]);
+				if (k > 0) { ++classCount[classOf(k)]; ++live; }
+			}
+			int start[80];
+			for (int i = 0, at = 0; i < 80; ++i) { start[i] = at; at += classCount[i]; }
+			order.assign(static_cast<size_t>(live), 0);
+			for (int c = 0; c < npop; ++c) {
+				const int k = static_cast<int>(offsets[c + 1] - offsets[c]);
+				if (k > 0) order[static_cast<size_t>(start[classOf(k)]++)] = c;
+			}
+		}
 		e->buckets.clear();
 		for (size_t i = 0; i < order.size(); ++i) {
 			const int k = static_cast<int>(offsets[order[i] + 1] - offsets[order[i]]);
