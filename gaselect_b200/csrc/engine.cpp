@@ -45,16 +45,35 @@ struct CudaFailure {
 		if (err__ != cudaSuccess) throw CudaFailure{err__, #expr, __FILE__, __LINE__}; \
 	} while (0)
 
+// GSB_GUARD=1 (read when the first engine is created): every device array gets a 256-byte guard zone behind its last
+// element, filled with a pattern; gsb_population_evaluate / download check all of them (and the shared-memory canaries of
+// the K1 kernels) and fail with GSB_ERR_CUDA when one was overwritten.  compute-sanitizer is not available on the pool
+// this was developed on: this is the engine's own evidence against out-of-bounds WRITES (tests/test_gpu_guard.py).
+bool g_guard = false;
+constexpr size_t kGuardBytes = 256;
+constexpr unsigned char kGuardByte = 0xA5;
+
 template <class T>
 struct DeviceArray {
 	T* ptr = nullptr;
 	size_t capacity = 0; // elements
+	bool guarded = false;
 	void reserve(size_t count) {
 		if (count <= capacity) return;
 		release();
 		const size_t want = std::max<size_t>(count, 16);
-		GSB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T)));
+		GSB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T) + (g_guard ? kGuardBytes : 0)));
 		capacity = want;
+		guarded = g_guard;
+		if (guarded) GSB_CUDA(cudaMemset(reinterpret_cast<unsigned char*>(ptr) + want * sizeof(T), kGuardByte, kGuardBytes));
+	}
+	// true when the guard zone still holds its pattern (or there is none)
+	bool guardIntact() const {
+		if (!ptr || !guarded) return true;
+		unsigned char host[kGuardBytes];
+		if (cudaMemcpy(host, reinterpret_cast<const unsigned char*>(ptr) + capacity * sizeof(T), kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+		for (size_t i = 0; i < kGuardBytes; ++i) if (host[i] != kGuardByte) return false;
+		return true;
 	}
 	void release() {
 		if (ptr) cudaFree(ptr);
@@ -304,6 +323,7 @@ struct gsb_engine {
 	// chromosomes K1k declines (ill-conditioned: it takes |v|^2 by subtraction) are scored again on the Gram-space kernel by
 	// a child engine without K1k, created the first time it is needed (resolveRetries)
 	DeviceArray<int> dRefit;
+	DeviceArray<int> dGuardFail;   // GSB_GUARD: shared-memory canaries the K1 kernels found overwritten
 	bool refitArmed = false;       // the most recent enqueue ran K1k: its results may hold kStatusRetry
 	gsb_engine* retryEngine = nullptr;
 	bool forceNoKspace = false;    // this IS such a child engine
@@ -347,7 +367,7 @@ void releaseDevice(gsb_engine* e) {
 	e->xz.release(); e->scoreScratch.release(); e->xReps.release(); e->xGroups8.release(); e->xGroups16.release(); e->xFits.release(); e->xTasks.release();
 	e->kFits.release(); e->kTasks.release();
 	for (int i = 0; i <= gsb_engine::kMaxSplit; ++i) { e->kSchedules[i].fitOrder.release(); e->kSchedules[i].parts.release(); e->kSchedules[i].ready = false; }
-	e->kSched.release(); e->kProducts.release(); e->dRefit.release();
+	e->kSched.release(); e->kProducts.release(); e->dRefit.release(); e->dGuardFail.release();
 	e->kSchedNf = -1;
 	e->dIdx.release(); e->dOffsets.release(); e->dBucket.release(); e->dStatus.release();
 	e->dMse.release(); e->dOstat.release(); e->dFitness.release();
@@ -382,7 +402,7 @@ void ensureDevice(gsb_engine* e) {
 	cudaDeviceProp prop;
 	GSB_CUDA(cudaGetDeviceProperties(&prop, e->cfg.device));
 	e->smCount = prop.multiProcessorCount;
-	e->smemLimit = static_cast<int>(prop.sharedMemPerBlockOptin);
+	e->smemLimit = static_cast<int>(prop.sharedMemPerBlockOptin) - (g_guard ? 64 : 0); // GSB_GUARD: room for the kernels' canaries
 	GSB_CUDA(cudaStreamCreateWithFlags(&e->ownStream, cudaStreamNonBlocking));
 	if (!e->callerStream) e->stream = e->ownStream;
 	for (int i = 0; i < 6; ++i) GSB_CUDA(cudaEventCreate(&e->ev[i]));
@@ -1154,6 +1174,7 @@ std::string deriveShape(gsb_engine* e, std::vector<gsb::RowSet>& seg, const uint
 // device -> one copy to pinned host memory -> un-permute into the caller's order.
 
 int resolveRetries(gsb_engine* e); // below, next to the download
+std::string checkGuards(gsb_engine* e);
 
 int failFrom(gsb_engine* e, int rc, const gsb_engine* child, int dev) {
 	char buf[768];
@@ -1406,6 +1427,7 @@ int gsb_create(gsb_engine** out, const gsb_config* cfg) {
 	}
 	gsb_engine* e = new (std::nothrow) gsb_engine();
 	if (!e) return fail(nullptr, GSB_ERR_MEMORY, "host allocation failed");
+	g_guard = std::getenv("GSB_GUARD") != nullptr; // (arrays remember whether they were allocated with a guard zone)
 	e->cfg = *cfg;
 	if (cfg->num_devices == 1) e->cfg.device = cfg->devices[0];
 	if (cfg->num_devices > 1) {
@@ -1939,6 +1961,8 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				kp.products = e->kProducts.ptr;
 				e->dRefit.reserve(static_cast<size_t>(e->npop));
 				kp.refit = e->dRefit.ptr;
+				if (g_guard && !e->dGuardFail.ptr) { e->dGuardFail.reserve(1); GSB_CUDA(cudaMemset(e->dGuardFail.ptr, 0, sizeof(int))); }
+				kp.guardFail = e->dGuardFail.ptr;
 				e->refitArmed = true;
 				GSB_CUDA(cudaMemsetAsync(e->dRefit.ptr, 0, static_cast<size_t>(e->npop) * sizeof(int), launchStream));
 				GSB_CUDA(cudaMemsetAsync(e->kProducts.ptr, 0, sizeof(unsigned long long), launchStream));
@@ -2037,6 +2061,8 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 				prm.genScratch = e->genScratch.ptr;
 				prm.genCapacity = e->genScratch.capacity;
 				prm.genStride = 0;
+				if (g_guard && !e->dGuardFail.ptr) { e->dGuardFail.reserve(1); GSB_CUDA(cudaMemset(e->dGuardFail.ptr, 0, sizeof(int))); }
+				prm.guardFail = e->dGuardFail.ptr;
 				if (bk.split) {
 					GSB_CUDA(gsb::launchFitOnlyKernel(prm, bk.kMax, e->tableA, e->smemLimit, launchStream, &ctas));
 					gsb::PredictParams pr;
@@ -2099,6 +2125,31 @@ void enqueuePopulation(gsb_engine* e, long long& ctas, int& launches) {
 			++launches;
 			GSB_CUDA(cudaEventRecord(e->ev[4], e->stream));
 		}
+}
+
+// GSB_GUARD: every device array's guard zone and the kernels' shared-memory canaries; "" or what was overwritten
+std::string checkGuards(gsb_engine* e) {
+	if (!g_guard) return "";
+	std::string bad;
+#define GSB_CHECK_GUARD(member) do { if (!e->member.guardIntact()) bad += std::string(bad.empty() ? "" : ", ") + #member; } while (0)
+	GSB_CHECK_GUARD(zpool); GSB_CHECK_GUARD(gram); GSB_CHECK_GUARD(s0); GSB_CHECK_GUARD(xm); GSB_CHECK_GUARD(fits); GSB_CHECK_GUARD(tasks);
+	GSB_CHECK_GUARD(blocks); GSB_CHECK_GUARD(outerRows); GSB_CHECK_GUARD(unitTab); GSB_CHECK_GUARD(unitSum); GSB_CHECK_GUARD(unitXy);
+	GSB_CHECK_GUARD(packFits); GSB_CHECK_GUARD(gpack); GSB_CHECK_GUARD(pvec); GSB_CHECK_GUARD(dPackOff); GSB_CHECK_GUARD(dVecOff);
+	GSB_CHECK_GUARD(dCoefOff); GSB_CHECK_GUARD(coefScratch); GSB_CHECK_GUARD(genScratch); GSB_CHECK_GUARD(activeBlocks);
+	GSB_CHECK_GUARD(blockTaskOff); GSB_CHECK_GUARD(predTasks); GSB_CHECK_GUARD(dIdx); GSB_CHECK_GUARD(dOffsets); GSB_CHECK_GUARD(dBucket);
+	GSB_CHECK_GUARD(dStatus); GSB_CHECK_GUARD(dMse); GSB_CHECK_GUARD(dOstat); GSB_CHECK_GUARD(dFitness); GSB_CHECK_GUARD(xz);
+	GSB_CHECK_GUARD(scoreScratch); GSB_CHECK_GUARD(xReps); GSB_CHECK_GUARD(xGroups8); GSB_CHECK_GUARD(xGroups16); GSB_CHECK_GUARD(xFits);
+	GSB_CHECK_GUARD(xTasks); GSB_CHECK_GUARD(kFits); GSB_CHECK_GUARD(kTasks); GSB_CHECK_GUARD(kSched); GSB_CHECK_GUARD(kProducts);
+	GSB_CHECK_GUARD(dRefit); GSB_CHECK_GUARD(traceBuf);
+	for (int i = 0; i <= gsb_engine::kMaxSplit; ++i) { GSB_CHECK_GUARD(kSchedules[i].fitOrder); GSB_CHECK_GUARD(kSchedules[i].parts); }
+#undef GSB_CHECK_GUARD
+	if (e->dGuardFail.ptr) {
+		int fails = 0;
+		if (cudaMemcpy(&fails, e->dGuardFail.ptr, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && fails != 0) {
+			bad += std::string(bad.empty() ? "" : ", ") + "shared-memory canary of a K1 kernel (" + std::to_string(fails) + " CTAs)";
+		}
+	}
+	return bad;
 }
 
 // Chromosomes the kernel-space kernel declined (kStatusRetry in hStatus[0 .. npop)): scored again by a child engine that
@@ -2205,6 +2256,8 @@ int gsb_population_evaluate(gsb_engine* e) {
 		e->timing.fit_ctas = ctas;
 		e->timing.kernel_launches = launches;
 		e->resultsReady = true;
+		const std::string overwritten = checkGuards(e);
+		if (!overwritten.empty()) return fail(e, GSB_ERR_CUDA, "GSB_GUARD: out-of-bounds write behind " + overwritten);
 	} catch (const CudaFailure& f) {
 		return failCuda(e, f);
 	}
@@ -2259,6 +2312,8 @@ static int downloadResults(gsb_engine* e, double* fitness, int32_t* status, bool
 			const int rc = resolveRetries(e);
 			if (rc != GSB_OK) return rc;
 		}
+		const std::string overwritten = checkGuards(e);
+		if (!overwritten.empty()) return fail(e, GSB_ERR_CUDA, "GSB_GUARD: out-of-bounds write behind " + overwritten);
 		std::memcpy(fitness, e->hFitness.ptr, np * sizeof(double));
 		for (size_t i = 0; i < np; ++i) status[i] = e->hStatus.ptr[i];
 	} catch (const CudaFailure& f) {
@@ -2469,6 +2524,7 @@ int gsb_simpls(gsb_engine* e, const uint32_t* cols, int32_t k, const uint32_t* r
 		const unsigned long long genPer = gsb::fitKernelScratchPerCta(k, A, 0, 0, e->smemLimit);
 		if (genPer > 0) dGen.reserve(static_cast<size_t>(genPer));
 		prm.genScratch = dGen.ptr; prm.genCapacity = dGen.capacity; prm.genStride = 0;
+		prm.guardFail = nullptr;
 		GSB_CUDA(gsb::launchFitKernel(prm, k, A, e->smemLimit, e->stream, nullptr));
 		std::vector<double> out(static_cast<size_t>(k) * A + A);
 		GSB_CUDA(cudaMemcpyAsync(out.data(), dOut.ptr, out.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));

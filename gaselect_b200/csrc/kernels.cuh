@@ -85,6 +85,7 @@ struct FitParams {
 	// genStride doubles per CTA of a launch (launchFitKernel walks the class in chunks of chromosomes that fit genCapacity)
 	double* genScratch;
 	unsigned long long genCapacity, genStride;
+	int* guardFail;                    // GSB_GUARD (fast-path instances): shared-memory canary, as in KParams
 };
 
 // ---- K1p (predict_blocks.cu): held-out prediction of the per-fit path, one CTA per (held-out block, chromosome) ----
@@ -335,6 +336,7 @@ struct KParams {
 	int schedStride;
 	unsigned long long* products; // += column tiles x products this launch issued (FP64 tensor work actually done)
 	int* refit;                   // per chromosome: set when a fit lost orthogonality (v'v by subtraction) or seemed to underflow
+	int* guardFail;               // GSB_GUARD: != nullptr: 64 bytes of canary behind the CTA's shared memory, counted here when overwritten
 };
 
 // status K2 gives a chromosome the kernel-space kernel marked in KParams::refit (GSB_STATUS_RETRY of the C ABI): the

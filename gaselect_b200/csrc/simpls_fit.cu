@@ -684,6 +684,17 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 	int phase = 0;
 	__shared__ __align__(8) uint64_t gramBar;
 
+	// GSB_GUARD: a canary behind the carve (the launch asks for 64 bytes more), checked where the CTA leaves
+	constexpr unsigned long long kCanary = 0xA5C3A5C3A5C3A5C3ull;
+	unsigned long long* canary = reinterpret_cast<unsigned long long*>(smem + cv.total);
+	if (prm.guardFail != nullptr && tid < 8) canary[tid] = kCanary;
+	auto checkCanary = [&]() {
+		if (prm.guardFail != nullptr) {
+			__syncthreads();
+			if (tid < 8 && canary[tid] != kCanary) atomicAdd(prm.guardFail, 1);
+		}
+	};
+
 	const bool tracing = TRACE && prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
 	int stamp = 0;
 #define GSB_STAMP() do { if (TRACE && tracing) prm.trace[stamp++] = clock64(); } while (0)
@@ -800,6 +811,7 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 			}
 		}
 		GSB_STAMP();
+		checkCanary();
 		return;
 	}
 
@@ -1061,6 +1073,7 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 			GSB_STAMP(); // one per prediction task
 		}
 	}
+	checkCanary();
 #undef GSB_STAMP
 }
 
@@ -1088,7 +1101,7 @@ cudaError_t launchFast(const FitParams& prm, int kMax, int A, int smemLimit, cud
 	const int rs = PRED ? fastRowsInSmem(kMax, A, prm.maxTasks, prm.maxBlockLd, smemLimit) : fitOnlyRowsInSmem(kMax, smemLimit);
 	if (rs <= 0) return cudaErrorInvalidValue;
 	const FastCarve cv = PRED ? fastCarve(kMax, A, threads / 32, prm.maxTasks, prm.maxBlockLd, -1, rs) : fitOnlyCarve(kMax, threads / 32, rs);
-	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double);
+	const size_t bytes = static_cast<size_t>(cv.total) * sizeof(double) + (prm.guardFail != nullptr ? 64 : 0);
 	const long long grid = static_cast<long long>(prm.nfits) * prm.bucketCount;
 	if (grid <= 0) return cudaSuccess;
 	if (grid > 2147483647LL) return cudaErrorInvalidConfiguration;

@@ -517,6 +517,10 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	const int total = pd.n0 + pd.n1;
 	if (total == 0) return;
 
+	// GSB_GUARD: a canary behind the carve (the launch asks for 64 bytes more); checked at the single exit below
+	constexpr unsigned long long kCanary = 0xA5C3A5C3A5C3A5C3ull;
+	unsigned long long* canary = reinterpret_cast<unsigned long long*>(smem + cv.total);
+	if (prm.guardFail != nullptr && tid < 8) canary[tid] = kCanary;
 	const bool tracing = TRACE && prm.trace != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
 	int stamp = 0;
 #define GSB_KSTAMP() do { if (tracing && stamp < 64) prm.trace[stamp++] = clock64(); } while (0)
@@ -734,6 +738,10 @@ __global__ void __launch_bounds__(32 * NF, 1) simplsKspaceKernel(const KParams p
 	}
 #undef GSB_KSTAMP
 	if (tid == 0 && prm.products != nullptr) atomicAdd(prm.products, nprod);
+	if (prm.guardFail != nullptr) {
+		__syncthreads();
+		if (tid < 8 && canary[tid] != kCanary) atomicAdd(prm.guardFail, 1);
+	}
 	if (NF != 8) {
 		__syncthreads();
 		if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmemBase));
@@ -765,7 +773,7 @@ static cudaError_t launchKspaceOne(const KParams& prm, int bytes, long long grid
 }
 
 cudaError_t launchKspaceKernel(const KParams& prm, cudaStream_t stream, long long* ctas) {
-	const int bytes = kspaceKernelSharedBytes(prm.n, prm.nf);
+	const int bytes = kspaceKernelSharedBytes(prm.n, prm.nf) + (prm.guardFail != nullptr ? 64 : 0);
 	const long long grid = static_cast<long long>(prm.fullCount) + static_cast<long long>(prm.bucketCount - prm.fullCount) * prm.tailSplit;
 	if (prm.bucketCount <= 0) return cudaSuccess;
 	if (grid > 2147483647LL || prm.tailSplit < 1 || prm.fullCount < 0 || prm.fullCount > prm.bucketCount || (prm.nf != 8 && prm.nf != 16)) return cudaErrorInvalidConfiguration;
