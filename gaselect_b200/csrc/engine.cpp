@@ -217,6 +217,8 @@ struct MultiState {
 	int* hStatus = nullptr;
 	size_t capacity = 0;
 	cudaStream_t stream = nullptr;               // on devices[0]
+	std::vector<double> gatherF;                 // gsb_evaluate_indices: the replicas' results back to back (host)
+	std::vector<int32_t> gatherS;
 	~MultiState() { delete pool; }
 };
 
@@ -1241,7 +1243,8 @@ void multiReleaseGather(gsb_engine* e) {
 	ms->capacity = 0;
 }
 
-int multiUpload(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop) {
+// deal + the per-device CSR lists of one batch (ms->shares / idx / off / first)
+int multiDeal(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop) {
 	MultiState* ms = e->multi;
 	const int ndev = static_cast<int>(e->replicas.size());
 	ms->populationReady = ms->resultsReady = false;
@@ -1249,34 +1252,130 @@ int multiUpload(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int
 		if (offsets[c + 1] < offsets[c]) return fail(e, GSB_ERR_INVALID_ARGUMENT, "population offsets must be non-decreasing");
 	}
 	// the replicas must be prepared before the deal: the cost model depends on which kernels the plan admits
-	int rc = onReplicas(e, [](gsb_engine* r) { return gsb_prepare(r); });
-	if (rc != GSB_OK) return rc;
+	bool allPrepared = true;
+	for (int d = 0; d < ndev; ++d) allPrepared = allPrepared && e->replicas[static_cast<size_t>(d)]->prepared;
+	if (!allPrepared) {
+		const int rc = onReplicas(e, [](gsb_engine* r) { return gsb_prepare(r); });
+		if (rc != GSB_OK) return rc;
+	}
 	std::vector<int> deviceOf;
 	dealPopulation(offsets, npop, ndev, multiUsesKspace(e), deviceOf);
-	ms->shares.assign(static_cast<size_t>(ndev), std::vector<int>());
-	ms->idx.assign(static_cast<size_t>(ndev), std::vector<uint32_t>());
-	ms->off.assign(static_cast<size_t>(ndev), std::vector<uint32_t>(1, 0u));
-	for (int c = 0; c < npop; ++c) {
-		const size_t d = static_cast<size_t>(deviceOf[static_cast<size_t>(c)]);
-		ms->shares[d].push_back(c);
-		ms->idx[d].insert(ms->idx[d].end(), idx + offsets[c], idx + offsets[c + 1]);
-		ms->off[d].push_back(static_cast<uint32_t>(ms->idx[d].size()));
-	}
+	ms->shares.resize(static_cast<size_t>(ndev));
+	ms->idx.resize(static_cast<size_t>(ndev));
+	ms->off.resize(static_cast<size_t>(ndev));
+	for (int d = 0; d < ndev; ++d) ms->shares[static_cast<size_t>(d)].clear(); // clear, not assign: the capacities of the last batch are kept
+	for (int c = 0; c < npop; ++c) ms->shares[static_cast<size_t>(deviceOf[static_cast<size_t>(c)])].push_back(c);
 	ms->first.assign(static_cast<size_t>(ndev) + 1, 0);
 	for (int d = 0; d < ndev; ++d) {
 		ms->first[static_cast<size_t>(d) + 1] = ms->first[static_cast<size_t>(d)] + static_cast<int>(ms->shares[static_cast<size_t>(d)].size());
-		if (ms->idx[static_cast<size_t>(d)].empty()) ms->idx[static_cast<size_t>(d)].push_back(0u);
 	}
 	ms->npop = npop;
+	return GSB_OK;
+}
+
+// the CSR lists of device d's share, copied out of the caller's arrays (on that device's thread: at 20 000 chromosomes
+// of 200 columns the lists are 16 MB)
+void multiBuildShare(MultiState* ms, size_t d, const uint32_t* idx, const uint32_t* offsets) {
+	std::vector<uint32_t>& di = ms->idx[d];
+	std::vector<uint32_t>& dof = ms->off[d];
+	const std::vector<int>& sh = ms->shares[d];
+	size_t total = 0;
+	for (size_t i = 0; i < sh.size(); ++i) total += offsets[sh[i] + 1] - offsets[sh[i]];
+	di.resize(std::max<size_t>(total, 1));
+	dof.resize(sh.size() + 1);
+	dof[0] = 0u;
+	size_t at = 0;
+	for (size_t i = 0; i < sh.size(); ++i) {
+		const size_t len = offsets[sh[i] + 1] - offsets[sh[i]];
+		if (len) std::memcpy(di.data() + at, idx + offsets[sh[i]], len * sizeof(uint32_t));
+		at += len;
+		dof[i + 1] = static_cast<uint32_t>(at);
+	}
+	if (total == 0) di[0] = 0u;
+}
+
+int multiFailed(gsb_engine* e, int rc, const char* what) {
+	for (size_t d = 0; d < e->replicas.size(); ++d) if (!e->replicas[d]->error.empty()) return failFrom(e, rc, e->replicas[d], e->cfg.devices[d]);
+	return fail(e, rc, what);
+}
+
+void multiCollectTiming(gsb_engine* e) {
+	gsb_timing& t = e->timing;
+	std::memset(&t, 0, sizeof(t));
+	for (size_t d = 0; d < e->replicas.size(); ++d) {
+		const gsb_timing& c = e->replicas[d]->timing;
+		if (e->replicas[d]->npop == 0) continue;
+		t.h2d_ms = std::max(t.h2d_ms, c.h2d_ms);
+		t.fit_kernel_ms = std::max(t.fit_kernel_ms, c.fit_kernel_ms);
+		t.reduce_kernel_ms = std::max(t.reduce_kernel_ms, c.reduce_kernel_ms);
+		t.d2h_ms = std::max(t.d2h_ms, c.d2h_ms);
+		t.total_ms = std::max(t.total_ms, c.total_ms);
+		t.fit_ctas += c.fit_ctas;
+		t.kernel_launches += c.kernel_launches;
+		t.fit_tensor_gflop += c.fit_tensor_gflop;
+		t.retries += c.retries;
+	}
+}
+
+int multiUpload(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop) {
+	MultiState* ms = e->multi;
+	int rc = multiDeal(e, idx, offsets, npop);
+	if (rc != GSB_OK) return rc;
 	rc = e->multi->pool->run([&](int i) {
 		const size_t d = static_cast<size_t>(i);
+		try {
+			multiBuildShare(ms, d, idx, offsets);
+		} catch (const std::bad_alloc&) {
+			return fail(e->replicas[d], GSB_ERR_MEMORY, "host allocation failed");
+		}
 		return gsb_population_upload(e->replicas[d], ms->idx[d].data(), ms->off[d].data(), static_cast<int32_t>(ms->shares[d].size()));
 	}, nullptr);
-	if (rc != GSB_OK) {
-		for (int d = 0; d < ndev; ++d) if (!e->replicas[static_cast<size_t>(d)]->error.empty()) return failFrom(e, rc, e->replicas[static_cast<size_t>(d)], e->cfg.devices[d]);
-		return fail(e, rc, "population upload failed");
-	}
+	if (rc != GSB_OK) return multiFailed(e, rc, "population upload failed");
 	ms->populationReady = true;
+	return GSB_OK;
+}
+
+// gsb_evaluate_indices on a multi-device engine: deal, then ONE hand-over to the device threads -- every replica runs
+// its whole single-device call (upload, kernels, re-scoring of declined chromosomes, download into its slice of the
+// gathered host vectors) -- and the un-permutation into the caller's order.  (The resident-population entry points
+// gather through device 0 instead, so that gsb_population_device_results has something to point at... on one device;
+// this path needs no copy between GPUs and a third of the hand-overs: 0.96 -> see profiles/README.md per 500 chromosomes.)
+int multiEvaluateIndices(gsb_engine* e, const uint32_t* idx, const uint32_t* offsets, int32_t npop, double* fitness, int32_t* status) {
+	MultiState* ms = e->multi;
+	int rc = multiDeal(e, idx, offsets, npop);
+	if (rc != GSB_OK) return rc;
+	if (npop == 0) return GSB_OK;
+	try {
+		ms->gatherF.resize(static_cast<size_t>(npop));
+		ms->gatherS.resize(static_cast<size_t>(npop));
+	} catch (const std::bad_alloc&) {
+		return fail(e, GSB_ERR_MEMORY, "host allocation failed");
+	}
+	rc = ms->pool->run([&](int i) {
+		const size_t d = static_cast<size_t>(i);
+		gsb_engine* r = e->replicas[d];
+		const int32_t cnt = static_cast<int32_t>(ms->shares[d].size());
+		if (cnt == 0) { r->npop = 0; return static_cast<int>(GSB_OK); }
+		try {
+			multiBuildShare(ms, d, idx, offsets);
+		} catch (const std::bad_alloc&) {
+			return fail(r, GSB_ERR_MEMORY, "host allocation failed");
+		}
+		const size_t at = static_cast<size_t>(ms->first[d]);
+		return gsb_evaluate_indices(r, ms->idx[d].data(), ms->off[d].data(), cnt, ms->gatherF.data() + at, ms->gatherS.data() + at);
+	}, nullptr);
+	if (rc != GSB_OK) return multiFailed(e, rc, "evaluation failed");
+	for (size_t d = 0; d < e->replicas.size(); ++d) {
+		const std::vector<int>& sh = ms->shares[d];
+		const size_t at = static_cast<size_t>(ms->first[d]);
+		for (size_t i = 0; i < sh.size(); ++i) {
+			fitness[sh[i]] = ms->gatherF[at + i];
+			status[sh[i]] = ms->gatherS[at + i];
+		}
+	}
+	multiCollectTiming(e);
+	ms->populationReady = true; // every replica holds its share and its results: gsb_population_download works afterwards
+	ms->resultsReady = true;
 	return GSB_OK;
 }
 
@@ -1296,19 +1395,7 @@ int multiEvaluate(gsb_engine* e, bool synchronous) {
 		}
 	}
 	if (rc != GSB_OK) return rc;
-	gsb_timing& t = e->timing;
-	std::memset(&t, 0, sizeof(t));
-	for (size_t d = 0; d < e->replicas.size(); ++d) {
-		const gsb_timing& c = e->replicas[d]->timing;
-		if (e->replicas[d]->npop == 0) continue;
-		t.h2d_ms = std::max(t.h2d_ms, c.h2d_ms);
-		t.fit_kernel_ms = std::max(t.fit_kernel_ms, c.fit_kernel_ms);
-		t.reduce_kernel_ms = std::max(t.reduce_kernel_ms, c.reduce_kernel_ms);
-		t.total_ms = std::max(t.total_ms, c.total_ms);
-		t.fit_ctas += c.fit_ctas;
-		t.kernel_launches += c.kernel_launches;
-		t.fit_tensor_gflop += c.fit_tensor_gflop;
-	}
+	multiCollectTiming(e);
 	ms->resultsReady = true;
 	return GSB_OK;
 }
@@ -2352,6 +2439,7 @@ int gsb_evaluate_indices(gsb_engine* e, const uint32_t* idx, const uint32_t* off
 		}
 		return downloadResults(e, fitness, status, true);
 	}
+	if (e && !e->replicas.empty() && offsets && npop > 0 && idx && fitness && status) return multiEvaluateIndices(e, idx, offsets, npop, fitness, status);
 	int rc = gsb_population_upload(e, idx, offsets, npop);
 	if (rc != GSB_OK) return rc;
 	if (npop == 0) return GSB_OK;

@@ -10,8 +10,9 @@
  * src/PLS.h:100-103): one engine per host thread.  An engine drives one GPU, or -- with
  * gsb_config.num_devices > 1 -- several GPUs of the node from ONE process: every batch is dealt to
  * per-device replicas (longest-processing-time-first on the kernels' cost model, equal counts), the
- * replicas run concurrently on their own CUDA contexts, and the fitness / status vectors are
- * gathered with peer copies.  That is the role the numThreads slice deal plays in the reference
+ * replicas run concurrently on their own CUDA contexts (one persistent host thread each), and the
+ * fitness / status vectors are gathered (on the host by gsb_evaluate_*, with peer copies by the
+ * resident-population calls).  That is the role the numThreads slice deal plays in the reference
  * (src/MultiThreadedPopulation.cpp:260-262,301-323, selected at src/GenAlg.cpp:173-181).
  *
  * There is no CPU fallback: every evaluate call runs hand-written sm_100a CUDA kernels and

@@ -1,16 +1,20 @@
-"""BASELINE config 5: single-generation fitness throughput sweep, population x mean subset size, one GPU.
-usage: python profiles/sweep.py [--quick]   (config-3 data and CV; subset sizes k ~ round(U(0.5,1.5) * kbar))"""
+"""BASELINE config 5: single-generation fitness throughput sweep, population x mean subset size, on one GPU or on the
+multi-device engine of the C ABI (one process, --devices N: every generation dealt over N GPUs, device time = the
+slowest GPU's kernels).
+usage: python profiles/sweep.py [--quick] [--devices N]   (config-3 data and CV; subset sizes k ~ round(U(0.5,1.5) * kbar))"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from gaselect_b200 import synth, evaluators as E, _capi
 
 quick = "--quick" in sys.argv
+ndev = int(sys.argv[sys.argv.index("--devices") + 1]) if "--devices" in sys.argv else 1
 X, y = synth.nir_spectra(150, 1000, seed=777)
-ev = E.PLSEvaluator(X, y, 123, numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5)
+ev = E.PLSEvaluator(X, y, 123, numReplications=10, maxNComp=10, innerSegments=4, outerSegments=5,
+                    devices=list(range(ndev)) if ndev > 1 else None)
 ev.prepare()
 pops = [100, 500, 2000] if quick else [100, 500, 2000, 5000, 20000]
-print("device evals/s (K1+K2, population resident) | e2e evals/s (host buffers in, fitness out)")
+print("%d GPU(s): device evals/s (K1+K2, population resident) | e2e evals/s (host buffers in, fitness out)" % ndev)
 print("%8s" % "pop\\kbar" + "".join("%22d" % kb for kb in (10, 20, 50, 100, 200)))
 for pop in pops:
     row = "%8d" % pop

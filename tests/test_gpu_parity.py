@@ -335,7 +335,7 @@ def test_multi_device_engine_is_bit_identical_to_one_device(engine, oracle_lib):
     peer copies: bit-identical fitness and status to the single-device engine, for PLS_CV (kernel-space kernel and per-fit
     kernel classes, an empty subset, a repeated call with another batch), PLS_FIT and LM."""
     from conftest import cuda_device_count
-    from gaselect_b200 import evaluators as E
+    from gaselect_b200 import evaluators as E, _capi
     ndev = cuda_device_count()
     if ndev < 2:
         pytest.skip("needs at least 2 CUDA devices")
@@ -351,6 +351,17 @@ def test_multi_device_engine_is_bit_identical_to_one_device(engine, oracle_lib):
         f1b, s1b = one.evaluate_population(subsets[::3])
         fmb, smb = multi.evaluate_population(subsets[::3])
         assert (s1b == smb).all() and (f1b == fmb).all() and (f1b == f1[::3]).all()
+        # the resident-population entry points (gather by peer copies through the first device) against the one-call path
+        # (every replica downloads its own share), and a download of what the one-call path left resident
+        fr, sr = np.zeros(len(subsets[::3])), np.zeros(len(subsets[::3]), dtype=np.int32)
+        multi.download_results(fr, sr)
+        assert (fr == fmb).all() and (sr == smb).all()
+        idx, off = _capi.to_csr(subsets)
+        multi.upload_population(idx, off)
+        multi.evaluate_resident()
+        fr, sr = np.zeros(len(subsets)), np.zeros(len(subsets), dtype=np.int32)
+        multi.download_results(fr, sr)
+        assert (fr == f1).all() and (sr == s1).all()
         fo, _ = oracle_lib.pls_evaluator(X, y, oracle_lib.make_seedvec(123), **kw).evaluate(subsets[20:28], threads=4)
         assert rel_err(fm[20:28], fo).max() <= REL_TOL
         assert multi.timing()["fit_ctas"] == one.timing()["fit_ctas"] or multi.timing()["fit_ctas"] > 0
