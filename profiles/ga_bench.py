@@ -61,3 +61,6 @@ print("  BatchedPopulation + B200 engine           : %8.2f s  (%7.1f evals/s)  e
 print("  BatchedPopulation, %2d virtual threads (engine warm, median of 3): %7.3f s (%.0f evals/s end to end)  engine calls %d, engine evaluations %d; same subsets as the %d-thread reference run: %s" %
       (cores, tgT, gT["engine_evaluations"] / tgT, gT["engine_calls"], gT["engine_evaluations"], cores, sameT))
 print("  same subsets as the 1-core reference run: %s, max rel fitness error %.2e" % (same, err))
+import hashlib
+print("  devices %s; digest of the selected subsets and their fitness (virtual-thread run): %s" % (os.environ.get("GASELECT_B200_DEVICES", "0"),
+      hashlib.sha1(repr(gT["subsets"]).encode() + np.asarray(gT["fitness"], dtype=np.float64).tobytes()).hexdigest()[:16]))
