@@ -48,6 +48,27 @@ __device__ __forceinline__ void cpAsyncCommitP() { asm volatile("cp.async.commit
 template <int N>
 __device__ __forceinline__ void cpAsyncWaitP() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// The products of one staged chunk for a warp that owns MI row tiles and NI column tiles (both known when the chunk loop
+// starts: as template arguments the loop body is loads and DMMAs only -- with the tile tests inside it every DMMA sat
+// behind its own predicate, branch and WARPSYNC, 19 other instructions per DMMA in the ncu source view)
+template <int MI, int NI>
+__device__ __forceinline__ void predSteps(double (&acc)[2][8][2], const double* __restrict__ ap, const double* __restrict__ bp,
+                                          int steps, int lda4, int aoff, int boff) {
+	for (int s = 0; s < steps; ++s) {
+		double a[MI], b[NI];
+#pragma unroll
+		for (int mi = 0; mi < MI; ++mi) a[mi] = ap[mi * aoff];
+#pragma unroll
+		for (int ni = 0; ni < NI; ++ni) b[ni] = bp[ni * boff];
+#pragma unroll
+		for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+			for (int ni = 0; ni < NI; ++ni) dmmaP(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+		ap += lda4;
+		bp += 4 * kPredLdb;
+	}
+}
+
 __global__ void __launch_bounds__(kPredThreads, 2) predictBlocksKernel(const PredictParams prm) {
 	extern __shared__ __align__(16) double psm[];
 	__shared__ uint32_t sel[kPredMaxK + 2];
@@ -89,6 +110,18 @@ __global__ void __launch_bounds__(kPredThreads, 2) predictBlocksKernel(const Pre
 		const int ncol = nt * A;
 		const int ntiles = (ncol + 7) >> 3;
 		for (int i = tid; i < 8 * kPredCols * 2; i += kPredThreads) (&red[0][0][0])[i] = 0.0;
+		// the coefficient columns this lane copies in every staged row: 16-byte pieces (columns 2 lane, 2 lane + 1: a row of
+		// a fit starts on an even offset when A is even) or two 8-byte pieces (columns lane, lane + 32)
+		const double* bsrc[2];
+		bool bval[2];
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			const int j = evenA ? 2 * lane : lane + 32 * q;
+			bval[q] = j < ncol && (evenA ? q == 0 : true);
+			const int t = bval[q] ? j / A : 0, a = bval[q] ? j - t * A : 0;
+			bsrc[q] = coefC + static_cast<size_t>(prm.ptasks[tb + t].fit) * fitStride + a;
+		}
+		const int nni = max(0, min(WM, (ntiles - wn + WN - 1) / WN)); // column tiles wn + ni WN < ntiles of this warp
 
 		for (int m0 = 0; m0 < bd.nrows; m0 += kPredRows) {
 			const int rows = min(kPredRows, bd.nrows - m0);
@@ -108,34 +141,28 @@ __global__ void __launch_bounds__(kPredThreads, 2) predictBlocksKernel(const Pre
 				const int nc = min(kPredKC, K2 - c0);
 				const int ncPad = (nc + 3) & ~3;
 				const int pieces = rowsLd >> 1;
-				for (int e = tid; e < ncPad * pieces; e += kPredThreads) {
-					const int cc = e / pieces, piece = e - cc * pieces;
+				// a warp per staged column (row of Bs), the lanes along it: no index arithmetic per piece
+				for (int cc = warp; cc < ncPad; cc += 8) {
 					// padding columns of the last chunk: the ones column (finite) against zero coefficient rows
 					const size_t col = sel[min(c0 + cc, K2 - 1)];
-					cpAsync16P(As + cc * kPredLda + 2 * piece, zb + col * bd.ld + m0 + 2 * piece);
-				}
-				if (evenA) { // 16-byte pieces: coefficient rows start on even offsets
-					const int half = ntiles * 4;
-					for (int e = tid; e < ncPad * half; e += kPredThreads) {
-						const int cc = e / half, j = 2 * (e - cc * half);
-						double* dst = Bs + cc * kPredLdb + j;
-						if (cc < nc && j < ncol) {
-							const int t = j / A, a = j - t * A;
-							cpAsync16P(dst, coefC + static_cast<size_t>(prm.ptasks[tb + t].fit) * fitStride + static_cast<size_t>(c0 + cc) * A + a);
-						} else {
-							dst[0] = 0.0;
-							dst[1] = 0.0;
+					const double* __restrict__ src = zb + col * bd.ld + m0;
+					double* __restrict__ dst = As + cc * kPredLda;
+					for (int piece = lane; piece < pieces; piece += 32) cpAsync16P(dst + 2 * piece, src + 2 * piece);
+					double* __restrict__ brow = Bs + cc * kPredLdb;
+					const size_t roff = static_cast<size_t>(c0 + cc) * A;
+					if (evenA) {
+						if (lane < ntiles * 4) {
+							if (cc < nc && bval[0]) cpAsync16P(brow + 2 * lane, bsrc[0] + roff);
+							else { brow[2 * lane] = 0.0; brow[2 * lane + 1] = 0.0; }
 						}
-					}
-				} else {
-					for (int e = tid; e < ncPad * (ntiles * 8); e += kPredThreads) {
-						const int cc = e / (ntiles * 8), j = e - cc * (ntiles * 8);
-						double* dst = Bs + cc * kPredLdb + j;
-						if (cc < nc && j < ncol) {
-							const int t = j / A, a = j - t * A;
-							cpAsync8P(dst, coefC + static_cast<size_t>(prm.ptasks[tb + t].fit) * fitStride + static_cast<size_t>(c0 + cc) * A + a);
-						} else {
-							*dst = 0.0;
+					} else {
+#pragma unroll
+						for (int q = 0; q < 2; ++q) {
+							const int j = lane + 32 * q;
+							if (j < ntiles * 8) {
+								if (cc < nc && bval[q]) cpAsync8P(brow + j, bsrc[q] + roff);
+								else brow[j] = 0.0;
+							}
 						}
 					}
 				}
@@ -156,32 +183,18 @@ __global__ void __launch_bounds__(kPredThreads, 2) predictBlocksKernel(const Pre
 				const double* __restrict__ Bs = As + kPredKC * kPredLda;
 				const int nc = min(kPredKC, K2 - chunk * kPredKC);
 				const int steps = (nc + 3) >> 2;
-				const double* __restrict__ ap = As + lcol * kPredLda + lrow;
-				const double* __restrict__ bp = Bs + lcol * kPredLdb + lrow;
-				for (int s = 0; s < steps; ++s) {
-					double a[2], b[8];
-#pragma unroll
-					for (int mi = 0; mi < 2; ++mi) {
-						const int mt = wm + mi * WM;
-						a[mi] = (mt < mtiles) ? ap[mt * 8] : 0.0;
-					}
-#pragma unroll
-					for (int ni = 0; ni < 8; ++ni) {
-						const int nt8 = wn + ni * WN;
-						if (ni < WM && nt8 < ntiles) b[ni] = bp[nt8 * 8];
-					}
-#pragma unroll
-					for (int mi = 0; mi < 2; ++mi) {
-						if (wm + mi * WM < mtiles) {
-#pragma unroll
-							for (int ni = 0; ni < 8; ++ni) {
-								if (ni < WM && wn + ni * WN < ntiles) dmmaP(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-							}
-						}
-					}
-					ap += 4 * kPredLda;
-					bp += 4 * kPredLdb;
+				const double* __restrict__ ap = As + lcol * kPredLda + lrow + wm * 8;
+				const double* __restrict__ bp = Bs + lcol * kPredLdb + lrow + wn * 8;
+				const int nmi = (wm < mtiles ? 1 : 0) + (wm + WM < mtiles ? 1 : 0);
+#define GSB_PRED_CASE(MI, NI) case (MI) * 16 + (NI): predSteps<MI, NI>(acc, ap, bp, steps, 4 * kPredLda, WM * 8, WN * 8); break;
+				switch (nmi * 16 + nni) {
+					GSB_PRED_CASE(1, 1) GSB_PRED_CASE(1, 2) GSB_PRED_CASE(1, 3) GSB_PRED_CASE(1, 4)
+					GSB_PRED_CASE(1, 5) GSB_PRED_CASE(1, 6) GSB_PRED_CASE(1, 7) GSB_PRED_CASE(1, 8)
+					GSB_PRED_CASE(2, 1) GSB_PRED_CASE(2, 2) GSB_PRED_CASE(2, 3) GSB_PRED_CASE(2, 4)
+					GSB_PRED_CASE(2, 5) GSB_PRED_CASE(2, 6) GSB_PRED_CASE(2, 7) GSB_PRED_CASE(2, 8)
+					default: break; // no tile of this chunk belongs to the warp
 				}
+#undef GSB_PRED_CASE
 				__syncthreads(); // this buffer is refilled two chunks on
 			}
 
