@@ -564,6 +564,12 @@ void buildUnitTables(gsb_engine* e) {
 	const int nfits = static_cast<int>(plan.fits.size());
 	const int units = 1 + static_cast<int>(e->unitBlocks.size());
 	const int upad = roundUp(units, 4);
+	if (gsb::gramPackSharedBytes(upad, nfits) > e->smemLimit || nfits > 65535) {
+		char buf[256];
+		std::snprintf(buf, sizeof(buf), "the per-fit kernel's pack stage holds the %d unit blocks and %d training sets of this segmentation in shared memory "
+		              "(%lld bytes, %d available): use fewer replications or segments", units - 1, nfits, gsb::gramPackSharedBytes(upad, nfits), e->smemLimit);
+		throw std::string(buf);
+	}
 	const size_t mDoubles = static_cast<size_t>(P2) * ldm;
 	const size_t triP = static_cast<size_t>(gsb::tri(static_cast<unsigned long long>(p)));
 	const double tableBytes = 8.0 * (static_cast<double>(triP) + 2.0 * p) * upad;

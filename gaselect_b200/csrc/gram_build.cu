@@ -285,7 +285,7 @@ __host__ __device__ inline int packTiles(int k) {
 	return pairs + 8 * m * (m - 1) + r * m;
 }
 
-__global__ void __launch_bounds__(kPackThreads) gramPackKernel(const PackParams prm) {
+__global__ void __launch_bounds__(kPackThreads, 4) gramPackKernel(const PackParams prm) {
 	extern __shared__ __align__(16) double psm[];
 	const int chrom = prm.bucket[blockIdx.y];
 	const uint32_t selBegin = prm.offsets[chrom];
@@ -301,40 +301,46 @@ __global__ void __launch_bounds__(kPackThreads) gramPackKernel(const PackParams 
 	constexpr int NC = kPackRows + kPackCols;  // its rows, then its columns
 	constexpr int NE = kPackRows * kPackCols;
 	double* __restrict__ tile = psm;                                          // [NE][ldt] unit runs of the entries (row-major over the tile)
-	PackFit* __restrict__ pfs = reinterpret_cast<PackFit*>(tile + NE * ldt);  // [nfits]
+	double* __restrict__ xr = tile + NE * ldt;                                // [2][nfits] nT x (mean of the tile's row 0 / row 1) per training set
+	PackFit* __restrict__ pfs = reinterpret_cast<PackFit*>(xr + 2 * prm.nfits); // [nfits]
 	uint32_t* __restrict__ cols = reinterpret_cast<uint32_t*>(pfs + prm.nfits); // [NC] global column ids
 
 	if (tid < NC) {
 		const int local = tid < kPackRows ? i0 + tid : j0 + (tid - kPackRows);
 		cols[tid] = prm.idx[selBegin + min(local, k - 1)];
 	}
-	for (int f = tid; f < prm.nfits; f += kPackThreads) pfs[f] = prm.pfits[f];
-	__syncthreads();
-
-	// ---- 1: the runs.  Entry e = row * 32 + column; valid when column <= row < k (lower triangle)
-	for (int e0 = warp * 4; e0 < NE; e0 += (kPackThreads / 32) * 4) {
-		const double* src[4];
-#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const int e = e0 + q;
-			const int i = i0 + e / kPackCols, j = j0 + (e % kPackCols);
-			src[q] = nullptr;
-			if (i < k && j <= i) {
-				// ascending column lists: sel[i] >= sel[j]
-				const unsigned long long gi = cols[e / kPackCols], gj = cols[kPackRows + (e % kPackCols)];
-				src[q] = prm.unitTab + (tri(gi) + gj) * upad;
-			}
-		}
-		for (int u = lane; u < upad; u += 32) {
-			double v[4];
-#pragma unroll
-			for (int q = 0; q < 4; ++q) v[q] = src[q] ? __ldg(src[q] + u) : 0.0;
-#pragma unroll
-			for (int q = 0; q < 4; ++q) tile[(e0 + q) * ldt + u] = v[q];
+	{
+		const int kp = (k + 1) & ~1;
+		const double* __restrict__ vec = prm.pvec + prm.vecOff[chrom];
+		const int i1c = min(i0 + 1, k - 1);
+		for (int f = tid; f < prm.nfits; f += kPackThreads) {
+			const PackFit pf = prm.pfits[f];
+			const double* __restrict__ xmf = vec + static_cast<size_t>(f) * 2 * kp + kp;
+			pfs[f] = pf;
+			xr[f] = pf.nT * __ldg(xmf + i0);
+			xr[prm.nfits + f] = pf.nT * __ldg(xmf + i1c);
 		}
 	}
 	__syncthreads();
 
+	// ---- 1: the runs.  Entry e = row * 32 + column; valid when column <= row < k (lower triangle).  8-byte cp.async
+	// straight into the tile (its leading dimension is odd): every piece of the CTA is in flight at once -- through
+	// registers, four runs per warp at a time, the kernel was latency-bound at 46 % of the HBM rate
+	for (int e = warp; e < NE; e += kPackThreads / 32) {
+		const int i = i0 + e / kPackCols, j = j0 + (e % kPackCols);
+		double* __restrict__ dst = tile + e * ldt;
+		if (i < k && j <= i) {
+			// ascending column lists: sel[i] >= sel[j]
+			const unsigned long long gi = cols[e / kPackCols], gj = cols[kPackRows + (e % kPackCols)];
+			const double* __restrict__ src = prm.unitTab + (tri(gi) + gj) * upad;
+			for (int u = lane; u < upad; u += 32) {
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst + u))), "l"(src + u));
+			}
+		} else {
+			for (int u = lane; u < upad; u += 32) dst[u] = 0.0;
+		}
+	}
+	asm volatile("cp.async.commit_group;\n" ::: "memory");
 	// ---- 2: a warp per training set; lane = column of the tile
 	const int kp = (k + 1) & ~1;
 	const size_t slab = static_cast<size_t>(packedDoubles(static_cast<unsigned long long>(k)));
@@ -345,32 +351,34 @@ __global__ void __launch_bounds__(kPackThreads) gramPackKernel(const PackParams 
 	const bool on0 = i0 < k && j <= i0, on1 = i0 + 1 < k && j <= i0 + 1;
 	const double* __restrict__ tr0 = tile + lane * ldt;
 	const double* __restrict__ tr1 = tile + (kPackCols + lane) * ldt;
-	const double full0 = tr0[0], full1 = tr1[0];
 	const size_t at0 = static_cast<size_t>(tri(static_cast<unsigned long long>(i0))) + j;
 	const size_t at1 = static_cast<size_t>(tri(static_cast<unsigned long long>(i0 + 1))) + j;
-	const int i1c = min(i0 + 1, k - 1);
-	constexpr int FU = 4; // training sets per iteration: their vector reads are in flight together
-	for (int f0 = warp; f0 < prm.nfits; f0 += FU * (kPackThreads / 32)) {
-		double xj[FU], xi0[FU], xi1[FU];
+	constexpr int FU = 8; // training sets per iteration: their vector reads are in flight together
+	double xj[FU];
+	auto loadVectors = [&](int f0) {
 #pragma unroll
 		for (int q = 0; q < FU; ++q) {
 			const int f = min(f0 + q * (kPackThreads / 32), prm.nfits - 1);
-			const double* __restrict__ xmf = vec + static_cast<size_t>(f) * 2 * kp + kp;
-			xj[q] = __ldg(xmf + jc);
-			xi0[q] = __ldg(xmf + i0);
-			xi1[q] = __ldg(xmf + i1c);
+			xj[q] = __ldg(vec + static_cast<size_t>(f) * 2 * kp + kp + jc);
 		}
+	};
+	loadVectors(warp); // in flight with the runs
+	asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+	__syncthreads();
+	const double full0 = tr0[0], full1 = tr1[0];
+	for (int f0 = warp; f0 < prm.nfits; f0 += FU * (kPackThreads / 32)) {
+		if (f0 != warp) loadVectors(f0);
 #pragma unroll
 		for (int q = 0; q < FU; ++q) {
 			const int f = f0 + q * (kPackThreads / 32);
 			if (f < prm.nfits) {
-				const PackFit pf = pfs[f];
+				const int u1 = pfs[f].u1, u2 = pfs[f].u2;
 				double* __restrict__ of = out + static_cast<size_t>(f) * slab;
 				double g0 = full0, g1 = full1;
-				if (pf.u1 >= 0) { g0 -= tr0[pf.u1]; g1 -= tr1[pf.u1]; }
-				if (pf.u2 >= 0) { g0 -= tr0[pf.u2]; g1 -= tr1[pf.u2]; }
-				g0 -= pf.nT * xi0[q] * xj[q];
-				g1 -= pf.nT * xi1[q] * xj[q];
+				if (u1 >= 0) { g0 -= tr0[u1]; g1 -= tr1[u1]; }
+				if (u2 >= 0) { g0 -= tr0[u2]; g1 -= tr1[u2]; }
+				g0 -= xr[f] * xj[q];
+				g1 -= xr[prm.nfits + f] * xj[q];
 				if (on0) of[at0] = g0;
 				if (on1) of[at1] = g1;
 			}
@@ -426,6 +434,16 @@ void launchUnitInterleave(const double* const* mUnits, int unitBegin, int unitCo
 	}
 }
 
+// dynamic shared memory of the two pack kernels (the larger one): the engine refuses a plan whose unit runs and training
+// sets outgrow it before any table is built
+long long gramPackSharedBytes(int upad, int nfits) {
+	const long long NC = kPackRows + kPackCols, NE = kPackRows * kPackCols;
+	const long long vbytes = 2LL * 32 * (upad + 1) * static_cast<long long>(sizeof(double));
+	const long long gbytes = (NE * (upad | 1) + 2LL * nfits) * static_cast<long long>(sizeof(double)) + static_cast<long long>(nfits) * static_cast<long long>(sizeof(PackFit)) +
+	                         NC * static_cast<long long>(sizeof(uint32_t)) + 16;
+	return vbytes > gbytes ? vbytes : gbytes;
+}
+
 // the vectors and then the packed Grams of every training set for the chromosomes of one launch (subsets <= kMax)
 cudaError_t launchGramPack(const PackParams& prm, int kMax, cudaStream_t stream) {
 	if (prm.bucketCount <= 0 || prm.nfits <= 0 || kMax <= 0) return cudaSuccess;
@@ -438,7 +456,7 @@ cudaError_t launchGramPack(const PackParams& prm, int kMax, cudaStream_t stream)
 	gramPackVectorsKernel<<<gv, kPackThreads, static_cast<size_t>(vbytes), stream>>>(prm);
 	const int ldg = prm.upad | 1;
 	const int NC = kPackRows + kPackCols, NE = kPackRows * kPackCols;
-	const int gbytes = NE * ldg * static_cast<int>(sizeof(double)) + prm.nfits * static_cast<int>(sizeof(PackFit)) +
+	const int gbytes = (NE * ldg + 2 * prm.nfits) * static_cast<int>(sizeof(double)) + prm.nfits * static_cast<int>(sizeof(PackFit)) +
 	                   NC * static_cast<int>(sizeof(uint32_t)) + 16;
 	err = cudaFuncSetAttribute(gramPackKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gbytes);
 	if (err != cudaSuccess) return err;

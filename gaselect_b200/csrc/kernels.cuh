@@ -375,6 +375,7 @@ void launchGramCombine(const double* mFull, const double* const* mBlocks, const 
 void launchUnitInterleave(const double* const* mUnits, int unitBegin, int unitCount, int p, int ldm, int upad, double* unitTab,
                           double* unitSum, double* unitXy, cudaStream_t stream);
 cudaError_t launchGramPack(const PackParams& prm, int kMax, cudaStream_t stream);
+long long gramPackSharedBytes(int upad, int nfits);
 void launchBlockGather(const double* z, int ldz, int ncols, const uint32_t* cols, const uint32_t* rows, int nrows,
                        double* dst, int ld, cudaStream_t stream);
 unsigned long long fitKernelScratchPerCta(int kMax, int A, int maxTasks, int maxBlockLd, int smemLimit);

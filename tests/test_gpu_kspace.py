@@ -250,3 +250,24 @@ def test_tables_that_do_not_fit_leave_everything_to_the_kernel_space_kernel(engi
             assert ev.info()["gram_bytes"] == 0               # no tables were built
             assert ev.timing()["kernel_launches"] == 2        # one K1k launch + K2
     assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL
+
+
+def test_segmentations_beyond_the_pack_stage(engine, oracle_lib):
+    """120 replications of 4 x 3-fold CV: 1 + 120 x (4 + 12) unit blocks, more than the pack stage of the per-fit kernel
+    holds in shared memory.  With n <= 160 the kernel-space kernel takes every subset size (it needs no tables); where no
+    other kernel can serve the plan (n = 200) the engine says so instead of failing inside a launch."""
+    from gaselect_b200 import evaluators as E, _capi
+    sv = oracle_lib.make_seedvec(11)
+    kw = dict(numReplications=120, maxNComp=5, innerSegments=3, outerSegments=4)
+    X, y = synth.nir_spectra(60, 300, seed=21)
+    subsets = synth.random_subsets(300, 10, 2, 40, seed=3) + synth.random_subsets(300, 6, 41, 120, seed=4)
+    want, wstatus = oracle_lib.pls_evaluator(X, y, sv, **kw).evaluate(subsets, threads=8)
+    with forced(GSB_NO_KSPACE=None, GSB_KSPACE_MINK=None, GSB_KSPACE_SPLIT=None):
+        with E.PLSEvaluator(X, y, sv, **kw) as ev:
+            fit, status = ev.evaluate_population(subsets)
+            assert ev.info()["gram_bytes"] == 0
+        assert (status == wstatus).all() and rel_err(fit, want).max() <= REL_TOL
+        X2, y2 = synth.nir_spectra(200, 300, seed=22)
+        with E.PLSEvaluator(X2, y2, sv, **kw) as ev:
+            with pytest.raises(_capi.EngineError, match="pack stage"):
+                ev.evaluate_population(subsets[:4])
