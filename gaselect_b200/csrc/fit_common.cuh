@@ -62,18 +62,19 @@ __device__ __forceinline__ double warpSum16(double (&v)[16], int lane) {
 }
 
 // CTA-wide totals of NV <= 16 values; every thread receives all of them, bitwise identical.
-template <int NV>
+// STRIDE: doubles per warp of one of the two phases of `red` (a kernel that also uses wider reductions passes theirs)
+template <int NV, int STRIDE = 16>
 __device__ __forceinline__ void blockSum16(double (&x)[NV], double* red, int& phase, int nw, int lane, int warp) {
 	double v[16];
 #pragma unroll
 	for (int i = 0; i < 16; ++i) v[i] = (i < NV) ? x[i] : 0.0;
 	double tot = warpSum16(v, lane);
 	if (nw > 1) {
-		double* buf = red + phase * (nw * 16);
-		if ((lane & 1) == 0) buf[warp * 16 + (lane >> 1)] = tot;
+		double* buf = red + phase * (nw * STRIDE);
+		if ((lane & 1) == 0) buf[warp * STRIDE + (lane >> 1)] = tot;
 		__syncthreads();
 		tot = buf[lane & 15];
-		for (int w = 1; w < nw; ++w) tot += buf[w * 16 + (lane & 15)];
+		for (int w = 1; w < nw; ++w) tot += buf[w * STRIDE + (lane & 15)];
 		phase ^= 1;
 #pragma unroll
 		for (int i = 0; i < NV; ++i) x[i] = __shfl_sync(0xffffffffu, tot, i);

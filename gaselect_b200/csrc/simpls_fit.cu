@@ -45,7 +45,7 @@ namespace gsb {
 namespace {
 
 constexpr int kChunk = 10;  // components per prediction pass (accumulators held in registers)
-constexpr int kDots = 6;    // loadings projected in the same reduction round as S'w and s0'S
+constexpr int kDots = 14;   // loadings projected in the same reduction round as S'w and s0'S (16 values: one blockSum16)
 constexpr int kRedMax = 20; // widest reduction (values per thread)
 constexpr int kMaxWarps = 13; // 416 threads: subsets up to k = 416 on the spill path
 
@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 				w[u] = a0;
 			}
 		}
-		// round 1: tn^2 = S'GS = ||Xc S||^2 (:138), q*tn = s0'S (:148), projections V_j'w
+		// round 1: tn^2 = S'GS = ||Xc S||^2 (:138), q*tn = s0'S (:148), projections V_j'w on the first kDots stored
+		// loadings -- 16 values, one butterfly in which the lanes halve the value set at every step
 		double r1[2 + kDots];
 #pragma unroll
 		for (int i = 0; i < 2 + kDots; ++i) r1[i] = 0.0;
@@ -237,13 +238,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 				}
 			}
 		}
-		blockSum<2 + kDots>(r1, red, phase, NW);
+		blockSum16<2 + kDots, kRedMax>(r1, red, phase, NW, lane, warp);
 		if (!(r1[0] >= 1e-50)) { // ||t|| < 1e-25 (NORM_TOL, :16,:141-143); also catches NaN / negative rounding
 			done = comp;
 			break;
 		}
-		const double tn = sqrt(r1[0]);
-		const double q = r1[1] / tn;
+		const double rtn = rsqrt(r1[0]); // 1/tn: no division, no square root (as in the fast kernel)
+		const double q = r1[1] * rtn;
 		double v[RPT];
 #pragma unroll
 		for (int u = 0; u < RPT; ++u) v[u] = w[u];
@@ -254,20 +255,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 				for (int u = 0; u < RPT; ++u) v[u] = fma(-V[j * k + row[u]], r1[2 + j], v[u]);
 			}
 		}
-		// more than kDots stored loadings (unconstrained component counts): further rounds of 8
-		for (int j0 = kDots; j0 < comp; j0 += 8) {
-			double d[8];
+		// more than kDots stored loadings (unconstrained component counts): further rounds of 16
+		for (int j0 = kDots; j0 < comp; j0 += 16) {
+			double d[16];
 #pragma unroll
-			for (int j = 0; j < 8; ++j) {
+			for (int j = 0; j < 16; ++j) {
 				d[j] = 0.0;
 				if (j0 + j < comp) {
 #pragma unroll
 					for (int u = 0; u < RPT; ++u) if (valid[u]) d[j] = fma(V[(j0 + j) * k + row[u]], w[u], d[j]);
 				}
 			}
-			blockSum<8>(d, red, phase, NW);
+			blockSum16<16, kRedMax>(d, red, phase, NW, lane, warp);
 #pragma unroll
-			for (int j = 0; j < 8; ++j) {
+			for (int j = 0; j < 16; ++j) {
 				if (j0 + j < comp) {
 #pragma unroll
 					for (int u = 0; u < RPT; ++u) v[u] = fma(-V[(j0 + j) * k + row[u]], d[j], v[u]);
@@ -275,8 +276,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 			}
 		}
 		// cumulative coefficients from S BEFORE deflation (:152-156); v = X't has the factor 1/tn (:145-147)
-		const double f = q / tn;
-		const double rtn = 1.0 / tn;
+		const double f = q * rtn;
 		double r2[2] = {0.0, 0.0};
 #pragma unroll
 		for (int u = 0; u < RPT; ++u) {
@@ -289,9 +289,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 			}
 		}
 		// round 2: deflate S, normalise v (:160, :70-88)
-		blockSum<2>(r2, red, phase, NW);
-		const double dd = r2[1] / r2[0];
-		const double rvn = 1.0 / sqrt(r2[0]);
+		blockSum16<2, kRedMax>(r2, red, phase, NW, lane, warp);
+		const double rvn = rsqrt(r2[0]);
+		const double dd = (r2[1] * rvn) * rvn;
 #pragma unroll
 		for (int u = 0; u < RPT; ++u) {
 			if (valid[u]) {
