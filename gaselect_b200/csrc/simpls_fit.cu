@@ -88,16 +88,25 @@ __host__ __device__ inline int stageMin(int k, int nw) { return nw * 32 * kChunk
 // vGlobal: the stored loadings V (A x k) and the cumulative coefficients (k x Apad) live in a global scratch (one region
 // per CTA of the launch, L2-resident while it runs) instead of shared memory: unconstrained component counts on wide
 // subsets (evaluatorPLS defaults on spectra: A = min(k, n_tr - 1) ~ 100 components of 200 columns = 320 KB)
+// The staging area of the held-out rows (after the fit) is the packed Gram AND the stored loadings behind it: both are
+// dead by then (with only the Gram area, a 30-column subset with 30 components took 26 KB per fit for 10 KB of staging
+// tiles: 8 single-warp CTAs per SM; now 11).
+__host__ __device__ inline int stageCapOf(int k, int A, bool gramInSmem, int nw, bool vGlobal) {
+	const int sizeP = gramInSmem ? roundUp(k * (k + 1) / 2, 2) : 0;
+	const int sizeV = vGlobal ? 0 : roundUp(A * k, 2);
+	return roundUp(max(sizeP + sizeV, stageMin(k, nw)), 2);
+}
 __host__ __device__ inline Carve carve(int k, int A, bool gramInSmem, int nw, bool vGlobal = false) {
 	Carve c;
 	const int Apad = roundUp(A, kChunk);
 	int o = 0;
-	// packed Gram; afterwards the staging area of the held-out rows (>= one 32-row column per warp)
-	c.P = o; o += gramInSmem ? roundUp(max(k * (k + 1) / 2, stageMin(k, nw)), 2) : stageMin(k, nw);
+	// packed Gram, then the stored loadings; afterwards the staging area of the held-out rows (>= one 32-row column per warp)
+	c.P = o;
+	c.V = o + (gramInSmem ? roundUp(k * (k + 1) / 2, 2) : 0);
+	o += stageCapOf(k, A, gramInSmem, nw, vGlobal);
 	c.S = o; o += roundUp(k, 2);
 	c.s0 = o; o += roundUp(k, 2);
 	c.xm = o; o += roundUp(k, 2);
-	c.V = o; o += vGlobal ? 0 : roundUp(A * k, 2);
 	c.coef = o; o += vGlobal ? 0 : k * Apad;
 	c.b0 = o; o += Apad;
 	c.red = o; o += 2 * nw * kRedMax;  // double-buffered
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 	// ---- held-out prediction and statistics -------------------------------------------------
 	// The Gram area is dead now: it stages [column pass][32-row slab] tiles of the held-out block
 	// (16-byte cp.async, everything in flight at once) and, at its end, the warps' partial sums.
-	const int stageCap = GSMEM ? max(k * (k + 1) / 2, stageMin(k, NW)) : stageMin(k, NW);
+	const int stageCap = stageCapOf(k, A, GSMEM, NW, VGLOB);
 	double* __restrict__ part = P + stageCap - NW * 32 * kChunk; // [warp][u][lane]
 	const int colsPerPass = max(1, min(k, (stageCap - NW * 32 * kChunk) / 32));
 	for (int t = 0; t < fd.taskCount; ++t) {
