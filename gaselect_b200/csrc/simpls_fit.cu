@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) simplsFitKernel(const FitParam
 			}
 		}
 		// round 2: deflate S, normalise v (:160, :70-88)
-		blockSum16<2, kRedMax>(r2, red, phase, NW, lane, warp);
+		blockSum2<kRedMax>(r2, red, phase, NW, lane, warp);
 		const double rvn = rsqrt(r2[0]);
 		const double dd = (r2[1] * rvn) * rvn;
 #pragma unroll
@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(SPILL ? kMaxWarps * 32 : 256, SPILL ? 1 : 2) s
 		double r2[2];
 		r2[0] = valid ? v * v : 0.0;
 		r2[1] = valid ? v * sOwn : 0.0;
-		blockSum16<2>(r2, red, phase, NW, lane, warp); // second round: deflate S, normalise v (:160, :70-88)
+		blockSum2<16>(r2, red, phase, NW, lane, warp); // second round: deflate S, normalise v (:160, :70-88)
 		const double rvn = rsqrt(r2[0]);
 		const double dd = (r2[1] * rvn) * rvn;
 		sOwn = fma(-v, dd, sOwn);
