@@ -10,6 +10,7 @@
 // with and without duplicate elimination, for one and for several (virtual) threads.
 #include <RcppArmadillo.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -152,15 +153,20 @@ int main(int argc, char** argv) {
 	const bool batched = std::string(argv[1]) == "batched";
 	const double threshold = std::atof(argv[2]);
 	const int dup = std::atoi(argv[3]), nthreads = std::atoi(argv[4]);
-	const int p = 200, n = 40;
+	// GA_HOST_SCALE="P POP GENS MINV MAXV ELITE" (profiling aid: the host side alone at another scale, e.g. config 3's
+	// "1000 500 50 10 200 10"); prints the wall time of run() on stderr
+	int p = 200, popSize = 60, gens = 12, elite = 6, minV = 3, maxV = 25;
+	if (const char* sc = std::getenv("GA_HOST_SCALE")) std::sscanf(sc, "%d %d %d %d %d %d", &p, &popSize, &gens, &minV, &maxV, &elite);
+	const int n = 40;
 	arma::mat X(n, p);
 	arma::vec y(n);
 	for (int i = 0; i < n; ++i) { y[i] = i; for (int j = 0; j < p; ++j) X(i, j) = (i * 31 + j * 17) % 101; }
 	std::vector<uint32_t> seed(624);
 	for (int i = 0; i < 624; ++i) seed[i] = 2654435761u * static_cast<uint32_t>(i + 1) + 12345u;
-	Control ctrl(p, 60, 12, 6, 3, 25, 0.05, nthreads, dup, threshold, 1e-6, 0, static_cast<CrossoverType>(0), static_cast<FitnessScaling>(0), OFF);
+	Control ctrl(p, popSize, gens, elite, minV, maxV, 0.05, nthreads, dup, threshold, 1e-6, 0, static_cast<CrossoverType>(0), static_cast<FitnessScaling>(0), OFF);
 	Outcome o;
 	unsigned long long calls = 0, evals = 0, passes = 0, confirmed = 0, flagged = 0;
+	const auto t0 = std::chrono::steady_clock::now();
 	if (batched) {
 		std::unique_ptr<GpuEvaluator> gpu(GpuEvaluator::makePLS(X, y, 2, 5, seed, OFF, 3));
 		BatchedPopulation pop(ctrl, *gpu, seed);
@@ -172,6 +178,9 @@ int main(int argc, char** argv) {
 		HashEvaluator hash;
 		if (nthreads > 1) { MultiThreadedPopulation pop(ctrl, hash, seed); pop.run(); o = collect(pop); }
 		else { SingleThreadPopulation pop(ctrl, hash, seed); pop.run(); o = collect(pop); }
+	}
+	if (std::getenv("GA_HOST_SCALE")) {
+		std::fprintf(stderr, "run + collect: %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 	}
 	// FNV-1a over the exact bits of the outcome
 	uint64_t h = 1469598103934665603ull;
