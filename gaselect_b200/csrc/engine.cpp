@@ -250,9 +250,9 @@ struct gsb_engine {
 	bool callerStream = false;
 	// K1 launches of different subset-size classes run concurrently: CTAs of small subsets fill the
 	// shared memory / issue slots that the one or two resident CTAs of a large subset leave idle
-	static constexpr int kSideStreams = 4;
-	cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
-	cudaEvent_t evFork = nullptr, evJoin[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
+	static constexpr int kSideStreams = 8;
+	cudaStream_t side[kSideStreams] = {};
+	cudaEvent_t evFork = nullptr, evJoin[kSideStreams] = {};
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int smCount = 0, smemLimit = 0;
 	int ldz = 0;
